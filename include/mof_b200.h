@@ -1,0 +1,211 @@
+/*
+ * mof_b200.h -- C ABI of libmof_b200.so: the per-frame velocity-field solve of
+ * SEU-dynamical-models/Manifold-based-optical-flow-method on NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI (it is pure Python); each entry
+ * point below names the reference function (file:line under /root/reference) whose
+ * arithmetic it replaces.  The Python package manifold_based_optical_flow_method_b200
+ * binds these symbols with ctypes and re-exposes the reference's own signatures
+ * (utils/compute_optical_flow.py, utils/find_singularity_point.py); INTEGRATION.md
+ * shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every array argument is a raw pointer + sizes.
+ *   - "host" pointers are ordinary CPU memory, "device" pointers are CUDA global
+ *     memory of the current device.  `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  Kernels are asynchronous on that stream
+ *     unless stated.
+ *   - return value: 0 = OK, <0 = CUDA/runtime/argument error (text available from
+ *     mof_last_error_string()), >0 = numerical status (see each function).
+ *   - fp64 arithmetic, int32 indices.  The library keeps no global state besides a
+ *     thread-local error string and a per-call ticket buffer inside the batch.
+ *
+ * Internal data layout
+ *   - vertices are renumbered (breadth-first / Cuthill-McKee) for gather locality:
+ *     internal vertex v  <->  reference vertex perm[v].
+ *   - the 2N x 2N system matrix (row index i + N*alpha, compute_optical_flow.py:83)
+ *     is stored as 2x2 blocks over the vertex-adjacency pattern: block b of row v
+ *     couples internal vertices (v, col[b]); n_blocks = N + 2E.
+ *   - frames are processed in groups of MOF_GROUP (=32) frames; every per-frame
+ *     quantity is stored frame-minor: value[group][slot][MOF_GROUP], so a warp
+ *     (lane = frame) reads/writes 256 contiguous bytes.
+ */
+#ifndef MOF_B200_H
+#define MOF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOF_GROUP 32          /* frames per group (= one warp, lane = frame)      */
+#define MOF_TILE_ROWS 64      /* block rows per CTA tile in the SpMV/PCG kernels  */
+
+/* numerical status per frame, written by mof_pcg_solve_batch */
+#define MOF_STATUS_CONVERGED 0
+#define MOF_STATUS_MAXITER 1      /* relres > tol after max_iter iterations        */
+#define MOF_STATUS_BREAKDOWN 2    /* p'Ap <= 0 or NaN/Inf met (e.g. NaN input)      */
+#define MOF_STATUS_ZERO_RHS 3     /* f == 0: V = 0 returned without iterating       */
+
+const char* mof_last_error_string(void);
+int mof_version(void);
+
+/* ------------------------------------------------------------------------- *
+ * Sparsity pattern (host, once per mesh).
+ * Replaces the implicit pattern that lil_matrix element updates create in
+ * compute_geometrical_quantities (compute_optical_flow.py:49,78-93) and worker
+ * (:106,127-141).
+ * ------------------------------------------------------------------------- */
+typedef struct mof_pattern mof_pattern;     /* opaque host object */
+
+/* triangles: host (n_faces,3) int64 vertex ids of the reference mesh.
+ * reorder: 1 = Cuthill-McKee renumbering, 0 = identity (tests).
+ * Errors: vertex id out of range, a face with a repeated vertex. */
+int mof_pattern_create(int64_t n_vertices, int64_t n_faces, const int64_t* triangles,
+                       int reorder, mof_pattern** out);
+void mof_pattern_destroy(mof_pattern* p);
+int64_t mof_pattern_num_blocks(const mof_pattern* p);    /* N + 2E                         */
+int64_t mof_pattern_num_contrib(const mof_pattern* p);   /* 9 F (ordered vertex pairs)      */
+int64_t mof_pattern_max_row_blocks(const mof_pattern* p);
+int64_t mof_pattern_bandwidth(const mof_pattern* p);     /* max |v - col| after renumbering */
+/* Copy the pattern into caller-allocated host arrays:
+ *   perm   [N]      internal -> reference vertex id
+ *   rowptr [N+1]    block-row pointers
+ *   col    [nb]     internal column vertex of each block, ascending inside a row
+ *   diag   [N]      index of the diagonal block of each row
+ *   cptr   [nb+1]   per-block list of contributing faces ...
+ *   centry [9F]     ... packed (face << 4 | m << 2 | n): face contributes its local
+ *                   pair (m,n) (positions of the row/col vertex inside the face) to
+ *                   that block; faces ascending, i.e. the reference's accumulation
+ *                   order (compute_optical_flow.py:60,113)
+ *   tri    [F*3]    triangles in internal vertex ids (face order unchanged)        */
+int mof_pattern_export(const mof_pattern* p, int32_t* perm, int32_t* rowptr, int32_t* col,
+                       int32_t* diag, int32_t* cptr, int32_t* centry, int32_t* tri);
+
+/* ------------------------------------------------------------------------- *
+ * Device-side descriptors (all pointers are device pointers).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n_vertices, n_faces, n_blocks, n_contrib;
+    const int32_t *perm, *rowptr, *col, *diag, *cptr, *centry, *tri;
+    const double* e;         /* (N,2,3)  tangent basis, internal vertex order           */
+    const double* grad_w;    /* (F,3,3)                                                 */
+    const double* integral;  /* (F,2)    A/6, A/12                                      */
+    const double* areas;     /* (F,)                                                    */
+    const double* a2v;       /* (nb,4)   a2 block values [2*alpha+beta], frame-shared   */
+} mof_mesh_dev;
+
+typedef struct {
+    int32_t n_groups;        /* G                                                       */
+    int32_t n_frames;        /* valid frames (<= G*MOF_GROUP); the rest is zero padding  */
+    double* It;              /* [G][N][32]       I(t_k) per vertex                      */
+    double* dIt;             /* [G][N][32]       (I(t_k+1) - I(t_k)) / dt               */
+    double* vals;            /* [G][nb][4][32]   a1 + lambda*a2 block values            */
+    double* rhs;             /* [G][N][2][32]    f                                      */
+    double* minv;            /* [G][N][3][32]    inverse of the diagonal 2x2 blocks     */
+    double* x;               /* [G][N][2][32]    solution (tangent coefficients)        */
+    double* r;               /* [G][N][2][32]                                           */
+    double* z;               /* [G][N][2][32]                                           */
+    double* p;               /* [G][N][2][32]                                           */
+    double* ap;              /* [G][N][2][32]                                           */
+    double* partial;         /* [G][n_tiles][2][32] per-tile partial dot products       */
+    double* scal;            /* [G][8][32]  rz, pAp, rr, bb, alpha, beta, relres_true, spare */
+    int32_t* state;          /* [G][4][32]  active, iters, status, spare ; then [G] group_done, [G] tickets, [1] groups_active */
+} mof_batch_dev;
+
+int64_t mof_num_tiles(int64_t n_vertices);                      /* ceil(N / MOF_TILE_ROWS) */
+int64_t mof_state_ints(int32_t n_groups);                       /* size of `state` in int32 */
+
+/* ------------------------------------------------------------------------- *
+ * K0: geometry, once per mesh (compute_geometrical_quantities,
+ * compute_optical_flow.py:27-97).
+ * ------------------------------------------------------------------------- */
+/* e[v] from normals[v] (compute_orthonormal_basis, :210-235); internal order in/out. */
+int mof_geom_basis(int64_t n_vertices, const double* normals, double* e, void* stream);
+/* grad_w (compute_gradient_w, :238-255, argument orders of :63-68) and
+ * integral_wi_wj (:73-75) per face; coords (N,3) internal order, tri internal ids. */
+int mof_geom_gradw(int64_t n_faces, const double* coords, const int32_t* tri,
+                   const double* areas, double* grad_w, double* integral, void* stream);
+/* a2 block values (compute_a2 :258-270 accumulated per :78-93) into mesh->a2v
+ * (cast away const); uses mesh->e, grad_w, areas and the contributor lists. */
+int mof_geom_a2(const mof_mesh_dev* mesh, double* a2v, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K1: per-frame assembly for a batch (worker face loop, :113-141, and a = a1 +
+ * lambda_*a2, :144).
+ * ------------------------------------------------------------------------- */
+/* Transpose/renumber frames into the frame-minor layout.  I_now/I_next: device,
+ * row k = frame k of this batch, row stride ld (elements), reference vertex order.
+ * Frame k uses I_now[k] for the gradient and as the old value and I_next[k] as the
+ * new value (:174-175); dt[k] = t_k[k+1]-t_k[k] (:125), device (n_frames,). */
+int mof_pack_frames(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const double* I_now,
+                    const double* I_next, int64_t ld, const double* dt, void* stream);
+/* vals = a1(I) + lambda*a2, rhs = f, minv = inverse diagonal blocks. */
+int mof_assemble_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double lambda_,
+                       void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2/K3: batched block-Jacobi PCG (replaces spsolve, :147).
+ * ------------------------------------------------------------------------- */
+/* y = A x for every group of the batch (x, y in the [G][N][2][32] layout).  Test and
+ * roofline hook for the SpMV kernel that the solver uses. */
+int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const double* x,
+                   double* y, void* stream);
+/* Solve A x = rhs for all frames of the batch, x0 = 0, until ||r||/||b|| <= tol
+ * (recurrence residual, confirmed on the true residual b - A x; at most
+ * max_restarts restarts from the true residual).  Synchronous: returns after the
+ * stream has drained.  Host outputs (each MOF_GROUP*n_groups long, may be NULL):
+ * iters, relres (true residual), status (MOF_STATUS_*).  Return value: 0 if every
+ * valid frame converged (or had a zero rhs), else the largest status met. */
+int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double tol,
+                        int32_t max_iter, int32_t check_every, int32_t max_restarts,
+                        int32_t* iters, double* relres, int32_t* status, void* stream);
+/* x -> V[k][i + N*alpha] (reference order and layout, :149); V: device, row stride ld. */
+int mof_unpack_solution(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double* V,
+                        int64_t ld, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4: tangent coefficients -> xyz (process_V_k, find_singularity_point.py:28-69),
+ * speed |V| (S3_compute_v_and_detection_singularity.py:130-132) and per-frame
+ * v_length_max (find_singularity_point.py:161-162).
+ * V (n_frames, 2N) row stride ldV; e (N,2,3) REFERENCE vertex order;
+ * Vxyz (n_frames,N,3); speed (n_frames,N) or NULL; vmax (n_frames,) or NULL.
+ * ------------------------------------------------------------------------- */
+int mof_tangent_to_xyz(int64_t n_vertices, int64_t n_frames, const double* V, int64_t ldV,
+                       const double* e, double* Vxyz, double* speed, double* vmax, void* stream);
+/* vmax only, from an existing (n_frames,N,3) field. */
+int mof_vmax(int64_t n_vertices, int64_t n_frames, const double* Vxyz, double* vmax, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K5: singularity detection (find_singularity_points,
+ * find_singularity_point.py:140-189).  Two calls with an exact-size allocation by
+ * the caller in between.
+ * ------------------------------------------------------------------------- */
+#define MOF_DETECT_CHUNK 1024
+/* Pass 1: vflag[k][i] = ||V_i/vmax|| <= eps (:72-90,:165-167); fflag[k][t] = face t
+ * holds an interior zero (:93-137,:170-180) and has no singular vertex (:171).
+ * Also writes per-chunk counts: vcnt [n_frames][ceil(N/1024)], fcnt
+ * [n_frames][ceil(F/1024)] and their per-frame exclusive scans in place (so that
+ * on return vcnt/fcnt hold chunk offsets) and totals[k] = {n_vertices_k, n_faces_k}.
+ * coords (N,3), tri (F,3) int32: REFERENCE vertex ids. */
+int mof_singularity_flags(int64_t n_vertices, int64_t n_faces, int64_t n_frames,
+                          const double* coords, const int32_t* tri, const double* Vxyz,
+                          const double* vmax, double eps, uint8_t* vflag, uint8_t* fflag,
+                          int32_t* vcnt, int32_t* fcnt, int32_t* totals, void* stream);
+/* Pass 2: ordered compaction.  voff/foff (n_frames,) int64: start of frame k inside
+ * the output lists (exclusive scan of totals, computed by the caller).
+ * Outputs: vertex_idx [sum nv]; face_idx [sum nf]; lam_mu [sum nf][2];
+ * P [sum nf][3] (:181-182); index [sum nf] int8 per-face Poincare index (+1/-1). */
+int mof_singularity_compact(int64_t n_vertices, int64_t n_faces, int64_t n_frames,
+                            const double* coords, const int32_t* tri, const double* Vxyz,
+                            const double* vmax, const uint8_t* vflag, const uint8_t* fflag,
+                            const int32_t* vcnt, const int32_t* fcnt, const int64_t* voff,
+                            const int64_t* foff, int32_t* vertex_idx, int32_t* face_idx,
+                            double* lam_mu, double* P, int8_t* index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOF_B200_H */

@@ -1,0 +1,172 @@
+"""Drop-in for the reference's ``utils/compute_optical_flow.py`` (hot-path functions).
+
+Same function names and positional signatures as the reference:
+
+    compute_geometrical_quantities(coordinates, normals, triangles, areas)
+        -> (a2, grad_w, e, integral_wi_wj, execution_time)            # reference :27-97
+    compute_velocity_field(processes_num, time_steps, a2, grad_w, e, integral_wi_wj,
+                           triangles, t_k, areas, lambda_, I_k, I_k_2)
+        -> (V_k, execution_time)                                       # reference :152-194
+    worker(k, a2, grad_w, e, integral_wi_wj, triangles, t_k, areas, lambda_, I_k_k, I_k_kplus1)
+        -> V                                                           # reference :100-149
+    reshape_and_save_data(data, file_path)                             # reference :314-320
+
+Differences a caller can observe (all documented in INTEGRATION.md):
+  * ``a2`` is a ``MeshOperator`` handle (device-resident geometry + a2 block values) rather
+    than a scipy lil_matrix; ``a2.tocsr()`` gives the reference's matrix.
+  * ``processes_num`` (the reference's Pool size) is ignored: frames are batched on the
+    GPU of this process; under torchrun (torch.distributed initialised) they are also
+    sharded across ranks and gathered with NCCL (see distributed.py).
+  * the linear systems are solved by block-Jacobi PCG to ||b-Ax||/||b|| <= 1e-12 instead
+    of SuperLU; frames that fail to converge raise ``UnconvergedError`` (the reference
+    would return NaNs with a MatrixRankWarning) unless ``allow_unconverged`` is set.
+  * float32 mesh arrays are promoted to float64 (the reference computes grad_w in
+    float32 when pyvista hands it float32 points).
+There is no CPU fallback: without a CUDA device / the compiled library these functions raise.
+"""
+import time
+
+import numpy as np
+
+from . import _lib
+from .mesh import MeshOperator
+from .solver import (DEFAULT_MAX_ITER, DEFAULT_TOL, SolveInfo, UnconvergedError, VelocitySolver, frame_dt)
+
+# solver settings (module-level so the reference's positional signatures stay untouched)
+settings = {
+    "tol": DEFAULT_TOL,
+    "max_iter": DEFAULT_MAX_ITER,
+    "batch_groups": None,          # None = sized from free device memory (<= 8 groups of 32 frames)
+    "allow_unconverged": False,
+    "device": None,                # None = current CUDA device
+}
+
+last_solve_info = None             # SolveInfo of the most recent compute_velocity_field / worker call
+_solvers = {}
+
+
+def compute_geometrical_quantities(coordinates, normals, triangles, areas):
+    """Reference :27-97.  -> (a2 handle, grad_w (F,3,3), e (N,2,3), integral_wi_wj (F,2), seconds)"""
+    start = time.time()
+    op = MeshOperator(coordinates, normals, triangles, areas, device=settings["device"])
+    execution_time = time.time() - start
+    return op, op.grad_w, op.e, op.integral_wi_wj, execution_time
+
+
+def _operator(a2, triangles):
+    if isinstance(a2, MeshOperator):
+        return a2
+    raise TypeError(
+        "a2 must be the handle returned by this module's compute_geometrical_quantities (a MeshOperator); "
+        "to reuse a matrix computed by the reference build one with MeshOperator.from_reference_a2(...)")
+
+
+def _solver(op):
+    key = id(op)
+    s = _solvers.get(key)
+    if s is None or s.op is not op:
+        _solvers.clear()           # one mesh at a time keeps device memory bounded
+        s = _solvers[key] = VelocitySolver(op, batch_groups=settings["batch_groups"])
+    s.tol, s.max_iter = settings["tol"], settings["max_iter"]
+    return s
+
+
+def _check_converged(info, first_frame=0):
+    bad = np.nonzero((info.status != _lib.STATUS_CONVERGED) & (info.status != _lib.STATUS_ZERO_RHS))[0]
+    if len(bad) and not settings["allow_unconverged"]:
+        raise UnconvergedError(info, [int(b) + first_frame for b in bad])
+
+
+def _upload_signals(op, I_k, I_k_2, n, first=0):
+    """Rows first .. first+n of the (T,N) signals -> device float64 tensors whose row 0 is
+    frame ``first``.  Frame k reads I_k[k] and I_k_2[k+1] (:174-175)."""
+    torch = _lib.require_cuda()
+    N = op.n_vertices
+
+    def rows(a, lo, hi, name):
+        if isinstance(a, (list, tuple)):
+            a = np.asarray(a[lo:hi], dtype=np.float64)
+            lo, hi = 0, len(a)
+        a = np.asarray(a)
+        if a.ndim != 2 or a.shape[1] != N or a.shape[0] < hi:
+            raise ValueError(f"{name} must have shape (>= {hi}, {N}), got {a.shape}")
+        return torch.from_numpy(np.ascontiguousarray(a[lo:hi], dtype=np.float64)).to(op.device)
+
+    if I_k_2 is I_k:
+        I_dev = rows(I_k, first, first + n + 1, "I_k")
+        return I_dev, I_dev
+    # row 0 of the second tensor (I_k_2[first]) is never read; it only keeps row k+1 aligned
+    return rows(I_k, first, first + n, "I_k"), rows(I_k_2, first, first + n + 1, "I_k_2")
+
+
+def solve_on_device(op, I_dev, I2_dev, t_k, lambda_, k0, k1, V_dev=None):
+    """Frames k0..k1-1 from device-resident signals (rows are absolute frame indices).
+    -> (V_dev (k1-k0, 2N) device tensor, SolveInfo).  Used by bench.py (inputs resident in
+    HBM) and by distributed.py."""
+    torch = _lib.require_cuda()
+    s = _solver(op)
+    dt = torch.from_numpy(frame_dt(t_k, k0, k1)).to(op.device)
+    return s.solve_frames(I_dev[k0:k1 + 1], I2_dev[k0:k1 + 1], dt, lambda_, V_dev)
+
+
+def compute_velocity_field(processes_num, time_steps, a2, grad_w, e, integral_wi_wj, triangles, t_k, areas,
+                           lambda_, I_k, I_k_2):
+    """Reference :152-194.  Frame k (k = 0 .. time_steps-2) uses (I_k[k], I_k_2[k+1]) (:174-175).
+    -> (V_k: list of time_steps-1 arrays (2N,), V_k[k][i + N*alpha]; seconds)"""
+    global last_solve_info
+    torch = _lib.require_cuda()
+    op = _operator(a2, triangles)
+    op.use_geometry(grad_w, e, integral_wi_wj, areas)
+    start_time = time.time()
+    n = int(time_steps) - 1
+    N = op.n_vertices
+    if n <= 0:
+        return [], 0.0
+    from . import distributed
+    if distributed.world_size() > 1:
+        V, info = distributed.compute_velocity_field_sharded(op, n, t_k, lambda_, I_k, I_k_2)
+    else:
+        I_dev, I2_dev = _upload_signals(op, I_k, I_k_2, n)
+        V_dev, info = solve_on_device(op, I_dev, I2_dev, t_k, lambda_, 0, n)
+        V = V_dev.cpu().numpy()
+    execution_time = time.time() - start_time
+    info.seconds = execution_time
+    last_solve_info = info
+    _check_converged(info)
+    return [V[k] for k in range(n)], execution_time
+
+
+def worker(k, a2, grad_w, e, integral_wi_wj, triangles, t_k, areas, lambda_, I_k_k, I_k_kplus1):
+    """Reference :100-149: one frame.  -> V (2N,) float64."""
+    global last_solve_info
+    torch = _lib.require_cuda()
+    op = _operator(a2, triangles)
+    op.use_geometry(grad_w, e, integral_wi_wj, areas)
+    s = _solver(op)
+    I_now = torch.from_numpy(np.ascontiguousarray(np.asarray(I_k_k, dtype=np.float64)).reshape(1, -1)).to(op.device)
+    I_next = torch.from_numpy(np.ascontiguousarray(np.asarray(I_k_kplus1, dtype=np.float64)).reshape(1, -1)).to(op.device)
+    dt = torch.from_numpy(frame_dt(t_k, k, k + 1)).to(op.device)
+    V_dev = torch.empty((1, 2 * op.n_vertices), dtype=torch.float64, device=op.device)
+    info = s.solve_batch(I_now, I_next, dt, lambda_, V_dev)
+    last_solve_info = info
+    _check_converged(info, first_frame=k)
+    return V_dev[0].cpu().numpy()
+
+
+def reshape_and_save_data(data, file_path):
+    """Reference :314-320 (same CSV layout: pandas DataFrame.to_csv of data.reshape(n, -1))."""
+    import pandas as pd
+    if isinstance(data, list):
+        data = np.array(data)
+    reshaped_data = data.reshape(data.shape[0], -1)
+    pd.DataFrame(reshaped_data).to_csv(file_path)
+
+
+def load_potentials(csv_path):
+    """Reference :203-207."""
+    import pandas as pd
+    return pd.read_csv(csv_path, sep=',', header='infer', index_col=0).values
+
+
+__all__ = ["compute_geometrical_quantities", "compute_velocity_field", "worker", "reshape_and_save_data",
+           "load_potentials", "solve_on_device", "settings", "SolveInfo", "UnconvergedError", "MeshOperator"]

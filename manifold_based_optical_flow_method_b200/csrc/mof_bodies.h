@@ -1,0 +1,223 @@
+// Scalar "bodies" of the kernels: the arithmetic one (row|face|vertex, frame) pair
+// performs, written once as __host__ __device__ inline functions.  The CUDA kernels in
+// geom.cu / assemble.cu / pcg.cu / detect.cu wrap them in the thread mapping; the
+// CPU-only test helper tests/hostcheck/hostcheck.cpp wraps the same bodies in plain
+// loops so that indexing and operation order can be checked against the oracle in the
+// build container, which has no GPU.  (That helper is test infrastructure: the product
+// library never calls these bodies on the host.)
+//
+// Reference citations: cof = utils/compute_optical_flow.py, fsp =
+// utils/find_singularity_point.py under /root/reference.
+#ifndef MOF_BODIES_H
+#define MOF_BODIES_H
+
+#include <math.h>
+#include <stdint.h>
+
+#include "mof_b200.h"
+
+#if defined(__CUDACC__)
+#define MOF_HD __host__ __device__ __forceinline__
+#else
+#define MOF_HD inline
+#endif
+
+// Exactly-rounded multiply/add that the compiler may not contract into an FMA, for
+// the few places where bit-equality with numpy's separate multiply and add is tested.
+#if defined(__CUDA_ARCH__)
+#define MOF_MUL(a, b) __dmul_rn((a), (b))
+#define MOF_ADD(a, b) __dadd_rn((a), (b))
+#else
+#define MOF_MUL(a, b) ((a) * (b))
+#define MOF_ADD(a, b) ((a) + (b))
+#endif
+
+#define MOF_W MOF_GROUP
+
+// ---- frame-minor layout offsets (elements) --------------------------------------
+MOF_HD size_t mof_ix_vec(int64_t N, int64_t g, int64_t v, int c) { return (size_t)((g * N + v) * 2 + c) * MOF_W; }
+MOF_HD size_t mof_ix_val(int64_t nb, int64_t g, int64_t b, int c) { return (size_t)((g * nb + b) * 4 + c) * MOF_W; }
+MOF_HD size_t mof_ix_sca(int64_t N, int64_t g, int64_t v) { return (size_t)(g * N + v) * MOF_W; }
+MOF_HD size_t mof_ix_minv(int64_t N, int64_t g, int64_t v, int c) { return (size_t)((g * N + v) * 3 + c) * MOF_W; }
+
+// ---- K0 ----------------------------------------------------------------------
+// compute_orthonormal_basis, cof:210-235.  e[0..2] = e1, e[3..5] = e2.
+MOF_HD void mof_basis_body(const double* n, double* e) {
+    double a0, a1, a2;
+    if (n[0] != 0 || n[1] != 0) { a0 = -n[1]; a1 = n[0]; a2 = 0.0; }     // cof:222-223
+    else                        { a0 = 0.0;  a1 = -n[2]; a2 = n[1]; }    // cof:225
+    // e2 = n x e1 (cof:228)
+    double b0 = MOF_ADD(MOF_MUL(n[1], a2), -MOF_MUL(n[2], a1));
+    double b1 = MOF_ADD(MOF_MUL(n[2], a0), -MOF_MUL(n[0], a2));
+    double b2 = MOF_ADD(MOF_MUL(n[0], a1), -MOF_MUL(n[1], a0));
+    double na = sqrt(MOF_ADD(MOF_ADD(MOF_MUL(a0, a0), MOF_MUL(a1, a1)), MOF_MUL(a2, a2)));   // cof:231
+    double nb = sqrt(MOF_ADD(MOF_ADD(MOF_MUL(b0, b0), MOF_MUL(b1, b1)), MOF_MUL(b2, b2)));   // cof:232
+    e[0] = a0 / na; e[1] = a1 / na; e[2] = a2 / na;
+    e[3] = b0 / nb; e[4] = b1 / nb; e[5] = b2 / nb;
+}
+
+// compute_gradient_w, cof:238-255: foot H of the perpendicular from p_i on line (p_j,p_k),
+// returns (H - p_i) / |H - p_i|^2  (minus the textbook gradient; used consistently).
+MOF_HD void mof_gradw_body(const double* pi, const double* pj, const double* pk, double* out) {
+    double jk0 = pk[0] - pj[0], jk1 = pk[1] - pj[1], jk2 = pk[2] - pj[2];      // cof:249
+    double ji0 = pi[0] - pj[0], ji1 = pi[1] - pj[1], ji2 = pi[2] - pj[2];      // cof:250
+    double d1 = ji0 * jk0 + ji1 * jk1 + ji2 * jk2;
+    double d2 = jk0 * jk0 + jk1 * jk1 + jk2 * jk2;
+    double q0 = d1 * jk0 / d2, q1 = d1 * jk1 / d2, q2 = d1 * jk2 / d2;          // cof:251-252
+    double h0 = pj[0] - pi[0] + q0, h1 = pj[1] - pi[1] + q1, h2 = pj[2] - pi[2] + q2;   // cof:253
+    double hh = h0 * h0 + h1 * h1 + h2 * h2;
+    out[0] = h0 / hh; out[1] = h1 / hh; out[2] = h2 / hh;                         // cof:254
+}
+
+// One face: grad_w[f][0..2] with the argument orders of cof:63-68, integral (cof:73-75).
+MOF_HD void mof_face_geom_body(const double* coords, const int32_t* tri, const double* areas,
+                               int64_t f, double* grad_w, double* integral) {
+    const double* A = coords + 3 * (int64_t)tri[3 * f];
+    const double* B = coords + 3 * (int64_t)tri[3 * f + 1];
+    const double* C = coords + 3 * (int64_t)tri[3 * f + 2];
+    mof_gradw_body(A, B, C, grad_w + 9 * f);
+    mof_gradw_body(B, A, C, grad_w + 9 * f + 3);
+    mof_gradw_body(C, A, B, grad_w + 9 * f + 6);
+    integral[2 * f] = areas[f] / 6;
+    integral[2 * f + 1] = areas[f] / 12;
+}
+
+// a2 block b of row v: sum over contributing faces (ascending) of
+// (e_v^al . e_j^be) * (g_m . g_n) * A_T   (compute_a2 cof:258-270, accumulation cof:78-93).
+MOF_HD void mof_a2_block_body(const mof_mesh_dev& M, int64_t v, int64_t b, double* out) {
+    const double* ei = M.e + 6 * v;
+    const double* ej = M.e + 6 * (int64_t)M.col[b];
+    double ee[4];
+    for (int al = 0; al < 2; ++al)
+        for (int be = 0; be < 2; ++be)
+            ee[2 * al + be] = ei[3 * al] * ej[3 * be] + ei[3 * al + 1] * ej[3 * be + 1] + ei[3 * al + 2] * ej[3 * be + 2];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int32_t q = M.cptr[b]; q < M.cptr[b + 1]; ++q) {
+        int32_t ent = M.centry[q];
+        int64_t f = ent >> 4;
+        int m = (ent >> 2) & 3, n = ent & 3;
+        const double* gm = M.grad_w + 9 * f + 3 * m;
+        const double* gn = M.grad_w + 9 * f + 3 * n;
+        double gg = gm[0] * gn[0] + gm[1] * gn[1] + gm[2] * gn[2];
+        double A = M.areas[f];
+        for (int c = 0; c < 4; ++c) acc[c] += ee[c] * gg * A;
+    }
+    for (int c = 0; c < 4; ++c) out[c] = acc[c];
+}
+
+// ---- K1 ----------------------------------------------------------------------
+// Block b (row v) of a = a1 + lambda*a2 for one frame (lane), plus -- on the diagonal
+// block -- the rhs f and the inverse of the diagonal block.
+//   It_l / dIt_l : base of this group's It / dIt already offset by the lane; vertex u
+//                  lives at [u * MOF_W].
+//   grad_M_I (cof:116-117), compute_a1 (cof:285), compute_f (cof:305-311).
+template <bool DIAG>
+MOF_HD void mof_assemble_block_body(const mof_mesh_dev& M, int64_t v, int64_t b, const double* It_l,
+                                    const double* dIt_l, double lambda_, double* a, double* f) {
+    const double* ei = M.e + 6 * v;
+    const double* ej = M.e + 6 * (int64_t)M.col[b];
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0, f0 = 0.0, f1 = 0.0;
+    for (int32_t q = M.cptr[b]; q < M.cptr[b + 1]; ++q) {
+        int32_t ent = M.centry[q];
+        int64_t fc = ent >> 4;
+        int m = (ent >> 2) & 3, n = ent & 3;
+        int64_t t0 = M.tri[3 * fc], t1 = M.tri[3 * fc + 1], t2 = M.tri[3 * fc + 2];
+        const double* g = M.grad_w + 9 * fc;
+        double I0 = It_l[t0 * MOF_W], I1 = It_l[t1 * MOF_W], I2 = It_l[t2 * MOF_W];
+        double Gx = I0 * g[0] + I1 * g[3] + I2 * g[6];
+        double Gy = I0 * g[1] + I1 * g[4] + I2 * g[7];
+        double Gz = I0 * g[2] + I1 * g[5] + I2 * g[8];
+        double ci0 = Gx * ei[0] + Gy * ei[1] + Gz * ei[2];
+        double ci1 = Gx * ei[3] + Gy * ei[4] + Gz * ei[5];
+        double cj0 = Gx * ej[0] + Gy * ej[1] + Gz * ej[2];
+        double cj1 = Gx * ej[3] + Gy * ej[4] + Gz * ej[5];
+        double integ = M.integral[2 * fc + (m == n ? 0 : 1)];           // cof:131-132
+        acc0 += ci0 * cj0 * integ;
+        acc1 += ci0 * cj1 * integ;
+        acc2 += ci1 * cj0 * integ;
+        acc3 += ci1 * cj1 * integ;
+        if (DIAG) {
+            double d0 = dIt_l[t0 * MOF_W], d1 = dIt_l[t1 * MOF_W], d2 = dIt_l[t2 * MOF_W];
+            double dm = m == 0 ? d0 : (m == 1 ? d1 : d2);
+            double oth = m == 0 ? d1 + d2 : (m == 1 ? d0 + d2 : d0 + d1);
+            double w = 2 * dm + oth;                                     // cof:311
+            double A = M.areas[fc];
+            f0 += ci0 * w * A / 12;
+            f1 += ci1 * w * A / 12;
+        }
+    }
+    const double* a2 = M.a2v + 4 * b;
+    a[0] = acc0 + lambda_ * a2[0];                                      // cof:144
+    a[1] = acc1 + lambda_ * a2[1];
+    a[2] = acc2 + lambda_ * a2[2];
+    a[3] = acc3 + lambda_ * a2[3];
+    if (DIAG) { f[0] = f0; f[1] = f1; }
+}
+
+// inverse of the symmetric 2x2 diagonal block [[a0,a1],[a2,a3]] -> (m00, m01, m11)
+MOF_HD void mof_inv2_body(const double* a, double* m) {
+    double det = a[0] * a[3] - a[1] * a[2];
+    double id = 1.0 / det;
+    m[0] = a[3] * id;
+    m[1] = -0.5 * (a[1] + a[2]) * id;
+    m[2] = a[0] * id;
+}
+
+// ---- K4 ----------------------------------------------------------------------
+// process_V_k fsp:61-66: V1*e1 + V2*e2 (separate multiplies and add, as numpy does).
+MOF_HD void mof_tangent_body(double v1, double v2, const double* e, double* out) {
+    out[0] = MOF_ADD(MOF_MUL(v1, e[0]), MOF_MUL(v2, e[3]));
+    out[1] = MOF_ADD(MOF_MUL(v1, e[1]), MOF_MUL(v2, e[4]));
+    out[2] = MOF_ADD(MOF_MUL(v1, e[2]), MOF_MUL(v2, e[5]));
+}
+// fsp:161 / S3:132: sqrt(x^2 + y^2 + z^2)
+MOF_HD double mof_len3_body(const double* v) {
+    return sqrt(MOF_ADD(MOF_ADD(MOF_MUL(v[0], v[0]), MOF_MUL(v[1], v[1])), MOF_MUL(v[2], v[2])));
+}
+
+// ---- K5 ----------------------------------------------------------------------
+// is_zero_velocity_vertex(V_i / vmax, eps), fsp:72-90,166.
+MOF_HD bool mof_vertex_zero_body(const double* V, double vmax, double eps) {
+    double t[3] = {V[0] / vmax, V[1] / vmax, V[2] / vmax};
+    return mof_len3_body(t) <= eps;
+}
+
+// has_zero_velocity_interior, fsp:93-137, for one face; VA,VB,VC are the raw vertex
+// velocities (divided by vmax here, fsp:178-179).  The reference solves the 3x2
+// least-squares system M [lam mu]' = -VC_p with M = [VA_p-VC_p | VB_p-VC_p]; all three
+// vectors lie in the face plane, so the system is solved exactly in an orthonormal basis
+// (u, w) of that plane by Cramer's rule.  sign = per-face Poincare index (orientation of
+// (VA_p-VC_p, VB_p-VC_p) relative to the face winding (B-A)x(C-A)).
+MOF_HD bool mof_face_zero_body(const double* A, const double* B, const double* C, const double* VA,
+                               const double* VB, const double* VC, double vmax, double* lam,
+                               double* mu, int* sign) {
+    double ab[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+    double ac[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+    double n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};   // fsp:113
+    double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    n[0] /= nn; n[1] /= nn; n[2] /= nn;                                                                          // fsp:114
+    double lu = sqrt(ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2]);
+    double u[3] = {ab[0] / lu, ab[1] / lu, ab[2] / lu};
+    double w[3] = {n[1] * u[2] - n[2] * u[1], n[2] * u[0] - n[0] * u[2], n[0] * u[1] - n[1] * u[0]};
+    double P[3][2];
+    const double* Vs[3] = {VA, VB, VC};
+    for (int k = 0; k < 3; ++k) {
+        double s[3] = {Vs[k][0] / vmax, Vs[k][1] / vmax, Vs[k][2] / vmax};                                       // fsp:178-179
+        double dn = s[0] * n[0] + s[1] * n[1] + s[2] * n[2];
+        double p[3] = {s[0] - dn * n[0], s[1] - dn * n[1], s[2] - dn * n[2]};                                    // fsp:117-119
+        P[k][0] = p[0] * u[0] + p[1] * u[1] + p[2] * u[2];
+        P[k][1] = p[0] * w[0] + p[1] * w[1] + p[2] * w[2];
+    }
+    double ax = P[0][0] - P[2][0], ay = P[0][1] - P[2][1];      // column 0 of M (fsp:122)
+    double bx = P[1][0] - P[2][0], by = P[1][1] - P[2][1];      // column 1 of M
+    double cx = -P[2][0], cy = -P[2][1];                        // rhs -VC_p (fsp:128)
+    double det = ax * by - ay * bx;
+    double l = (cx * by - cy * bx) / det;
+    double m = (ax * cy - ay * cx) / det;
+    *lam = l;
+    *mu = m;
+    *sign = det > 0 ? 1 : (det < 0 ? -1 : 0);
+    return (l + m <= 1) && (l >= 0) && (m >= 0);               // fsp:130 (false for NaN)
+}
+
+#endif  // MOF_BODIES_H

@@ -1,0 +1,43 @@
+// Shared device/host helpers for the sm_100a kernels of libmof_b200.
+#ifndef MOF_COMMON_CUH
+#define MOF_COMMON_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mof_b200.h"
+#include "mof_bodies.h"
+#include "mof_error.h"
+
+#define MOF_CUDA_TRY(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return mof_set_error(-100 - (int)_e, "%s:%d: %s failed: %s", __FILE__, __LINE__,    \
+                                 #expr, cudaGetErrorString(_e));                                \
+    } while (0)
+
+#define MOF_LAUNCH_CHECK(name)                                                                  \
+    do {                                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                    \
+        if (_e != cudaSuccess)                                                                  \
+            return mof_set_error(-100 - (int)_e, "launch of %s failed: %s", name,               \
+                                 cudaGetErrorString(_e));                                       \
+    } while (0)
+
+#define MOF_REQUIRE(cond, msg)                                                                  \
+    do {                                                                                        \
+        if (!(cond)) return mof_set_error(-1, "%s: %s", __func__, msg);                         \
+    } while (0)
+
+static inline cudaStream_t mof_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline unsigned mof_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// scal[g][MOF_S_*][32]
+enum { MOF_S_RZ = 0, MOF_S_PAP = 1, MOF_S_RR = 2, MOF_S_BB = 3, MOF_S_ALPHA = 4, MOF_S_BETA = 5,
+       MOF_S_RRTRUE = 6, MOF_S_SPARE = 7, MOF_S_COUNT = 8 };
+// state[g][MOF_I_*][32], then group_done[G], ticket[G], groups_active[1]
+enum { MOF_I_ACTIVE = 0, MOF_I_ITERS = 1, MOF_I_STATUS = 2, MOF_I_SPARE = 3, MOF_I_COUNT = 4 };
+#define MOF_STATUS_PENDING (-1)
+
+#endif  // MOF_COMMON_CUH

@@ -1,0 +1,483 @@
+// K2/K3 -- batched fp64 conjugate gradients with 2x2 block-Jacobi preconditioning.
+// Replaces scipy.sparse.linalg.spsolve (SuperLU) in worker,
+// utils/compute_optical_flow.py:147, for a whole batch of frames at once.
+//
+// Layout and mapping.  The matrix of every frame shares one block pattern (rowptr/col over
+// the renumbered vertex adjacency).  Values and vectors are frame-minor,
+// [group][slot][32 frames]: a warp works on one block row, lane = frame, so each value /
+// vector access of a warp is one 256-byte line and the column index is read once for 32
+// frames.  A CTA (8 warps) owns a tile of MOF_TILE_ROWS consecutive rows; grid = (tiles,
+// groups).
+//
+// Reductions.  Dot products are private to a lane (a frame) while a warp walks its rows;
+// the 8 warps of a CTA are combined through shared memory in warp order, the per-tile
+// partials are written to `partial`, and the last CTA of a group to finish (ticket
+// counter) adds the tiles in index order.  No floating-point atomics: results are
+// bit-reproducible and independent of how frames are batched or sharded over GPUs.
+// That last CTA also does the scalar step (alpha, beta, convergence test per frame).
+//
+// Per iteration: spmv_kernel (ap = A p, p'Ap, alpha), update_kernel (x += alpha p,
+// r -= alpha ap, z = Minv r, r'z, r'r, beta, convergence), pupdate_kernel (p = z + beta p).
+// Converged frames get alpha = beta = 0 (frozen); a group whose frames are all done makes
+// its CTAs return at once.
+//
+// HBM bytes per frame-iteration at N vertices, nb blocks:
+//   spmv   : 32 nb (values) + 16 N (p, gathered through L2) + 16 N (ap)   [+ 4 nb/32 indices]
+//   update : read p, ap, x, r (64 N) + minv (24 N), write x, r, z (48 N)
+//   pupdate: read z, p (32 N), write p (16 N)
+#include <math.h>
+
+#include "mof_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kRowsPerWarp = MOF_TILE_ROWS / kWarps;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double* scal_ptr(double* scal, int64_t g, int which) {
+    return scal + ((size_t)g * MOF_S_COUNT + which) * MOF_W;
+}
+__device__ __forceinline__ int32_t* state_ptr(int32_t* st, int64_t g, int which) {
+    return st + ((size_t)g * MOF_I_COUNT + which) * MOF_W;
+}
+__device__ __forceinline__ int32_t* group_done_ptr(int32_t* st, int G) { return st + (size_t)G * MOF_I_COUNT * MOF_W; }
+__device__ __forceinline__ int32_t* ticket_ptr(int32_t* st, int G) { return group_done_ptr(st, G) + G; }
+__device__ __forceinline__ int32_t* groups_active_ptr(int32_t* st, int G) { return group_done_ptr(st, G) + 2 * G; }
+
+// Deterministic CTA + cross-tile reduction of NV per-lane values.  Returns true (for every
+// thread of the CTA) in the last CTA of group g; there `tot` holds the totals in warp 0.
+template <int NV>
+__device__ __forceinline__ bool tile_reduce(const double (&val)[NV], double* __restrict__ partial_g, int ntiles,
+                                            int tile, int32_t* ticket_g, double (&tot)[NV]) {
+    __shared__ double red[kWarps][NV][MOF_W];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[warp][k][lane] = val[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = red[0][k][lane];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s += red[w][k][lane];
+            partial_g[((size_t)tile * 2 + k) * MOF_W + lane] = s;
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket_g, 1) == ntiles - 1);
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double acc = 0.0;
+        for (int t = warp; t < ntiles; t += kWarps) acc += __ldcg(partial_g + ((size_t)t * 2 + k) * MOF_W + lane);
+        red[warp][k][lane] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = red[0][k][lane];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s += red[w][k][lane];
+            tot[k] = s;
+        }
+    }
+    if (threadIdx.x == 0) *ticket_g = 0;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------
+// K2: y = A x (block CSR, frame-minor), optionally x'y and the alpha step.
+// ---------------------------------------------------------------------------------
+template <bool SOLVER>
+__global__ void __launch_bounds__(256) spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                   const double* __restrict__ vals, const double* __restrict__ x,
+                                                   double* __restrict__ y, int64_t N, int64_t nb, int ntiles,
+                                                   double* __restrict__ partial, double* __restrict__ scal,
+                                                   int32_t* __restrict__ state, int G) {
+    const int64_t g = blockIdx.y;
+    if (SOLVER && group_done_ptr(state, G)[g]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x;
+    const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    const double* __restrict__ vg = vals + (size_t)g * nb * 4 * MOF_W + lane;
+    const double* __restrict__ xg = x + (size_t)g * N * 2 * MOF_W + lane;
+    double* __restrict__ yg = y + (size_t)g * N * 2 * MOF_W + lane;
+
+    int32_t rp = 0;
+    if (lane <= kRowsPerWarp && row0 + lane <= N) rp = rowptr[row0 + lane];
+    double dot = 0.0;
+    // software-pipelined column indices: the first <=32 indices of the next row are
+    // fetched while the current row is processed
+    int32_t cj_next = 0;
+    {
+        int32_t bs = __shfl_sync(kFull, rp, 0), be = __shfl_sync(kFull, rp, 1);
+        if (row0 < N && lane < be - bs) cj_next = col[bs + lane];
+    }
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int64_t v = row0 + rr;
+        if (v >= N) break;
+        const int32_t bs = __shfl_sync(kFull, rp, rr), be = __shfl_sync(kFull, rp, rr + 1);
+        int32_t cj = cj_next;
+        if (rr + 1 < kRowsPerWarp && v + 1 < N) {
+            int32_t be2 = __shfl_sync(kFull, rp, rr + 2 > kRowsPerWarp ? kRowsPerWarp : rr + 2);
+            if (lane < be2 - be) cj_next = col[be + lane];
+        }
+        double y0 = 0.0, y1 = 0.0;
+        for (int32_t base = bs; base < be; base += 32) {
+            const int cnt = min(32, be - base);
+            if (base != bs) cj = lane < cnt ? col[base + lane] : 0;
+            const double* __restrict__ a = vg + (size_t)base * 4 * MOF_W;
+#pragma unroll 4
+            for (int k = 0; k < cnt; ++k) {
+                const int32_t j = __shfl_sync(kFull, cj, k);
+                const double a00 = __ldcs(a + (size_t)k * 4 * MOF_W);
+                const double a01 = __ldcs(a + (size_t)k * 4 * MOF_W + MOF_W);
+                const double a10 = __ldcs(a + (size_t)k * 4 * MOF_W + 2 * MOF_W);
+                const double a11 = __ldcs(a + (size_t)k * 4 * MOF_W + 3 * MOF_W);
+                const double x0 = __ldg(xg + (size_t)j * 2 * MOF_W);
+                const double x1 = __ldg(xg + (size_t)j * 2 * MOF_W + MOF_W);
+                y0 = fma(a00, x0, y0);
+                y0 = fma(a01, x1, y0);
+                y1 = fma(a10, x0, y1);
+                y1 = fma(a11, x1, y1);
+            }
+        }
+        yg[(size_t)v * 2 * MOF_W] = y0;
+        yg[(size_t)v * 2 * MOF_W + MOF_W] = y1;
+        if (SOLVER) {
+            const double xi0 = __ldg(xg + (size_t)v * 2 * MOF_W), xi1 = __ldg(xg + (size_t)v * 2 * MOF_W + MOF_W);
+            dot = fma(xi0, y0, dot);
+            dot = fma(xi1, y1, dot);
+        }
+    }
+    if (!SOLVER) return;
+
+    double val[1] = {dot}, tot[1];
+    if (!tile_reduce<1>(val, partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(state, G) + g, tot))
+        return;
+    if (warp == 0) {
+        int32_t* active = state_ptr(state, g, MOF_I_ACTIVE);
+        double alpha = 0.0;
+        if (active[lane]) {
+            const double pap = tot[0];
+            const double rz = scal_ptr(scal, g, MOF_S_RZ)[lane];
+            if (!(pap > 0.0) || isinf(pap)) {          // not SPD / NaN / overflow
+                state_ptr(state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
+                active[lane] = 0;
+            } else {
+                alpha = rz / pap;
+            }
+        }
+        scal_ptr(scal, g, MOF_S_PAP)[lane] = tot[0];
+        scal_ptr(scal, g, MOF_S_ALPHA)[lane] = alpha;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K3a: x += alpha p ; r -= alpha ap ; z = Minv r ; r'z, r'r ; beta and convergence.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N, int ntiles, double tol2) {
+    const int64_t g = blockIdx.y;
+    const int G = B.n_groups;
+    if (group_done_ptr(B.state, G)[g]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x;
+    const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    const double alpha = scal_ptr(B.scal, g, MOF_S_ALPHA)[lane];
+    double rz = 0.0, rr = 0.0;
+#pragma unroll 2
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int64_t v = row0 + q;
+        if (v >= N) break;
+        const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
+        const size_t im = mof_ix_minv(N, g, v, 0) + lane;
+        const double p0 = B.p[i0], p1 = B.p[i1];
+        const double a0 = __ldcs(B.ap + i0), a1 = __ldcs(B.ap + i1);
+        double x0 = B.x[i0], x1 = B.x[i1];
+        double r0 = B.r[i0], r1 = B.r[i1];
+        const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
+        x0 = fma(alpha, p0, x0);
+        x1 = fma(alpha, p1, x1);
+        r0 = fma(-alpha, a0, r0);
+        r1 = fma(-alpha, a1, r1);
+        const double z0 = m0 * r0 + m1 * r1;
+        const double z1 = m1 * r0 + m2 * r1;
+        B.x[i0] = x0; B.x[i1] = x1;
+        B.r[i0] = r0; B.r[i1] = r1;
+        B.z[i0] = z0; B.z[i1] = z1;
+        rz = fma(r0, z0, rz); rz = fma(r1, z1, rz);
+        rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
+    }
+    double val[2] = {rz, rr}, tot[2];
+    if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
+        return;
+    if (warp == 0) {
+        int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
+        double beta = 0.0;
+        int act = active[lane];
+        if (act) {
+            const double rz_old = scal_ptr(B.scal, g, MOF_S_RZ)[lane];
+            const double bb = scal_ptr(B.scal, g, MOF_S_BB)[lane];
+            state_ptr(B.state, g, MOF_I_ITERS)[lane] += 1;
+            scal_ptr(B.scal, g, MOF_S_RZ)[lane] = tot[0];
+            scal_ptr(B.scal, g, MOF_S_RR)[lane] = tot[1];
+            if (!isfinite(tot[0]) || !isfinite(tot[1])) {
+                state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
+                act = 0;
+            } else if (tot[1] <= tol2 * bb) {
+                state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_CONVERGED;
+                act = 0;
+            } else {
+                beta = tot[0] / rz_old;
+            }
+            active[lane] = act;
+        }
+        scal_ptr(B.scal, g, MOF_S_BETA)[lane] = beta;
+        const int any = __any_sync(kFull, act);
+        if (!any && lane == 0) {
+            group_done_ptr(B.state, G)[g] = 1;
+            atomicSub(groups_active_ptr(B.state, G), 1);
+        }
+    }
+}
+
+// K3b: p = z + beta p
+__global__ void __launch_bounds__(256) pupdate_kernel(mof_batch_dev B, int64_t N) {
+    const int64_t g = blockIdx.y;
+    if (group_done_ptr(B.state, B.n_groups)[g]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    const double beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
+#pragma unroll 4
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int64_t v = row0 + q;
+        if (v >= N) break;
+        const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
+        const double z0 = __ldcs(B.z + i0), z1 = __ldcs(B.z + i1);
+        B.p[i0] = fma(beta, B.p[i0], z0);
+        B.p[i1] = fma(beta, B.p[i1], z1);
+    }
+}
+
+// Start (mode 0: x = 0, r = b) or verification / restart (mode 1: r = b - ap with
+// ap = A x already computed): z = Minv r, p = z, r'z, r'r and per-frame bookkeeping.
+__global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, int ntiles, int mode, double tol2) {
+    const int64_t g = blockIdx.y;
+    const int G = B.n_groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x;
+    const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    double rz = 0.0, rr = 0.0;
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int64_t v = row0 + q;
+        if (v >= N) break;
+        const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
+        const size_t im = mof_ix_minv(N, g, v, 0) + lane;
+        double r0 = B.rhs[i0], r1 = B.rhs[i1];
+        if (mode == 0) {
+            B.x[i0] = 0.0; B.x[i1] = 0.0;
+        } else {
+            r0 -= B.ap[i0]; r1 -= B.ap[i1];
+        }
+        const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
+        const double z0 = m0 * r0 + m1 * r1;
+        const double z1 = m1 * r0 + m2 * r1;
+        B.r[i0] = r0; B.r[i1] = r1;
+        B.z[i0] = z0; B.z[i1] = z1;
+        B.p[i0] = z0; B.p[i1] = z1;
+        rz = fma(r0, z0, rz); rz = fma(r1, z1, rz);
+        rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
+    }
+    double val[2] = {rz, rr}, tot[2];
+    if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
+        return;
+    if (warp == 0) {
+        int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
+        int32_t* status = state_ptr(B.state, g, MOF_I_STATUS);
+        int act;
+        if (mode == 0) {
+            const bool valid = g * MOF_W + lane < B.n_frames;
+            scal_ptr(B.scal, g, MOF_S_BB)[lane] = tot[1];
+            scal_ptr(B.scal, g, MOF_S_RRTRUE)[lane] = tot[1];
+            state_ptr(B.state, g, MOF_I_ITERS)[lane] = 0;
+            if (!valid || tot[1] == 0.0) { act = 0; status[lane] = MOF_STATUS_ZERO_RHS; }
+            else if (!isfinite(tot[1]) || !isfinite(tot[0])) { act = 0; status[lane] = MOF_STATUS_BREAKDOWN; }
+            else { act = 1; status[lane] = MOF_STATUS_PENDING; }
+        } else {
+            const double bb = scal_ptr(B.scal, g, MOF_S_BB)[lane];
+            scal_ptr(B.scal, g, MOF_S_RRTRUE)[lane] = tot[1];
+            act = active[lane];
+            if (status[lane] == MOF_STATUS_CONVERGED && !(tot[1] <= tol2 * bb)) {
+                act = 1;                                   // recurrence drifted: restart from the true residual
+                status[lane] = MOF_STATUS_PENDING;
+            }
+        }
+        scal_ptr(B.scal, g, MOF_S_RZ)[lane] = tot[0];
+        scal_ptr(B.scal, g, MOF_S_RR)[lane] = tot[1];
+        active[lane] = act;
+        const int any = __any_sync(kFull, act);
+        if (lane == 0) {
+            int32_t* done = group_done_ptr(B.state, G) + g;
+            if (mode == 0) {
+                *done = any ? 0 : 1;
+                if (any) atomicAdd(groups_active_ptr(B.state, G), 1);
+            } else if (any && *done) {
+                *done = 0;
+                atomicAdd(groups_active_ptr(B.state, G), 1);
+            }
+        }
+    }
+}
+
+// x [G][N][2][32] -> V[k][perm[v] + N*alpha]   (reference layout, cof:149)
+__global__ void __launch_bounds__(256) unpack_kernel(int64_t N, int32_t n_frames, const int32_t* __restrict__ perm,
+                                                     const double* __restrict__ x, double* __restrict__ V, int64_t ld) {
+    __shared__ double s[2][32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t g = blockIdx.y;
+    const int64_t v0 = (int64_t)blockIdx.x * 32;
+    for (int vv = ty; vv < 32; vv += 8) {
+        int64_t v = v0 + vv;
+        if (v < N) {
+            s[0][vv][tx] = x[mof_ix_vec(N, g, v, 0) + tx];
+            s[1][vv][tx] = x[mof_ix_vec(N, g, v, 1) + tx];
+        }
+    }
+    __syncthreads();
+    const int64_t v = v0 + tx;
+    if (v >= N) return;
+    const int64_t o = perm[v];
+    for (int fr = ty; fr < 32; fr += 8) {
+        int64_t k = g * 32 + fr;
+        if (k < n_frames) {
+            V[k * ld + o] = s[0][tx][fr];
+            V[k * ld + N + o] = s[1][tx][fr];
+        }
+    }
+}
+
+int check_batch(const mof_mesh_dev* mesh, const mof_batch_dev* b) {
+    if (!mesh || !b) return mof_set_error(-1, "NULL mesh/batch");
+    if (b->n_groups <= 0 || b->n_groups > 65535) return mof_set_error(-1, "n_groups out of range (1..65535)");
+    if (b->n_frames < 0 || b->n_frames > b->n_groups * MOF_GROUP) return mof_set_error(-1, "n_frames does not fit n_groups");
+    if (!mesh->rowptr || !mesh->col) return mof_set_error(-1, "mesh pattern missing");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t mof_state_ints(int32_t n_groups) {
+    return (int64_t)n_groups * MOF_I_COUNT * MOF_W + 2 * (int64_t)n_groups + 1;
+}
+
+extern "C" int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const double* x, double* y,
+                              void* stream) {
+    if (int rc = check_batch(mesh, batch)) return rc;
+    MOF_REQUIRE(x && y && batch->vals, "NULL argument");
+    const int ntiles = (int)mof_num_tiles(mesh->n_vertices);
+    dim3 grid(ntiles, batch->n_groups);
+    spmv_kernel<false><<<grid, 256, 0, mof_stream(stream)>>>(mesh->rowptr, mesh->col, batch->vals, x, y,
+                                                            mesh->n_vertices, mesh->n_blocks, ntiles, nullptr,
+                                                            nullptr, nullptr, batch->n_groups);
+    MOF_LAUNCH_CHECK("spmv_kernel<false>");
+    return 0;
+}
+
+extern "C" int mof_unpack_solution(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double* V, int64_t ld,
+                                   void* stream) {
+    if (int rc = check_batch(mesh, batch)) return rc;
+    MOF_REQUIRE(V && batch->x && ld >= 2 * mesh->n_vertices, "bad V / ld");
+    dim3 grid(mof_cdiv(mesh->n_vertices, 32), batch->n_groups), block(32, 8);
+    unpack_kernel<<<grid, block, 0, mof_stream(stream)>>>(mesh->n_vertices, batch->n_frames, mesh->perm, batch->x, V, ld);
+    MOF_LAUNCH_CHECK("unpack_kernel");
+    return 0;
+}
+
+extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double tol,
+                                   int32_t max_iter, int32_t check_every, int32_t max_restarts, int32_t* iters,
+                                   double* relres, int32_t* status, void* stream) {
+    if (int rc = check_batch(mesh, batch)) return rc;
+    const mof_batch_dev& B = *batch;
+    MOF_REQUIRE(B.vals && B.rhs && B.minv && B.x && B.r && B.z && B.p && B.ap && B.partial && B.scal && B.state,
+                "batch buffers missing");
+    MOF_REQUIRE(tol > 0 && max_iter >= 0, "bad tol / max_iter");
+    if (check_every <= 0) check_every = 25;
+    cudaStream_t st = mof_stream(stream);
+    const int64_t N = mesh->n_vertices, nb = mesh->n_blocks;
+    const int G = B.n_groups;
+    const int ntiles = (int)mof_num_tiles(N);
+    const double tol2 = tol * tol;
+    dim3 grid(ntiles, G);
+    int32_t* d_active_groups = B.state + (size_t)G * MOF_I_COUNT * MOF_W + 2 * (size_t)G;
+
+    // group_done, tickets, groups_active <- 0
+    MOF_CUDA_TRY(cudaMemsetAsync(B.state + (size_t)G * MOF_I_COUNT * MOF_W, 0, (2 * (size_t)G + 1) * sizeof(int32_t), st));
+    init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, 0, tol2);
+    MOF_LAUNCH_CHECK("init_kernel");
+
+    int32_t h_active = 0;
+    MOF_CUDA_TRY(cudaMemcpyAsync(&h_active, d_active_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MOF_CUDA_TRY(cudaStreamSynchronize(st));
+    int it = 0, restarts = 0;
+    for (;;) {
+        while (h_active > 0 && it < max_iter) {
+            const int n = (max_iter - it) < check_every ? (max_iter - it) : check_every;
+            for (int q = 0; q < n; ++q) {
+                spmv_kernel<true><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.p, B.ap, N, nb, ntiles,
+                                                       B.partial, B.scal, B.state, G);
+                update_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, tol2);
+                pupdate_kernel<<<grid, 256, 0, st>>>(B, N);
+            }
+            MOF_LAUNCH_CHECK("pcg iteration kernels");
+            it += n;
+            MOF_CUDA_TRY(cudaMemcpyAsync(&h_active, d_active_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            MOF_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        // confirm on the true residual b - A x; frames whose recurrence drifted restart
+        spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.x, B.ap, N, nb, ntiles, nullptr,
+                                                nullptr, nullptr, G);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, 1, tol2);
+        MOF_LAUNCH_CHECK("verification kernels");
+        MOF_CUDA_TRY(cudaMemcpyAsync(&h_active, d_active_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MOF_CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_active <= 0 || it >= max_iter || restarts >= max_restarts) break;
+        ++restarts;
+    }
+
+    // per-frame report
+    const size_t nf = (size_t)G * MOF_W;
+    int32_t* h_state = (int32_t*)malloc(nf * MOF_I_COUNT * sizeof(int32_t));
+    double* h_scal = (double*)malloc(nf * MOF_S_COUNT * sizeof(double));
+    if (!h_state || !h_scal) { free(h_state); free(h_scal); return mof_set_error(-3, "out of host memory"); }
+    cudaError_t e1 = cudaMemcpyAsync(h_state, B.state, nf * MOF_I_COUNT * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaMemcpyAsync(h_scal, B.scal, nf * MOF_S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    int worst = 0;
+    if (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
+        for (int g = 0; g < G; ++g)
+            for (int l = 0; l < MOF_W; ++l) {
+                const size_t k = (size_t)g * MOF_W + l;
+                int32_t s = h_state[((size_t)g * MOF_I_COUNT + MOF_I_STATUS) * MOF_W + l];
+                if (s == MOF_STATUS_PENDING) s = MOF_STATUS_MAXITER;
+                const double bb = h_scal[((size_t)g * MOF_S_COUNT + MOF_S_BB) * MOF_W + l];
+                const double rt = h_scal[((size_t)g * MOF_S_COUNT + MOF_S_RRTRUE) * MOF_W + l];
+                if (iters) iters[k] = h_state[((size_t)g * MOF_I_COUNT + MOF_I_ITERS) * MOF_W + l];
+                if (relres) relres[k] = bb > 0 ? sqrt(rt / bb) : 0.0;
+                if (status) status[k] = s;
+                if ((int64_t)k < B.n_frames && s != MOF_STATUS_CONVERGED && s != MOF_STATUS_ZERO_RHS && s > worst) worst = s;
+            }
+    }
+    free(h_state);
+    free(h_scal);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return mof_set_error(-100, "mof_pcg_solve_batch: report copy failed: %s",
+                             cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    if (worst) mof_set_error(worst, "mof_pcg_solve_batch: at least one frame did not converge (status %d)", worst);
+    return worst;
+}

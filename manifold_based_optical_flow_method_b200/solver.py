@@ -1,0 +1,162 @@
+"""Frame-batch driver: pack -> assemble (K1) -> batched PCG (K2/K3) -> unpack.
+
+Host orchestration only (PyTorch provides device memory and streams); all arithmetic is in
+libmof_b200.so.  Replaces the multiprocessing fan-out of compute_velocity_field
+(utils/compute_optical_flow.py:152-194) and the per-frame worker (:100-149).
+"""
+import ctypes
+import dataclasses
+
+import numpy as np
+
+from . import _lib
+from ._lib import GROUP
+
+DEFAULT_TOL = 1e-12          # ||b - A x|| / ||b||, north-star parity setting
+DEFAULT_MAX_ITER = 20000
+DEFAULT_CHECK_EVERY = 32
+DEFAULT_MAX_RESTARTS = 3
+DEFAULT_BATCH_GROUPS = 8     # 8 x 32 = 256 frames per launch (~15 GB at 164k vertices)
+
+
+@dataclasses.dataclass
+class SolveInfo:
+    """Per-frame solver report (the reference's spsolve returns nothing comparable)."""
+    iterations: np.ndarray      # (n_frames,) int32
+    relres: np.ndarray          # (n_frames,) true ||b - A x|| / ||b||
+    status: np.ndarray          # (n_frames,) _lib.STATUS_*
+    seconds: float = 0.0
+
+    @property
+    def converged(self):
+        return bool(np.all((self.status == _lib.STATUS_CONVERGED) | (self.status == _lib.STATUS_ZERO_RHS)))
+
+
+class UnconvergedError(RuntimeError):
+    def __init__(self, info, frames):
+        self.info, self.frames = info, frames
+        super().__init__(
+            f"{len(frames)} frame(s) did not converge (first: frame {frames[0]}, status {int(info.status[frames[0]])}, "
+            f"relres {info.relres[frames[0]]:.3e}, {int(info.iterations[frames[0]])} iterations)")
+
+
+class FrameBatch:
+    """Device buffers of one batch of ``n_groups`` x 32 frames (mof_batch_dev)."""
+
+    def __init__(self, op, n_groups):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        self.op, self.n_groups = op, int(n_groups)
+        N, nb, G, W = op.n_vertices, op.n_blocks, self.n_groups, GROUP
+        dev = op.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.n_tiles = int(lib.mof_num_tiles(N))
+        self.It = torch.empty((G, N, W), **f64)
+        self.dIt = torch.empty((G, N, W), **f64)
+        self.vals = torch.empty((G, nb, 4, W), **f64)
+        self.rhs = torch.empty((G, N, 2, W), **f64)
+        self.minv = torch.empty((G, N, 3, W), **f64)
+        self.x = torch.empty((G, N, 2, W), **f64)
+        self.r = torch.empty((G, N, 2, W), **f64)
+        self.z = torch.empty((G, N, 2, W), **f64)
+        self.p = torch.empty((G, N, 2, W), **f64)
+        self.ap = torch.empty((G, N, 2, W), **f64)
+        self.partial = torch.zeros((G, self.n_tiles, 2, W), **f64)
+        self.scal = torch.zeros((G, 8, W), **f64)
+        self.state = torch.zeros((int(lib.mof_state_ints(G)),), dtype=torch.int32, device=dev)
+        self.n_frames = 0
+
+    def struct(self, n_frames=None, n_groups=None):
+        """Descriptor for the first ``n_groups`` groups (every buffer is group-major, so a
+        prefix of the allocation is a valid smaller batch)."""
+        if n_frames is not None:
+            self.n_frames = int(n_frames)
+        G = self.n_groups if n_groups is None else int(n_groups)
+        assert 0 < G <= self.n_groups and self.n_frames <= G * GROUP
+        return _lib.BatchDev(
+            G, self.n_frames, self.It.data_ptr(), self.dIt.data_ptr(), self.vals.data_ptr(),
+            self.rhs.data_ptr(), self.minv.data_ptr(), self.x.data_ptr(), self.r.data_ptr(), self.z.data_ptr(),
+            self.p.data_ptr(), self.ap.data_ptr(), self.partial.data_ptr(), self.scal.data_ptr(), self.state.data_ptr())
+
+    @staticmethod
+    def bytes_per_group(n_vertices, n_blocks):
+        return 8 * GROUP * (4 * n_blocks + n_vertices * (2 + 2 * 6 + 3))
+
+
+class VelocitySolver:
+    """Solves batches of frames on one GPU.  Buffers are allocated once and reused."""
+
+    def __init__(self, op, batch_groups=None, tol=DEFAULT_TOL, max_iter=DEFAULT_MAX_ITER,
+                 check_every=DEFAULT_CHECK_EVERY, max_restarts=DEFAULT_MAX_RESTARTS):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.load()
+        self.op = op
+        self.tol, self.max_iter, self.check_every, self.max_restarts = tol, max_iter, check_every, max_restarts
+        if batch_groups is None:
+            free, _total = self.torch.cuda.mem_get_info(op.device)
+            per_group = FrameBatch.bytes_per_group(op.n_vertices, op.n_blocks)
+            batch_groups = max(1, min(DEFAULT_BATCH_GROUPS, int(0.6 * free) // max(per_group, 1)))
+        self.batch_groups = int(batch_groups)
+        self._batch = None
+
+    def batch(self, n_groups):
+        if self._batch is None or self._batch.n_groups < n_groups:
+            self._batch = None
+            self._batch = FrameBatch(self.op, n_groups)
+        return self._batch
+
+    def assemble(self, batch, I_now, I_next, dt, lambda_, n_frames):
+        """pack + K1 for the first n_frames rows of I_now / I_next (device, (>=n_frames, N))."""
+        torch, lib, op = self.torch, self.lib, self.op
+        st = torch.cuda.current_stream(op.device).cuda_stream
+        ms, bs = op.struct(), batch.struct(n_frames, (int(n_frames) + GROUP - 1) // GROUP)
+        assert I_now.stride(1) == 1 and I_next.stride(1) == 1
+        assert I_now.stride(0) == I_next.stride(0)
+        _lib.check(lib.mof_pack_frames(ctypes.byref(ms), ctypes.byref(bs), I_now.data_ptr(), I_next.data_ptr(),
+                                       I_now.stride(0), dt.data_ptr(), st))
+        _lib.check(lib.mof_assemble_batch(ctypes.byref(ms), ctypes.byref(bs), float(lambda_), st))
+        return ms, bs
+
+    def solve_batch(self, I_now, I_next, dt, lambda_, V_out):
+        """One batch: frames = rows of I_now.  V_out: device (n_frames, 2N) view.  -> SolveInfo"""
+        torch, lib, op = self.torch, self.lib, self.op
+        n_frames = int(I_now.shape[0])
+        G = (n_frames + GROUP - 1) // GROUP
+        batch = self.batch(G)
+        st = torch.cuda.current_stream(op.device).cuda_stream
+        ms, bs = self.assemble(batch, I_now, I_next, dt, lambda_, n_frames)
+        iters = np.zeros(G * GROUP, np.int32)
+        relres = np.zeros(G * GROUP, np.float64)
+        status = np.zeros(G * GROUP, np.int32)
+        _lib.check(lib.mof_pcg_solve_batch(ctypes.byref(ms), ctypes.byref(bs), float(self.tol), int(self.max_iter),
+                                           int(self.check_every), int(self.max_restarts), iters.ctypes.data,
+                                           relres.ctypes.data, status.ctypes.data, st), allow_positive=True)
+        assert V_out.stride(1) == 1
+        _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
+        return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames])
+
+    def solve_frames(self, I_dev, I2_dev, dt_dev, lambda_, V_dev=None):
+        """All frames k = 0 .. n-1 with (I_dev[k], I2_dev[k+1]) (compute_optical_flow.py:174-175).
+        I_dev, I2_dev: device (>= n+1, N) float64 (may be the same tensor); dt_dev: device (n,).
+        -> (V_dev (n, 2N) device, SolveInfo)"""
+        torch, op = self.torch, self.op
+        n = int(dt_dev.shape[0])
+        if V_dev is None:
+            V_dev = torch.empty((n, 2 * op.n_vertices), dtype=torch.float64, device=op.device)
+        infos = []
+        step = self.batch_groups * GROUP
+        for k0 in range(0, n, step):
+            k1 = min(n, k0 + step)
+            infos.append(self.solve_batch(I_dev[k0:k1], I2_dev[k0 + 1:k1 + 1], dt_dev[k0:k1], lambda_, V_dev[k0:k1]))
+        if infos:
+            info = SolveInfo(np.concatenate([i.iterations for i in infos]), np.concatenate([i.relres for i in infos]),
+                             np.concatenate([i.status for i in infos]))
+        else:
+            info = SolveInfo(np.zeros(0, np.int32), np.zeros(0), np.zeros(0, np.int32))
+        return V_dev, info
+
+
+def frame_dt(t_k, k0, k1):
+    """dt[k] = t_k[k+1] - t_k[k] evaluated in fp64 exactly like the reference's
+    ``t_k[k + 1] - t_k[k]`` on Python floats (compute_optical_flow.py:125)."""
+    return np.array([t_k[k + 1] - t_k[k] for k in range(k0, k1)], dtype=np.float64)

@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE ONLY (built by tests/hostcheck/__init__.py with g++, no CUDA).
+// Wraps the __host__ __device__ kernel bodies of csrc/mof_bodies.h in plain loops with
+// the same frame-minor layout as the CUDA kernels, so that indexing and operation order
+// can be checked against the oracle in the GPU-less build container.  The product
+// library (libmof_b200.so) never runs these loops; its entry points launch CUDA kernels.
+#include <cstdint>
+#include <cstring>
+
+#include "mof_b200.h"
+#include "mof_bodies.h"
+
+extern "C" {
+
+void hc_geom(const mof_mesh_dev* M, const double* coords, const double* normals, double* e, double* grad_w,
+             double* integral) {
+    for (int64_t v = 0; v < M->n_vertices; ++v) mof_basis_body(normals + 3 * v, e + 6 * v);
+    for (int64_t f = 0; f < M->n_faces; ++f) mof_face_geom_body(coords, M->tri, M->areas, f, grad_w, integral);
+}
+
+void hc_a2(const mof_mesh_dev* M, double* a2v) {
+    for (int64_t v = 0; v < M->n_vertices; ++v)
+        for (int32_t b = M->rowptr[v]; b < M->rowptr[v + 1]; ++b) mof_a2_block_body(*M, v, b, a2v + 4 * b);
+}
+
+// It/dIt [G][N][32] from (n_frames, N) rows (pack_kernel)
+void hc_pack(const mof_mesh_dev* M, int32_t G, int32_t n_frames, const double* I_now, const double* I_next, int64_t ld,
+             const double* dt, double* It, double* dIt) {
+    const int64_t N = M->n_vertices;
+    for (int64_t g = 0; g < G; ++g)
+        for (int64_t v = 0; v < N; ++v)
+            for (int l = 0; l < MOF_W; ++l) {
+                int64_t k = g * MOF_W + l;
+                double a = 0, d = 0;
+                if (k < n_frames) {
+                    a = I_now[k * ld + M->perm[v]];
+                    d = (I_next[k * ld + M->perm[v]] - a) / dt[k];
+                }
+                It[mof_ix_sca(N, g, v) + l] = a;
+                dIt[mof_ix_sca(N, g, v) + l] = d;
+            }
+}
+
+void hc_assemble(const mof_mesh_dev* M, int32_t G, const double* It, const double* dIt, double lambda_, double* vals,
+                 double* rhs, double* minv) {
+    const int64_t N = M->n_vertices, nb = M->n_blocks;
+    for (int64_t g = 0; g < G; ++g)
+        for (int l = 0; l < MOF_W; ++l) {
+            const double* It_l = It + mof_ix_sca(N, g, 0) + l;
+            const double* dIt_l = dIt + mof_ix_sca(N, g, 0) + l;
+            for (int64_t v = 0; v < N; ++v)
+                for (int32_t b = M->rowptr[v]; b < M->rowptr[v + 1]; ++b) {
+                    double a[4], f[2];
+                    if (b == M->diag[v]) {
+                        mof_assemble_block_body<true>(*M, v, b, It_l, dIt_l, lambda_, a, f);
+                        double mi[3];
+                        mof_inv2_body(a, mi);
+                        for (int c = 0; c < 2; ++c) rhs[mof_ix_vec(N, g, v, c) + l] = f[c];
+                        for (int c = 0; c < 3; ++c) minv[mof_ix_minv(N, g, v, c) + l] = mi[c];
+                    } else {
+                        mof_assemble_block_body<false>(*M, v, b, It_l, dIt_l, lambda_, a, f);
+                    }
+                    for (int c = 0; c < 4; ++c) vals[mof_ix_val(nb, g, b, c) + l] = a[c];
+                }
+        }
+}
+
+void hc_spmv(const mof_mesh_dev* M, int32_t G, const double* vals, const double* x, double* y) {
+    const int64_t N = M->n_vertices, nb = M->n_blocks;
+    for (int64_t g = 0; g < G; ++g)
+        for (int l = 0; l < MOF_W; ++l)
+            for (int64_t v = 0; v < N; ++v) {
+                double y0 = 0, y1 = 0;
+                for (int32_t b = M->rowptr[v]; b < M->rowptr[v + 1]; ++b) {
+                    int64_t j = M->col[b];
+                    double x0 = x[mof_ix_vec(N, g, j, 0) + l], x1 = x[mof_ix_vec(N, g, j, 1) + l];
+                    y0 += vals[mof_ix_val(nb, g, b, 0) + l] * x0 + vals[mof_ix_val(nb, g, b, 1) + l] * x1;
+                    y1 += vals[mof_ix_val(nb, g, b, 2) + l] * x0 + vals[mof_ix_val(nb, g, b, 3) + l] * x1;
+                }
+                y[mof_ix_vec(N, g, v, 0) + l] = y0;
+                y[mof_ix_vec(N, g, v, 1) + l] = y1;
+            }
+}
+
+void hc_tangent(int64_t N, int64_t n_frames, const double* V, int64_t ldV, const double* e, double* Vxyz, double* speed,
+                double* vmax) {
+    for (int64_t k = 0; k < n_frames; ++k) {
+        double mx = 0;
+        for (int64_t i = 0; i < N; ++i) {
+            double* o = Vxyz + (k * N + i) * 3;
+            mof_tangent_body(V[k * ldV + i], V[k * ldV + N + i], e + 6 * i, o);
+            double len = mof_len3_body(o);
+            speed[k * N + i] = len;
+            if (!(len <= mx)) mx = len;
+        }
+        vmax[k] = mx;
+    }
+}
+
+// one frame; returns counts; lists ascending
+void hc_detect(int64_t N, int64_t F, const double* coords, const int32_t* tri, const double* Vxyz, double vmax, double eps,
+               int32_t* nv, int32_t* vidx, int32_t* nf, int32_t* fidx, double* lam_mu, int8_t* sign) {
+    uint8_t* vf = new uint8_t[N];
+    *nv = *nf = 0;
+    for (int64_t i = 0; i < N; ++i) {
+        vf[i] = mof_vertex_zero_body(Vxyz + 3 * i, vmax, eps);
+        if (vf[i]) vidx[(*nv)++] = (int32_t)i;
+    }
+    for (int64_t t = 0; t < F; ++t) {
+        int64_t a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+        if (vf[a] | vf[b] | vf[c]) continue;
+        double l, m;
+        int s;
+        if (mof_face_zero_body(coords + 3 * a, coords + 3 * b, coords + 3 * c, Vxyz + 3 * a, Vxyz + 3 * b, Vxyz + 3 * c, vmax,
+                               &l, &m, &s)) {
+            fidx[*nf] = (int32_t)t;
+            lam_mu[2 * *nf] = l;
+            lam_mu[2 * *nf + 1] = m;
+            sign[*nf] = (int8_t)s;
+            ++*nf;
+        }
+    }
+    delete[] vf;
+}
+}

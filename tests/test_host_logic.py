@@ -1,0 +1,284 @@
+"""CPU-only tests (no GPU): the C-ABI library loads and exports every declared symbol, the
+host-side pattern builder is correct, and the kernel bodies of csrc/mof_bodies.h -- run
+through the test-only loop harness tests/hostcheck -- reproduce the reference's golden
+outputs with the same frame-minor layout the CUDA kernels use."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import ROOT, load_golden, rel_l2
+from manifold_based_optical_flow_method_b200 import _lib, synthetic
+from manifold_based_optical_flow_method_b200.mesh import Pattern
+from manifold_based_optical_flow_method_b200.solver import frame_dt
+
+import hostcheck
+
+W = _lib.GROUP
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "mof_b200.h")).read()
+    declared = set(re.findall(r"\b(mof_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mof_version() >= 100
+    assert lib.mof_num_tiles(129) == 3
+    assert lib.mof_state_ints(2) == 2 * 4 * 32 + 2 * 2 + 1
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8
+    assert ctypes.sizeof(_lib.BatchDev) == 8 + 13 * 8
+
+
+@pytest.mark.parametrize("reorder", [False, True])
+@pytest.mark.parametrize("mesh", ["ico2", "patch", "two"])
+def test_pattern(mesh, reorder):
+    if mesh == "ico2":
+        coords, tris, _, _ = synthetic.icosphere(2)
+    elif mesh == "patch":
+        coords, tris, _, _ = synthetic.open_patch(9, seed=1)
+    else:
+        coords, tris, _, _ = synthetic.two_hemispheres(2)
+    N, F = len(coords), len(tris)
+    P = Pattern(N, tris, reorder=reorder)
+    e = np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]])
+    e.sort(axis=1)
+    E = len(np.unique(e, axis=0))
+    assert P.n_blocks == N + 2 * E and P.n_contrib == 9 * F
+    assert np.array_equal(np.sort(P.perm), np.arange(N))
+    if not reorder:
+        assert np.array_equal(P.perm, np.arange(N))
+    assert np.array_equal(P.perm[P.tri], tris)
+    rows = P.block_rows()
+    for v in range(N):
+        c = P.col[P.rowptr[v]:P.rowptr[v + 1]]
+        assert np.all(np.diff(c) > 0)
+        assert P.col[P.diag[v]] == v
+    # adjacency equals mesh edges
+    pairs = set(map(tuple, np.stack([P.perm[rows], P.perm[P.col]], axis=1)))
+    want = {(i, i) for i in range(N)} | {(a, b) for a, b in e} | {(b, a) for a, b in e}
+    assert pairs == want
+    # contributor lists: ascending faces, (m, n) are the positions of (row, col) in the face
+    for b in range(P.n_blocks):
+        ent = P.centry[P.cptr[b]:P.cptr[b + 1]]
+        f, m, n = ent >> 4, (ent >> 2) & 3, ent & 3
+        assert np.all(np.diff(f) > 0) and len(f) >= 1
+        assert np.all(P.tri[f, m] == rows[b]) and np.all(P.tri[f, n] == P.col[b])
+    assert np.sum(np.diff(P.cptr)) == 9 * F
+    assert P.max_row_blocks == np.max(np.diff(P.rowptr))
+
+
+def test_pattern_reorder_reduces_bandwidth():
+    coords, tris, _, _ = synthetic.icosphere(4)
+    p0 = Pattern(len(coords), tris, reorder=False)
+    p1 = Pattern(len(coords), tris, reorder=True)
+    assert p1.bandwidth < p0.bandwidth / 4
+
+
+def test_pattern_rejects_bad_faces():
+    with pytest.raises(_lib.MofError):
+        Pattern(4, np.array([[0, 1, 4]]))
+    with pytest.raises(_lib.MofError):
+        Pattern(4, np.array([[0, 1, 1]]))
+    with pytest.raises(ValueError):
+        Pattern(4, np.array([[0, 1, 2, 3]]))
+
+
+def test_block_csr_roundtrip():
+    coords, tris, _, _ = synthetic.icosphere(1)
+    P = Pattern(len(coords), tris)
+    vals = np.random.default_rng(0).standard_normal((P.n_blocks, 4))
+    m = P.block_values_to_csr(vals)
+    assert m.shape == (2 * len(coords),) * 2 and m.nnz == 4 * P.n_blocks
+    assert np.array_equal(P.csr_to_block_values(m), vals)
+
+
+# ---------------------------------------------------------------------------------
+# kernel bodies through the loop harness
+# ---------------------------------------------------------------------------------
+class HostMesh:
+    """numpy-backed mof_mesh_dev for the harness"""
+
+    def __init__(self, g, reorder=True):
+        self.hc = hostcheck.load()
+        self.coords, self.tris = g["coordinates"], g["triangles"]
+        N = len(self.coords)
+        self.P = P = Pattern(N, self.tris, reorder=reorder)
+        self.areas = np.ascontiguousarray(g["areas"], dtype=np.float64)
+        self.e = np.zeros((N, 2, 3))
+        self.grad_w = np.zeros((P.n_faces, 3, 3))
+        self.integral = np.zeros((P.n_faces, 2))
+        self.a2v = np.zeros((P.n_blocks, 4))
+        self.cint = np.ascontiguousarray(self.coords[P.perm])
+        self.nint = np.ascontiguousarray(g["normals"][P.perm])
+        ms = self.struct()
+        self.hc.hc_geom(ctypes.byref(ms), self.cint.ctypes.data, self.nint.ctypes.data, self.e.ctypes.data,
+                        self.grad_w.ctypes.data, self.integral.ctypes.data)
+        self.hc.hc_a2(ctypes.byref(ms), self.a2v.ctypes.data)
+
+    def struct(self):
+        P = self.P
+        p = lambda a: a.ctypes.data
+        return _lib.MeshDev(P.n_vertices, P.n_faces, P.n_blocks, P.n_contrib, p(P.perm), p(P.rowptr), p(P.col), p(P.diag),
+                            p(P.cptr), p(P.centry), p(P.tri), p(self.e), p(self.grad_w), p(self.integral), p(self.areas),
+                            p(self.a2v))
+
+    def assemble(self, I, t_k, lambda_):
+        P, hc = self.P, self.hc
+        n = len(I) - 1
+        G = -(-n // W)
+        N, nb = P.n_vertices, P.n_blocks
+        dt = frame_dt(list(t_k), 0, n)
+        I = np.ascontiguousarray(I, dtype=np.float64)
+        It, dIt = np.zeros((G, N, W)), np.zeros((G, N, W))
+        vals, rhs, minv = np.zeros((G, nb, 4, W)), np.zeros((G, N, 2, W)), np.zeros((G, N, 3, W))
+        ms = self.struct()
+        hc.hc_pack(ctypes.byref(ms), G, n, I.ctypes.data, I[1:].ctypes.data, ctypes.c_int64(I.shape[1]), dt.ctypes.data,
+                   It.ctypes.data, dIt.ctypes.data)
+        hc.hc_assemble(ctypes.byref(ms), G, It.ctypes.data, dIt.ctypes.data, ctypes.c_double(lambda_), vals.ctypes.data,
+                       rhs.ctypes.data, minv.ctypes.data)
+        return vals, rhs, minv
+
+
+def _frame_matrix(P, vals, k):
+    return P.block_values_to_csr(vals[k // W, :, :, k % W])
+
+
+def _frame_vector(P, vec, k):
+    """[G][N][2][W] internal -> (2N,) reference order"""
+    N = P.n_vertices
+    out = np.empty(2 * N)
+    out[P.perm] = vec[k // W, :, 0, k % W]
+    out[P.perm + N] = vec[k // W, :, 1, k % W]
+    return out
+
+
+@pytest.mark.parametrize("reorder", [False, True])
+def test_bodies_geometry_and_assembly_match_reference(golden, reorder):
+    g = golden
+    hm = HostMesh(g, reorder)
+    P = hm.P
+    N = P.n_vertices
+    e_ref = np.empty_like(hm.e)
+    e_ref[:] = g["e"][P.perm]
+    assert np.max(np.abs(hm.e - e_ref)) <= 1e-15
+    assert rel_l2(hm.grad_w, g["grad_w"]) <= 1e-15
+    assert np.array_equal(hm.integral, g["integral_wi_wj"])
+    if "a2_data" in g:
+        a2_ref = sp.csr_matrix((g["a2_data"], g["a2_indices"], g["a2_indptr"]), shape=(2 * N, 2 * N))
+        a2 = P.block_values_to_csr(hm.a2v)
+        assert abs(a2 - a2_ref).max() <= 1e-14 * abs(a2_ref).max()
+    vals, rhs, minv = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]))
+    if "a0_data" in g:
+        a_ref = sp.csr_matrix((g["a0_data"], g["a0_indices"], g["a0_indptr"]), shape=(2 * N, 2 * N))
+        a = _frame_matrix(P, vals, 0)
+        assert abs(a - a_ref).max() <= 1e-14 * abs(a_ref).max()
+        assert abs(a - a.T).max() == 0.0            # exactly symmetric, like the reference's mirror assignment
+        assert rel_l2(_frame_vector(P, rhs, 0), g["f0"]) <= 1e-14
+    # solving the harness-assembled system reproduces the reference's velocity field
+    from scipy.sparse.linalg import spsolve
+    for k in range(len(g["V_k"])):
+        V = spsolve(sp.csc_matrix(_frame_matrix(P, vals, k)), _frame_vector(P, rhs, k))
+        assert rel_l2(V, g["V_k"][k]) <= (1e-9 if "phase" in g["name"] else 1e-11)
+    # block-Jacobi inverse
+    k = 0
+    a = _frame_matrix(P, vals, k).toarray()
+    for v in (0, N // 2, N - 1):
+        o = P.perm[v]
+        D = a[np.ix_([o, o + N], [o, o + N])]
+        Mi = np.array([[minv[0, v, 0, 0], minv[0, v, 1, 0]], [minv[0, v, 1, 0], minv[0, v, 2, 0]]])
+        assert np.allclose(Mi @ D, np.eye(2), atol=1e-12)
+    # padding lanes are zero
+    n = len(g["V_k"])
+    assert np.all(rhs[-1, :, :, n % W:] == 0) if n % W else True
+
+
+def test_bodies_spmv_matches_scipy():
+    g = load_golden("ico2_wave")
+    hm = HostMesh(g)
+    P = hm.P
+    N, nb = P.n_vertices, P.n_blocks
+    vals, rhs, _ = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]))
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((1, N, 2, W))
+    y = np.zeros_like(x)
+    ms = hm.struct()
+    hm.hc.hc_spmv(ctypes.byref(ms), 1, vals.ctypes.data, x.ctypes.data, y.ctypes.data)
+    for k in range(len(g["V_k"])):
+        a = _frame_matrix(P, vals, k)
+        assert rel_l2(_frame_vector(P, y, k), a @ _frame_vector(P, x, k)) <= 1e-14
+
+
+def test_bodies_tangent_and_detection_match_reference(golden):
+    g = golden
+    hc = hostcheck.load()
+    N, F = len(g["coordinates"]), len(g["triangles"])
+    V = np.ascontiguousarray(g["V_k"])
+    n = len(V)
+    e = np.ascontiguousarray(g["e"])
+    Vxyz, speed, vmax = np.zeros((n, N, 3)), np.zeros((n, N)), np.zeros(n)
+    hc.hc_tangent(ctypes.c_int64(N), ctypes.c_int64(n), V.ctypes.data, ctypes.c_int64(2 * N), e.ctypes.data,
+                  Vxyz.ctypes.data, speed.ctypes.data, vmax.ctypes.data)
+    assert np.array_equal(Vxyz, g["V_xyz"])                      # bit-exact (separate mul/add like numpy)
+    assert np.array_equal(vmax, g["v_length_max"])
+    assert np.array_equal(speed, np.sqrt(np.sum(g["V_xyz"] ** 2, axis=2)))
+    coords = np.ascontiguousarray(g["coordinates"])
+    tri = np.ascontiguousarray(g["triangles"], dtype=np.int32)
+    off_v = off_f = 0
+    for k in range(n):
+        nv, nf = ctypes.c_int32(), ctypes.c_int32()
+        vidx, fidx = np.zeros(N, np.int32), np.zeros(F, np.int32)
+        lam_mu, sign = np.zeros((F, 2)), np.zeros(F, np.int8)
+        hc.hc_detect(ctypes.c_int64(N), ctypes.c_int64(F), coords.ctypes.data, tri.ctypes.data, Vxyz[k].ctypes.data,
+                     ctypes.c_double(vmax[k]), ctypes.c_double(float(g["eps"])), ctypes.byref(nv), vidx.ctypes.data,
+                     ctypes.byref(nf), fidx.ctypes.data, lam_mu.ctypes.data, sign.ctypes.data)
+        cv, cf = g["sing_counts"][k]
+        assert nv.value == cv and nf.value == cf
+        assert np.array_equal(vidx[:cv], g["sing_vertex_idx"][off_v:off_v + cv])
+        assert np.array_equal(fidx[:cf], g["sing_face_idx"][off_f:off_f + cf])
+        assert np.allclose(lam_mu[:cf], g["sing_face_lam_mu"][off_f:off_f + cf], rtol=0, atol=1e-10)
+        assert np.all(np.abs(sign[:cf]) == 1)
+        off_v += cv
+        off_f += cf
+
+
+def test_bodies_detection_with_singular_vertices():
+    g = load_golden("ico2_vertex_singular")
+    hc = hostcheck.load()
+    coords = np.ascontiguousarray(g["coordinates"])
+    tri = np.ascontiguousarray(g["triangles"], dtype=np.int32)
+    N, F = len(coords), len(tri)
+    V = np.ascontiguousarray(g["V_now"])
+    nv, nf = ctypes.c_int32(), ctypes.c_int32()
+    vidx, fidx = np.zeros(N, np.int32), np.zeros(F, np.int32)
+    lam_mu, sign = np.zeros((F, 2)), np.zeros(F, np.int8)
+    hc.hc_detect(ctypes.c_int64(N), ctypes.c_int64(F), coords.ctypes.data, tri.ctypes.data, V.ctypes.data,
+                 ctypes.c_double(float(g["v_length_max"])), ctypes.c_double(float(g["eps"])), ctypes.byref(nv),
+                 vidx.ctypes.data, ctypes.byref(nf), fidx.ctypes.data, lam_mu.ctypes.data, sign.ctypes.data)
+    assert np.array_equal(vidx[:nv.value], g["sing_vertex_idx"])
+    assert np.array_equal(fidx[:nf.value], g["sing_face_idx"])
+
+
+def test_frame_dt_matches_python_float_arithmetic():
+    t_k = synthetic.time_axis(50, 512.0)
+    dt = frame_dt(t_k, 3, 40)
+    assert all(dt[i] == t_k[3 + i + 1] - t_k[3 + i] for i in range(37))
+
+
+def test_product_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow, find_singularity_point
+    coords, tris, normals, areas = synthetic.icosphere(1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        compute_optical_flow.compute_geometrical_quantities(coords, normals, tris, areas)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        find_singularity_point.process_V_k(np.zeros((1, 84)), np.zeros((42, 2, 3)))
