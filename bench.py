@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame velocity-field solve (assemble + batched PCG) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Metric (BASELINE.json): velocity-field frames/sec on the ~160k-vertex pial-like mesh
+(configs[1]: ico7 topology, N = 163,842, 1000-frame signal -> 999 solves per step per GPU;
+with N GPUs every rank solves its own 1000-frame shard of an N*1000-frame signal: weak
+scaling, no data-path collective).  One JSON line on stdout (rank 0).
+
+  value     frames/s with the signal already resident in HBM (device-timed, max over ranks)
+  e2e       frames/s through the reference-shaped API with HOST buffers: pinned H2D of the
+            signal, solve, D2H of the velocity fields (and the NCCL gather for N > 1)
+  roofline  SpMV kernel: algorithmic bytes / CUDA-event time sampled live inside the timed
+            region (one iteration per check interval), against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference algorithm (vectorised assembly + SuperLU
+            spsolve, one process per frame like the reference's Pool) on the host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+LAMBDA = 0.01     # reference config.yaml:3
+SF = 512.0
+METRIC = "velocity-field frames/sec @160k-vertex mesh (assemble+solve)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--level", type=int, default=7, help="icosphere level of the pial-like mesh (7 = 163,842 vertices)")
+    ap.add_argument("--frames", type=int, default=1000, help="frames of signal per GPU (frames-1 solves per step)")
+    ap.add_argument("--batch-groups", type=int, default=None)
+    ap.add_argument("--tol", type=float, default=1e-12)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=None)
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-clock budget of the reference arm")
+    return ap.parse_args()
+
+
+def workload_name(args, n_gpus):
+    return (f"C2/C3 pial-like ico{args.level} mesh, {args.frames}-frame travelling-wave signal per GPU "
+            f"({args.frames - 1} solves/step/GPU, {n_gpus} GPU(s)), lambda={LAMBDA}, PCG tol={args.tol:g}")
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference algorithm, one process per frame
+# --------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_frame(k):
+    from oracle import mof_oracle
+    c = _CPU
+    return mof_oracle.worker(k, c["a2"], c["gw"], c["e"], c["integ"], c["tris"], c["t_k"], c["areas"], LAMBDA,
+                             c["I"][k], c["I"][k + 1])[:4].copy()
+
+
+def cpu_procs(requested=None):
+    n = os.cpu_count() or 1
+    try:
+        import psutil
+        n = min(n, max(1, int(psutil.virtual_memory().available / 3.0e9)))   # ~2.1 GB RSS per SuperLU solve at 164k
+    except Exception:
+        pass
+    n = min(n, 32)
+    return max(1, min(n, requested)) if requested else n
+
+
+def cpu_wave(mesh, I, t_k, procs):
+    """One wave of `procs` frames (assemble + spsolve each) on `procs` processes -> (frames/s, seconds)."""
+    import multiprocessing
+    from oracle import mof_oracle
+    coords, tris, normals, areas = mesh
+    if "a2" not in _CPU:
+        a2, gw, e, integ = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+        _CPU.update(a2=a2, gw=gw, e=e, integ=integ, tris=tris, areas=areas)
+    _CPU.update(t_k=t_k, I=I)
+    ctx = multiprocessing.get_context("fork")
+    t0 = time.time()
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_frame, range(procs), chunksize=1)
+    secs = time.time() - t0
+    return procs / secs, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from manifold_based_optical_flow_method_b200 import synthetic
+    mesh = synthetic.pial_like(args.level)
+    procs = cpu_procs(args.cpu_procs)
+    t_k = synthetic.time_axis(procs + 1, SF)
+    I = synthetic.travelling_wave(mesh[0], t_k, seed=0)
+    t_start = time.time()
+    fps, secs = cpu_wave(mesh, I, t_k, procs)          # first wave doubles as the size probe
+    warm_done = 1
+    # honour --steps / --warmup as far as the wall-clock budget allows (one wave is ~1 min at
+    # 164k vertices); timed steps take precedence over further warm-up waves
+    budget_waves = max(2, int(args.ref_budget_s / max(secs, 1e-3)))
+    steps = max(1, min(args.steps, budget_waves - warm_done))
+    warm = max(0, min(args.warmup - warm_done, budget_waves - warm_done - steps))
+    for _ in range(warm):
+        cpu_wave(mesh, I, t_k, procs)
+    total = 0.0
+    for _ in range(steps):
+        _, s = cpu_wave(mesh, I, t_k, procs)
+        total += s
+    value = procs * steps / total
+    sample = (f"one wave of {procs} frames on {procs} processes per step (assemble + SuperLU spsolve per frame), "
+              f"N={len(mesh[0])}; {steps} timed step(s), {warm_done + warm} warm-up wave(s); frames are independent, so "
+              "frames/s of a wave is the rate of the full workload")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm_done + warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, args.gpus), "requested_steps": args.steps, "requested_warmup": args.warmup,
+                   "note": "reference is pure Python (cannot be compiled into oracle/_ref); its literal code needs ~165 s/frame, "
+                           "so the arm times the oracle port (same algorithm: P1 assembly + SuperLU), kind=port"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.time() - t_start,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    except Exception:
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic():
+    """DRAM bytes per SpMV launch from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "spmv_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from manifold_based_optical_flow_method_b200 import synthetic
+
+    # ---- workload: every rank owns frames [rank*T, (rank+1)*T) of a world*T-frame signal
+    T = args.frames
+    n = T - 1
+    mesh = synthetic.pial_like(args.level)
+    coords, tris, normals, areas = mesh
+    N = len(coords)
+    t_all = synthetic.time_axis(world * T, SF)
+    t_k = t_all[rank * T:(rank + 1) * T]
+    I_np = synthetic.travelling_wave(coords, t_k, seed=0, frame_offset=rank * T)
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only); runs BEFORE CUDA is initialised
+    # because it forks one process per frame like the reference's Pool
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        procs = cpu_procs(args.cpu_procs)
+        fps, secs = cpu_wave(mesh, I_np[:procs + 1], t_k[:procs + 1], procs)
+        _CPU.clear()
+        cpu = {"value": fps, "unit": UNIT, "cores": procs, "kind": "port",
+               "sample": f"one wave of {procs} frames on {procs} processes ({secs:.1f} s): oracle port of the reference "
+                         "algorithm (vectorised P1 assembly + scipy SuperLU spsolve per frame, one process per frame like "
+                         "the reference's Pool); the literal pure-Python reference needs ~165 s/frame/core at this size"}
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from manifold_based_optical_flow_method_b200 import _lib
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    from manifold_based_optical_flow_method_b200 import distributed as mdist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    I_pin = torch.empty((T, N), dtype=torch.float64).pin_memory()
+    I_host = I_pin.numpy()
+    I_host[:] = I_np
+    del I_np
+    cof.settings["tol"] = args.tol
+    cof.settings["batch_groups"] = args.batch_groups
+    t0 = time.time()
+    op, grad_w, e, integral, geom_s = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    nb = op.n_blocks
+    solver = cof._solver(op)
+
+    # ---- device-resident leg ("value")
+    I_dev = I_pin.to(dev, non_blocking=False)
+    V_dev = torch.empty((n, 2 * N), dtype=torch.float64, device=dev)
+    for _ in range(args.warmup):
+        _, info = cof.solve_on_device(op, I_dev, I_dev, t_k, LAMBDA, 0, n, V_dev)
+    solver.profile = _lib.PcgProfile()
+    solver.aux_launches = 0
+    barrier()
+    clocks = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        _, info = cof.solve_on_device(op, I_dev, I_dev, t_k, LAMBDA, 0, n, V_dev)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clock_report = clocks.stop()
+    prof = solver.profile
+    solver.profile = None
+    launches = int(sum_over_ranks(prof.launches_total + solver.aux_launches))
+    converged = bool(info.converged)
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (SpMV), sampled live inside the timed region
+    peak, peak_src = peaks()
+    spmv_bytes = prof.frame_launches * (32.0 * nb + 32.0 * N) + prof.group_launches * (4.0 * nb + 4.0 * (N + 1))
+    upd_bytes = prof.frame_launches * (64.0 + 24.0 + 48.0) * N
+    pup_bytes = prof.frame_launches * 48.0 * N
+    gbs = lambda b, ms: (b / (ms * 1e-3) / 1e9) if ms > 0 else None
+    achieved = gbs(spmv_bytes, prof.ms_spmv)
+    traffic = ncu_traffic()
+    roofline = {
+        "kernel": "spmv_kernel<true> (ap = A p, p'Ap, alpha)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+        "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+        "peak_source": peak_src, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
+        "algorithmic_bytes_per_frame_launch": 32.0 * nb + 32.0 * N, "sampled_launches": int(prof.samples),
+        "avg_launch_ms": prof.ms_spmv / prof.samples if prof.samples else None,
+        "avg_active_frames_per_launch": prof.frame_launches / prof.samples if prof.samples else None,
+        "other_kernels": {
+            "update_kernel": {"achieved": gbs(upd_bytes, prof.ms_update), "avg_launch_ms": prof.ms_update / max(prof.samples, 1)},
+            "pupdate_kernel": {"achieved": gbs(pup_bytes, prof.ms_pupdate), "avg_launch_ms": prof.ms_pupdate / max(prof.samples, 1)},
+        },
+        "pcg_time_share": {"spmv": prof.ms_spmv / max(prof.ms_spmv + prof.ms_update + prof.ms_pupdate, 1e-9),
+                           "update": prof.ms_update / max(prof.ms_spmv + prof.ms_update + prof.ms_pupdate, 1e-9),
+                           "pupdate": prof.ms_pupdate / max(prof.ms_spmv + prof.ms_update + prof.ms_pupdate, 1e-9)},
+    }
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the reference-shaped API
+    e2e = None
+    if not args.no_e2e:
+        h2d = T * N * 8
+        d2h = n * 2 * N * 8
+        counts = [n] * world
+
+        def e2e_step():
+            if world == 1:
+                V_k, _ = cof.compute_velocity_field(1, T, op, grad_w, e, integral, tris, t_k, areas, LAMBDA, I_host, I_host)
+                return V_k
+            return mdist.solve_shard_and_gather(op, I_host, I_host, t_k, LAMBDA, counts, gather="root")[0]
+
+        out = e2e_step()                              # one warm-up pass (allocations, pinned staging)
+        del out
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            out = e2e_step()
+            del out
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t1)
+        e2e = {"value": world * n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * e2e_s / args.steps,
+               "api": "compute_optical_flow.compute_velocity_field(numpy in, list of numpy out)" if world == 1 else
+                      "distributed.solve_shard_and_gather(numpy shard in; NCCL gather to rank 0; numpy out)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "n_vertices": N, "n_faces": len(tris), "n_blocks": nb,
+                       "frames_per_step": world * n, "batch_frames": solver.batch_groups * 32,
+                       "l2": "no flush: the per-step working set (1.17 GB of matrix values per 32-frame group) is >> 126 MB L2",
+                       "parallelism": f"frames sharded over {world} GPU(s), one process per GPU"},
+            "clocks": clock_report, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "solver": {"converged": converged, "iterations_mean": float(np.mean(info.iterations)),
+                       "iterations_max": int(np.max(info.iterations)), "relres_max": float(np.max(info.relres)),
+                       "geometry_seconds": geom_s, "setup_seconds": time.time() - t0},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -112,11 +112,22 @@ typedef struct {
     double* ap;              /* [G][N][2][32]                                           */
     double* partial;         /* [G][n_tiles][2][32] per-tile partial dot products       */
     double* scal;            /* [G][8][32]  rz, pAp, rr, bb, alpha, beta, relres_true, spare */
-    int32_t* state;          /* [G][4][32]  active, iters, status, spare ; then [G] group_done, [G] tickets, [1] groups_active */
+    int32_t* state;          /* [G][4][32]  active, iters, status, spare ; then [G] group_done, [G] tickets, groups_active, frames_active */
 } mof_batch_dev;
 
 int64_t mof_num_tiles(int64_t n_vertices);                      /* ceil(N / MOF_TILE_ROWS) */
 int64_t mof_state_ints(int32_t n_groups);                       /* size of `state` in int32 */
+
+/* Optional sampled timing of the PCG kernels (caller-owned accumulator, may be NULL): one
+ * iteration per check interval is bracketed with CUDA events on the solver's stream. */
+typedef struct {
+    double ms_spmv, ms_update, ms_pupdate;  /* summed device time of the sampled launches      */
+    int64_t samples;                        /* sampled iterations (one launch of each kernel)   */
+    int64_t group_launches;                 /* sum over samples of groups still iterating       */
+    int64_t frame_launches;                 /* sum over samples of frames still iterating       */
+    int64_t iterations_total;               /* iterations launched by the call(s)               */
+    int64_t launches_total;                 /* kernel launches issued by the call(s)            */
+} mof_pcg_profile;
 
 /* ------------------------------------------------------------------------- *
  * K0: geometry, once per mesh (compute_geometrical_quantities,
@@ -161,7 +172,8 @@ int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const d
  * valid frame converged (or had a zero rhs), else the largest status met. */
 int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double tol,
                         int32_t max_iter, int32_t check_every, int32_t max_restarts,
-                        int32_t* iters, double* relres, int32_t* status, void* stream);
+                        int32_t* iters, double* relres, int32_t* status, mof_pcg_profile* prof,
+                        void* stream);
 /* x -> V[k][i + N*alpha] (reference order and layout, :149); V: device, row stride ld. */
 int mof_unpack_solution(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double* V,
                         int64_t ld, void* stream);

@@ -56,6 +56,15 @@ class BatchDev(Structure):
     ]
 
 
+class PcgProfile(Structure):
+    """mof_pcg_profile"""
+    _fields_ = [
+        ("ms_spmv", c_double), ("ms_update", c_double), ("ms_pupdate", c_double),
+        ("samples", c_int64), ("group_launches", c_int64), ("frame_launches", c_int64),
+        ("iterations_total", c_int64), ("launches_total", c_int64),
+    ]
+
+
 _lib = None
 
 
@@ -90,7 +99,8 @@ def _declare(lib):
     lib.mof_spmv_batch.restype = c_int
     lib.mof_spmv_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, P, P]
     lib.mof_pcg_solve_batch.restype = c_int
-    lib.mof_pcg_solve_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, c_int32, c_int32, c_int32, P, P, P, P]
+    lib.mof_pcg_solve_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, c_int32, c_int32, c_int32, P, P, P,
+                                        POINTER(PcgProfile), P]
     lib.mof_unpack_solution.restype = c_int
     lib.mof_unpack_solution.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, c_int64, P]
     lib.mof_tangent_to_xyz.restype = c_int

@@ -44,6 +44,7 @@ __device__ __forceinline__ int32_t* state_ptr(int32_t* st, int64_t g, int which)
 __device__ __forceinline__ int32_t* group_done_ptr(int32_t* st, int G) { return st + (size_t)G * MOF_I_COUNT * MOF_W; }
 __device__ __forceinline__ int32_t* ticket_ptr(int32_t* st, int G) { return group_done_ptr(st, G) + G; }
 __device__ __forceinline__ int32_t* groups_active_ptr(int32_t* st, int G) { return group_done_ptr(st, G) + 2 * G; }
+__device__ __forceinline__ int32_t* lanes_active_ptr(int32_t* st, int G) { return group_done_ptr(st, G) + 2 * G + 1; }
 
 // Deterministic CTA + cross-tile reduction of NV per-lane values.  Returns true (for every
 // thread of the CTA) in the last CTA of group g; there `tot` holds the totals in warp 0.
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(const int32_t* __restrict__ r
             if (!(pap > 0.0) || isinf(pap)) {          // not SPD / NaN / overflow
                 state_ptr(state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
                 active[lane] = 0;
+                atomicSub(lanes_active_ptr(state, G), 1);
             } else {
                 alpha = rz / pap;
             }
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
         int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
         double beta = 0.0;
         int act = active[lane];
+        const int was = act;
         if (act) {
             const double rz_old = scal_ptr(B.scal, g, MOF_S_RZ)[lane];
             const double bb = scal_ptr(B.scal, g, MOF_S_BB)[lane];
@@ -240,9 +243,13 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
         }
         scal_ptr(B.scal, g, MOF_S_BETA)[lane] = beta;
         const int any = __any_sync(kFull, act);
-        if (!any && lane == 0) {
-            group_done_ptr(B.state, G)[g] = 1;
-            atomicSub(groups_active_ptr(B.state, G), 1);
+        const int dropped = __popc(__ballot_sync(kFull, was && !act));
+        if (lane == 0) {
+            if (dropped) atomicSub(lanes_active_ptr(B.state, G), dropped);
+            if (!any) {
+                group_done_ptr(B.state, G)[g] = 1;
+                atomicSub(groups_active_ptr(B.state, G), 1);
+            }
         }
     }
 }
@@ -301,6 +308,7 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
         int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
         int32_t* status = state_ptr(B.state, g, MOF_I_STATUS);
         int act;
+        const int was = mode == 0 ? 0 : active[lane];
         if (mode == 0) {
             const bool valid = g * MOF_W + lane < B.n_frames;
             scal_ptr(B.scal, g, MOF_S_BB)[lane] = tot[1];
@@ -322,7 +330,9 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
         scal_ptr(B.scal, g, MOF_S_RR)[lane] = tot[1];
         active[lane] = act;
         const int any = __any_sync(kFull, act);
+        const int gained = __popc(__ballot_sync(kFull, act && !was));
         if (lane == 0) {
+            if (gained) atomicAdd(lanes_active_ptr(B.state, G), gained);
             int32_t* done = group_done_ptr(B.state, G) + g;
             if (mode == 0) {
                 *done = any ? 0 : 1;
@@ -373,7 +383,7 @@ int check_batch(const mof_mesh_dev* mesh, const mof_batch_dev* b) {
 }  // namespace
 
 extern "C" int64_t mof_state_ints(int32_t n_groups) {
-    return (int64_t)n_groups * MOF_I_COUNT * MOF_W + 2 * (int64_t)n_groups + 1;
+    return (int64_t)n_groups * MOF_I_COUNT * MOF_W + 2 * (int64_t)n_groups + 2;
 }
 
 extern "C" int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const double* x, double* y,
@@ -401,7 +411,7 @@ extern "C" int mof_unpack_solution(const mof_mesh_dev* mesh, const mof_batch_dev
 
 extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double tol,
                                    int32_t max_iter, int32_t check_every, int32_t max_restarts, int32_t* iters,
-                                   double* relres, int32_t* status, void* stream) {
+                                   double* relres, int32_t* status, mof_pcg_profile* prof, void* stream) {
     if (int rc = check_batch(mesh, batch)) return rc;
     const mof_batch_dev& B = *batch;
     MOF_REQUIRE(B.vals && B.rhs && B.minv && B.x && B.r && B.z && B.p && B.ap && B.partial && B.scal && B.state,
@@ -416,35 +426,65 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     dim3 grid(ntiles, G);
     int32_t* d_active_groups = B.state + (size_t)G * MOF_I_COUNT * MOF_W + 2 * (size_t)G;
 
-    // group_done, tickets, groups_active <- 0
-    MOF_CUDA_TRY(cudaMemsetAsync(B.state + (size_t)G * MOF_I_COUNT * MOF_W, 0, (2 * (size_t)G + 1) * sizeof(int32_t), st));
+    // group_done, tickets, groups_active, lanes_active <- 0
+    MOF_CUDA_TRY(cudaMemsetAsync(B.state + (size_t)G * MOF_I_COUNT * MOF_W, 0, (2 * (size_t)G + 2) * sizeof(int32_t), st));
     init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, 0, tol2);
     MOF_LAUNCH_CHECK("init_kernel");
 
-    int32_t h_active = 0;
-    MOF_CUDA_TRY(cudaMemcpyAsync(&h_active, d_active_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    // optional sampled per-kernel timing (one iteration per check interval) for the roofline report
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (prof)
+        for (int q = 0; q < 4; ++q) MOF_CUDA_TRY(cudaEventCreate(&ev[q]));
+    struct EventGuard {
+        cudaEvent_t* e;
+        ~EventGuard() { for (int q = 0; q < 4; ++q) if (e[q]) cudaEventDestroy(e[q]); }
+    } guard{ev};
+
+    int32_t h_act[2] = {0, 0};          // groups, lanes still iterating
+    int32_t& h_active = h_act[0];
+    MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MOF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (prof) prof->launches_total += 1;
     int it = 0, restarts = 0;
     for (;;) {
         while (h_active > 0 && it < max_iter) {
             const int n = (max_iter - it) < check_every ? (max_iter - it) : check_every;
             for (int q = 0; q < n; ++q) {
+                const bool sample = prof && q == 0;
+                if (sample) cudaEventRecord(ev[0], st);
                 spmv_kernel<true><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.p, B.ap, N, nb, ntiles,
                                                        B.partial, B.scal, B.state, G);
+                if (sample) cudaEventRecord(ev[1], st);
                 update_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, tol2);
+                if (sample) cudaEventRecord(ev[2], st);
                 pupdate_kernel<<<grid, 256, 0, st>>>(B, N);
+                if (sample) cudaEventRecord(ev[3], st);
             }
             MOF_LAUNCH_CHECK("pcg iteration kernels");
             it += n;
-            MOF_CUDA_TRY(cudaMemcpyAsync(&h_active, d_active_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            const int32_t groups_before = h_act[0], lanes_before = h_act[1];
+            MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             MOF_CUDA_TRY(cudaStreamSynchronize(st));
+            if (prof) {
+                float ms[3] = {0, 0, 0};
+                for (int q = 0; q < 3; ++q) MOF_CUDA_TRY(cudaEventElapsedTime(&ms[q], ev[q], ev[q + 1]));
+                prof->ms_spmv += ms[0];
+                prof->ms_update += ms[1];
+                prof->ms_pupdate += ms[2];
+                prof->samples += 1;
+                prof->group_launches += groups_before;
+                prof->frame_launches += lanes_before;
+                prof->iterations_total += n;
+                prof->launches_total += 3 * (int64_t)n;
+            }
         }
         // confirm on the true residual b - A x; frames whose recurrence drifted restart
         spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.x, B.ap, N, nb, ntiles, nullptr,
                                                 nullptr, nullptr, G);
         init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, 1, tol2);
         MOF_LAUNCH_CHECK("verification kernels");
-        MOF_CUDA_TRY(cudaMemcpyAsync(&h_active, d_active_groups, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (prof) prof->launches_total += 2;
+        MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         MOF_CUDA_TRY(cudaStreamSynchronize(st));
         if (h_active <= 0 || it >= max_iter || restarts >= max_restarts) break;
         ++restarts;

@@ -37,15 +37,17 @@ def shard_counts(n_frames, world):
     return [shard_range(n_frames, world, r)[1] - shard_range(n_frames, world, r)[0] for r in range(world)]
 
 
-def gather_rows(local, counts, group=None):
-    """All-gather row blocks of unequal height: ``local`` is this rank's (counts[rank], C)
-    tensor (CUDA -> NCCL over NVLink, CPU -> gloo); returns the (sum(counts), C) tensor on
-    every rank.  Shards are padded to the tallest one so a single collective moves them."""
+def gather_rows(local, counts, group=None, root=None):
+    """Gather row blocks of unequal height: ``local`` is this rank's (counts[rank], C) tensor
+    (CUDA -> NCCL over NVLink, CPU -> gloo).  root=None: all-gather, every rank gets the
+    (sum(counts), C) tensor; root=r: only rank r gets it (others get None).  Shards are
+    padded to the tallest one so a single collective moves them."""
     import torch
     dist = _dist()
     world = len(counts)
     if world == 1:
         return local
+    me = dist.get_rank(group)
     cmax = max(counts)
     tail = tuple(local.shape[1:])
     if local.shape[0] != cmax:
@@ -53,32 +55,61 @@ def gather_rows(local, counts, group=None):
         pad[:local.shape[0]] = local
     else:
         pad = local.contiguous()
-    out = torch.empty((world, cmax) + tail, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out.view((world * cmax,) + tail), pad, group=group)
+    if root is None:
+        out = torch.empty((world, cmax) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view((world * cmax,) + tail), pad, group=group)
+    else:
+        out = torch.empty((world, cmax) + tail, dtype=local.dtype, device=local.device) if me == root else None
+        dist.gather(pad, list(out.unbind(0)) if me == root else None, dst=root, group=group)
+        if me != root:
+            return None
     if all(c == cmax for c in counts):
         return out.view((world * cmax,) + tail)
     return torch.cat([out[r, :counts[r]] for r in range(world)], dim=0)
 
 
-def compute_velocity_field_sharded(op, n_frames, t_k, lambda_, I_k, I_k_2, to_host=True):
-    """Rank-local solve of frames shard_range(...) + all-gather.  -> (V (n_frames, 2N), SolveInfo)
-    V is a numpy array (to_host) or a device tensor."""
+def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather="all", to_host=True):
+    """Multi-GPU entry point: this rank solves the frames of its shard -- ``I_shard`` /
+    ``I2_shard`` hold rows k0 .. k1 (one-frame halo: frame k1-1 reads I2[k1]) and
+    ``t_k_shard`` the matching k1-k0+1 time stamps -- then the per-frame fields are gathered
+    over NCCL.  gather: "all" (every rank gets all frames), "root" (rank 0 only; other ranks
+    get None) or "none" (each rank keeps its shard).  -> (V, SolveInfo); V is a numpy array
+    if to_host else a device tensor."""
     import torch
     from . import compute_optical_flow as cof
     from .solver import SolveInfo
-    world, r = world_size(), rank()
-    counts = shard_counts(n_frames, world)
-    k0, k1 = shard_range(n_frames, world, r)
+    r = rank()
+    n_loc = counts[r] if len(counts) > 1 else len(t_k_shard) - 1
     N = op.n_vertices
-    if k1 > k0:
-        # one-frame input halo: frame k1-1 reads I_k_2[k1]
-        I_dev, I2_dev = cof._upload_signals(op, I_k, I_k_2, k1 - k0, first=k0)
-        V_loc, info = cof.solve_on_device(op, I_dev, I2_dev, t_k[k0:k1 + 1], lambda_, 0, k1 - k0)
+    if n_loc > 0:
+        I_dev, I2_dev = cof._upload_signals(op, I_shard, I2_shard, n_loc)
+        V_loc, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc)
         rep = np.stack([info.iterations.astype(np.float64), info.relres, info.status.astype(np.float64)], axis=1)
     else:
         V_loc = torch.empty((0, 2 * N), dtype=torch.float64, device=op.device)
         rep = np.zeros((0, 3))
-    V_all = gather_rows(V_loc, counts)
-    rep_all = gather_rows(torch.from_numpy(rep).to(op.device), counts).cpu().numpy()
-    info = SolveInfo(rep_all[:, 0].astype(np.int32), rep_all[:, 1].copy(), rep_all[:, 2].astype(np.int32))
+    rep_dev = torch.from_numpy(rep).to(op.device)
+    if gather == "none" or len(counts) == 1:
+        V_all, rep_all = V_loc, rep_dev
+    else:
+        root = 0 if gather == "root" else None
+        V_all = gather_rows(V_loc, counts, root=root)
+        rep_all = gather_rows(rep_dev, counts, root=root)
+    if V_all is None:
+        return None, SolveInfo(info.iterations, info.relres, info.status) if n_loc > 0 else None
+    rep_np = rep_all.cpu().numpy()
+    info = SolveInfo(rep_np[:, 0].astype(np.int32), rep_np[:, 1].copy(), rep_np[:, 2].astype(np.int32))
     return (V_all.cpu().numpy() if to_host else V_all), info
+
+
+def compute_velocity_field_sharded(op, n_frames, t_k, lambda_, I_k, I_k_2, gather="all", to_host=True):
+    """compute_velocity_field under torchrun: every rank holds the full (T,N) signal like
+    the reference's processes do, solves frames shard_range(...) and all-gathers.
+    -> (V (n_frames, 2N), SolveInfo)"""
+    world, r = world_size(), rank()
+    counts = shard_counts(n_frames, world)
+    k0, k1 = shard_range(n_frames, world, r)
+    same = I_k_2 is I_k
+    I_sh = I_k[k0:k1 + 1]
+    I2_sh = I_sh if same else I_k_2[k0:k1 + 1]
+    return solve_shard_and_gather(op, I_sh, I2_sh, t_k[k0:k1 + 1], lambda_, counts, gather=gather, to_host=to_host)

@@ -98,6 +98,8 @@ class VelocitySolver:
             batch_groups = max(1, min(DEFAULT_BATCH_GROUPS, int(0.6 * free) // max(per_group, 1)))
         self.batch_groups = int(batch_groups)
         self._batch = None
+        self.profile = None          # set to _lib.PcgProfile() to accumulate sampled kernel timings
+        self.aux_launches = 0        # pack / assemble / unpack launches issued so far
 
     def batch(self, n_groups):
         if self._batch is None or self._batch.n_groups < n_groups:
@@ -130,7 +132,10 @@ class VelocitySolver:
         status = np.zeros(G * GROUP, np.int32)
         _lib.check(lib.mof_pcg_solve_batch(ctypes.byref(ms), ctypes.byref(bs), float(self.tol), int(self.max_iter),
                                            int(self.check_every), int(self.max_restarts), iters.ctypes.data,
-                                           relres.ctypes.data, status.ctypes.data, st), allow_positive=True)
+                                           relres.ctypes.data, status.ctypes.data,
+                                           ctypes.byref(self.profile) if self.profile is not None else None, st),
+                   allow_positive=True)
+        self.aux_launches += 3
         assert V_out.stride(1) == 1
         _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
         return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames])

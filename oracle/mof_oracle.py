@@ -141,7 +141,7 @@ def assemble_frame(grad_w, e, integral_wi_wj, triangles, areas, dt, I_now, I_nex
     a1 = _to_csr(rows, cols, vals, N)
     d = (I_next - I_now) / dt                               # (N,)
     dT = d[t]                                               # (F,3)
-    others = dT.sum(axis=1, keepdims=True) - dT
+    others = np.stack([dT[:, 1] + dT[:, 2], dT[:, 0] + dT[:, 2], dT[:, 0] + dT[:, 1]], axis=1)   # :308-309
     w = 2 * dT + others                                     # (F,3)
     fl = c * w[:, :, None] * areas[:, None, None] / 12      # (F,3,2)
     f = np.zeros(2 * N)

@@ -1,0 +1,397 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the reference-shaped
+Python API and the C ABI, against (a) the golden outputs of the unmodified reference
+(tests/golden/*.npz), (b) the numpy/scipy oracle on seeded inputs the oracle finishes in
+seconds, and (c) size-independent properties at the full BASELINE.json sizes.
+
+Tolerances (BASELINE.json north_star): velocity fields rel-L2 <= 1e-8 (fp64, PCG true
+residual <= 1e-12); assembled values/rhs <= 1e-13 relative; singular vertex / face indices
+exactly equal; (lam, mu) within 1e-10.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import load_golden, rel_l2
+from manifold_based_optical_flow_method_b200 import _lib, synthetic
+from oracle import mof_oracle
+
+pytestmark = pytest.mark.gpu
+
+W = _lib.GROUP
+V_TOL = 1e-8
+RES_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow, find_singularity_point
+    return compute_optical_flow, find_singularity_point
+
+
+def _csr(g, prefix, n):
+    return sp.csr_matrix((g[prefix + "_data"], g[prefix + "_indices"], g[prefix + "_indptr"]), shape=(n, n))
+
+
+def _frame_matrix(P, vals, k):
+    return P.block_values_to_csr(vals[k // W, :, :, k % W])
+
+
+def _frame_vector(P, vec, k):
+    N = P.n_vertices
+    out = np.empty(2 * N)
+    out[P.perm] = vec[k // W, :, 0, k % W]
+    out[P.perm + N] = vec[k // W, :, 1, k % W]
+    return out
+
+
+def _assemble_on_gpu(cof, op, I, t_k, lambda_):
+    """pack + K1 through the C ABI; returns host copies of vals / rhs / minv and the batch"""
+    import torch
+    from manifold_based_optical_flow_method_b200.solver import VelocitySolver, frame_dt
+    n = len(I) - 1
+    s = VelocitySolver(op, batch_groups=-(-n // W))
+    batch = s.batch(-(-n // W))
+    I_dev = torch.from_numpy(np.ascontiguousarray(I, dtype=np.float64)).to(op.device)
+    dt = torch.from_numpy(frame_dt(list(t_k), 0, n)).to(op.device)
+    s.assemble(batch, I_dev[:n], I_dev[1:n + 1], dt, lambda_, n)
+    torch.cuda.synchronize()
+    return s, batch, batch.vals.cpu().numpy(), batch.rhs.cpu().numpy(), batch.minv.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------
+# golden vectors of the unmodified reference
+# ---------------------------------------------------------------------------------
+def test_geometry_matches_reference(golden, mods):
+    cof, _ = mods
+    g = golden
+    a2, grad_w, e, integral, secs = cof.compute_geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    assert a2.shape == (2 * len(g["coordinates"]),) * 2 and secs >= 0
+    assert np.max(np.abs(e - g["e"])) <= 1e-15
+    assert rel_l2(grad_w, g["grad_w"]) <= 1e-14
+    assert np.allclose(integral, g["integral_wi_wj"], rtol=1e-15, atol=0)
+    if "a2_data" in g:
+        ref = _csr(g, "a2", a2.shape[0])
+        assert abs(a2.tocsr() - ref).max() <= 1e-13 * abs(ref).max()
+
+
+def test_assembled_system_matches_reference(golden, mods):
+    cof, _ = mods
+    g = golden
+    N = len(g["coordinates"])
+    op, gw, e, integ, _ = cof.compute_geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    _, _, vals, rhs, minv = _assemble_on_gpu(cof, op, g["I"], g["t_k"], float(g["lambda_"]))
+    P = op.pattern
+    if "a0_data" in g:
+        ref = _csr(g, "a0", 2 * N)
+        a = _frame_matrix(P, vals, 0)
+        assert abs(a - ref).max() <= 1e-13 * abs(ref).max()
+        assert abs(a - a.T).max() == 0.0
+        assert rel_l2(_frame_vector(P, rhs, 0), g["f0"]) <= 1e-13
+    # every frame against the oracle's assembly
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    for k in range(len(g["I"]) - 1):
+        dt = g["t_k"][k + 1] - g["t_k"][k]
+        a1, f = mof_oracle.assemble_frame(gwo, eo, into, g["triangles"], g["areas"], dt, g["I"][k], g["I"][k + 1])
+        ao = mof_oracle.system_matrix(a1, a2o, float(g["lambda_"]))
+        a = _frame_matrix(P, vals, k)
+        assert abs(a - ao).max() <= 1e-13 * abs(ao).max()
+        assert rel_l2(_frame_vector(P, rhs, k), f) <= 1e-13
+    # padded lanes carry a zero rhs
+    n = len(g["I"]) - 1
+    assert np.all(rhs[-1, :, :, n % W:] == 0.0)
+    assert np.all(np.isfinite(minv))
+
+
+def test_spmv_matches_scipy(mods):
+    import torch
+    cof, _ = mods
+    g = load_golden("ico3_phase")
+    op, *_ = cof.compute_geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    s, batch, vals, _, _ = _assemble_on_gpu(cof, op, g["I"], g["t_k"], float(g["lambda_"]))
+    P = op.pattern
+    x = torch.randn(batch.x.shape, dtype=torch.float64, device=op.device, generator=torch.Generator(op.device).manual_seed(3))
+    y = torch.full_like(x, float("nan"))
+    ms, bs = op.struct(), batch.struct()
+    _lib.check(_lib.load().mof_spmv_batch(ctypes.byref(ms), ctypes.byref(bs), x.data_ptr(), y.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    xh, yh = x.cpu().numpy(), y.cpu().numpy()
+    for k in range(len(g["I"]) - 1):
+        a = _frame_matrix(P, vals, k)
+        assert rel_l2(_frame_vector(P, yh, k), a @ _frame_vector(P, xh, k)) <= 1e-14
+
+
+def test_velocity_field_matches_reference(golden, mods):
+    cof, _ = mods
+    g = golden
+    T = len(g["t_k"])
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    V_k, secs = cof.compute_velocity_field(4, T, a2, gw, e, integ, g["triangles"], list(g["t_k"]), g["areas"],
+                                           float(g["lambda_"]), g["I"], g["I"])
+    assert isinstance(V_k, list) and len(V_k) == T - 1 and V_k[0].shape == (2 * len(g["coordinates"]),)
+    info = cof.last_solve_info
+    assert info.converged and np.all(info.relres <= RES_TOL)
+    for k in range(T - 1):
+        assert rel_l2(V_k[k], g["V_k"][k]) <= V_TOL, (k, rel_l2(V_k[k], g["V_k"][k]))
+    # the reference's own consumers of V_k (compute_optical_flow.py:314-319)
+    assert np.array(V_k).reshape(len(V_k), -1).shape == (T - 1, 2 * len(g["coordinates"]))
+
+
+def test_worker_single_frame_matches_reference_and_batch(mods):
+    cof, _ = mods
+    g = load_golden("ico2_wave")
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    t_k = list(g["t_k"])
+    V1 = cof.worker(1, a2, gw, e, integ, g["triangles"], t_k, g["areas"], float(g["lambda_"]), g["I"][1], g["I"][2])
+    assert rel_l2(V1, g["V_k"][1]) <= V_TOL
+    V_k, _ = cof.compute_velocity_field(1, len(t_k), a2, gw, e, integ, g["triangles"], t_k, g["areas"],
+                                        float(g["lambda_"]), g["I"], g["I"])
+    # reductions are deterministic and lane-private: a frame does not depend on its batch
+    assert np.array_equal(V1, V_k[1])
+
+
+def test_second_signal_argument(mods):
+    """I_k_2 != I_k: frame k must use I_k[k] and I_k_2[k+1] (compute_optical_flow.py:174-175)."""
+    cof, _ = mods
+    g = load_golden("ico1_wave")
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    I2 = g["I"] + 0.01 * np.random.default_rng(5).standard_normal(g["I"].shape)
+    T = len(g["t_k"])
+    Vo, _ = mof_oracle.compute_velocity_field(1, T, a2o, gwo, eo, into, g["triangles"], list(g["t_k"]), g["areas"], 0.02, g["I"], I2)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, g["triangles"], list(g["t_k"]), g["areas"], 0.02, g["I"], I2)
+    for k in range(T - 1):
+        assert rel_l2(V_k[k], Vo[k]) <= V_TOL
+
+
+def test_process_V_k_and_singularities_match_reference(golden, mods):
+    _, fsp = mods
+    g = golden
+    V_xyz = fsp.process_V_k(list(g["V_k"]), g["e"])
+    assert V_xyz.shape == g["V_xyz"].shape
+    assert np.array_equal(V_xyz, g["V_xyz"])                       # bit-exact
+    assert np.array_equal(fsp.speed_magnitude(g["V_k"], g["e"]), np.sqrt(np.sum(g["V_xyz"][:, :, :3] ** 2, axis=2)))
+    s = fsp.detect_singularities(g["V_xyz"], g["coordinates"], g["triangles"], float(g["eps"]))
+    assert np.array_equal(s.v_length_max, g["v_length_max"])
+    assert np.array_equal(np.diff(s.vertex_offsets), g["sing_counts"][:, 0])
+    assert np.array_equal(np.diff(s.face_offsets), g["sing_counts"][:, 1])
+    assert np.array_equal(s.vertex_idx, g["sing_vertex_idx"])
+    assert np.array_equal(s.face_idx, g["sing_face_idx"])          # bit-exact index lists
+    assert np.allclose(s.lam_mu, g["sing_face_lam_mu"], rtol=0, atol=1e-10)
+    R = np.max(np.linalg.norm(g["coordinates"], axis=1))
+    assert np.allclose(s.P, g["sing_face_P"], rtol=0, atol=1e-10 * R)
+    assert np.all(np.abs(s.index) == 1)
+    # per-face Poincare index agrees with the winding-angle definition of S7_winding_line.py
+    for k in range(len(g["V_xyz"])):
+        _, fi, _, _, idx = s.frame(k)
+        assert np.array_equal(idx, mof_oracle.face_poincare_index(g["coordinates"], g["triangles"], g["V_xyz"][k], fi))
+    # reference-shaped API, one frame
+    sv, si, vmax = fsp.find_singularity_points(g["coordinates"], g["triangles"], g["V_xyz"][0], float(g["eps"]))
+    nv, nf = g["sing_counts"][0]
+    assert [r[0] for r in sv] == list(g["sing_vertex_idx"][:nv]) and [r[0] for r in si] == list(g["sing_face_idx"][:nf])
+    assert vmax == g["v_length_max"][0]
+    for r in si:
+        assert len(r) == 5 and np.array_equal(r[2], g["triangles"][r[0]]) and abs(sum(r[3]) - 1) < 1e-15
+    pts = fsp.find_singularity_points_for_all_Vk(g["V_xyz"], g["coordinates"], g["triangles"], float(g["eps"]))
+    flat = np.asarray([p for fr in pts for p in fr]).reshape(-1, 3)
+    assert np.allclose(flat, g["all_points_flat"], rtol=0, atol=1e-10 * R)
+
+
+def test_singular_vertices_and_face_skip(mods):
+    _, fsp = mods
+    g = load_golden("ico2_vertex_singular")
+    sv, si, vmax = fsp.find_singularity_points(g["coordinates"], g["triangles"], g["V_now"], float(g["eps"]))
+    assert [r[0] for r in sv] == list(g["sing_vertex_idx"]) and len(sv) == 2
+    assert np.array_equal(sv[0][1], g["coordinates"][sv[0][0]])
+    assert [r[0] for r in si] == list(g["sing_face_idx"])
+    assert vmax == float(g["v_length_max"])
+
+
+# ---------------------------------------------------------------------------------
+# oracle on seeded inputs (sizes the oracle finishes in seconds)
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["C1_wave", "patch_wave", "two_phase"])
+def test_velocity_field_matches_oracle(case, mods):
+    cof, fsp = mods
+    if case == "C1_wave":          # BASELINE.json configs[0] mesh (ico5, 10,242 vertices)
+        coords, tris, normals, areas = synthetic.icosphere(5)
+        T, SF, kind = 7, 512.0, "wave"
+    elif case == "patch_wave":     # open surface with boundary, irregular valence
+        coords, tris, normals, areas = synthetic.open_patch(40, seed=2)
+        T, SF, kind = 36, 256.0, "wave"      # 35 frames: one full group + 3 ragged lanes
+    else:                          # two components + wrapped-phase input (config 4 style)
+        coords, tris, normals, areas = synthetic.two_hemispheres(4, radius=80.0)
+        T, SF, kind = 4, 512.0, "phase"
+    t_k = synthetic.time_axis(T, SF)
+    I = synthetic.travelling_wave(coords, t_k, seed=1) if kind == "wave" else synthetic.wrapped_phase(coords, t_k, seed=1)
+    lam = 0.01
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    Vo, _ = mof_oracle.compute_velocity_field(4, T, a2o, gwo, eo, into, tris, t_k, areas, lam, I, I)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    assert abs(a2.tocsr() - a2o).max() <= 1e-13 * abs(a2o).max()
+    V_k, _ = cof.compute_velocity_field(8, T, a2, gw, e, integ, tris, t_k, areas, lam, I, I)
+    info = cof.last_solve_info
+    assert info.converged and np.all(info.relres <= RES_TOL)
+    worst = max(rel_l2(V_k[k], Vo[k]) for k in range(T - 1))
+    assert worst <= V_TOL, worst
+    # detection on the GPU field vs the oracle's detection on the oracle field
+    Vx = fsp.process_V_k(V_k, e)
+    Vxo = mof_oracle.process_V_k(Vo, eo)
+    s = fsp.detect_singularities(Vx, coords, tris, 1e-4)
+    for k in range(min(T - 1, 3)):
+        vi, fi, lm, P, vmax = mof_oracle.find_singularity_points(coords, tris, Vxo[k], 1e-4)
+        gvi, gfi, glm, gP, _ = s.frame(k)
+        assert np.array_equal(gvi, vi) and np.array_equal(gfi, fi)
+        assert np.allclose(glm, lm, rtol=0, atol=1e-6)      # fields differ by <=1e-8 rel-L2
+
+
+# ---------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_frames", [1, 31, 32, 33, 70])
+def test_ragged_frame_counts(n_frames, mods):
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(2)
+    T = n_frames + 1
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=4)
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    cof.settings["batch_groups"] = 2          # forces several batches for 70 frames
+    try:
+        V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    finally:
+        cof.settings["batch_groups"] = None
+    assert len(V_k) == n_frames
+    for k in sorted({0, n_frames // 2, n_frames - 1}):
+        Vo = mof_oracle.worker(k, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[k], I[k + 1])
+        assert rel_l2(V_k[k], Vo) <= V_TOL
+
+
+def test_empty_time_axis(mods):
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(1)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    V_k, secs = cof.compute_velocity_field(1, 1, a2, gw, e, integ, tris, [0.0], areas, 0.01, np.zeros((1, 42)), np.zeros((1, 42)))
+    assert V_k == [] and secs == 0.0
+
+
+def test_constant_and_nan_frames_do_not_poison_others(mods):
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(2)
+    T = 6
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=9)
+    I[2] = 0.0                      # frame 2: grad I = 0 exactly -> a1 = 0, f = 0 -> V = 0 (spsolve(a, 0) = 0)
+    I[5, 7] = np.nan                # frame 4 reads I[5] as "next" -> NaN rhs
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    cof.settings["allow_unconverged"] = True
+    try:
+        V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    finally:
+        cof.settings["allow_unconverged"] = False
+    info = cof.last_solve_info
+    assert info.status[2] == _lib.STATUS_ZERO_RHS and np.all(V_k[2] == 0.0)
+    assert info.status[4] == _lib.STATUS_BREAKDOWN
+    for k in (0, 1, 3):
+        assert info.status[k] == _lib.STATUS_CONVERGED
+        Vo = mof_oracle.worker(k, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[k], I[k + 1])
+        assert rel_l2(V_k[k], Vo) <= V_TOL
+    with pytest.raises(cof.UnconvergedError):
+        cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+
+
+def test_max_iter_reports_unconverged(mods):
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(3)
+    t_k = synthetic.time_axis(3, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=2)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    cof.settings["max_iter"] = 5
+    try:
+        with pytest.raises(cof.UnconvergedError):
+            cof.compute_velocity_field(1, 3, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+        assert np.all(cof.last_solve_info.status == _lib.STATUS_MAXITER)
+        assert np.all(cof.last_solve_info.iterations == 5)
+    finally:
+        cof.settings["max_iter"] = 20000
+
+
+def test_caller_supplied_geometry_and_reference_a2(mods):
+    """worker uses the grad_w / e / integral it is handed (compute_optical_flow.py:100-101)."""
+    cof, _ = mods
+    from manifold_based_optical_flow_method_b200.mesh import MeshOperator
+    g = load_golden("ico2_wave")
+    t_k = list(g["t_k"])
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    # rotate every tangent basis by 30 degrees: a different but valid e
+    c, s_ = np.cos(0.5), np.sin(0.5)
+    e2 = np.stack([c * eo[:, 0] + s_ * eo[:, 1], -s_ * eo[:, 0] + c * eo[:, 1]], axis=1)
+    a2_rot = mof_oracle.a2_matrix(g["triangles"], g["areas"], e2, gwo)
+    Vo = mof_oracle.worker(0, a2_rot, gwo, e2, into, g["triangles"], t_k, g["areas"], 0.01, g["I"][0], g["I"][1])
+    op = MeshOperator.from_reference_a2(a2_rot, g["coordinates"], g["normals"], g["triangles"], g["areas"])
+    V = cof.worker(0, op, gwo, e2, into, g["triangles"], t_k, g["areas"], 0.01, g["I"][0], g["I"][1])
+    assert rel_l2(V, Vo) <= V_TOL
+    with pytest.raises(TypeError):
+        cof.worker(0, a2o, gwo, eo, into, g["triangles"], t_k, g["areas"], 0.01, g["I"][0], g["I"][1])
+
+
+def test_c_abi_argument_errors(mods):
+    lib = _lib.load()
+    assert lib.mof_geom_basis(0, None, None, None) < 0
+    assert "bad arguments" in _lib.last_error()
+    with pytest.raises(_lib.MofError):
+        _lib.check(lib.mof_tangent_to_xyz(10, 1, None, 20, None, None, None, None, None))
+
+
+# ---------------------------------------------------------------------------------
+# full size (BASELINE.json configs[1]: ~160k-vertex pial-like mesh): size-independent properties
+# ---------------------------------------------------------------------------------
+def test_full_size_properties(mods):
+    import torch
+    cof, fsp = mods
+    coords, tris, normals, areas = synthetic.pial_like(7)
+    N = len(coords)
+    assert N == 163842
+    T = 34                          # 33 frames: one full group + one ragged lane
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=0)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    info = cof.last_solve_info
+    assert info.converged and np.all(info.relres <= RES_TOL)
+    # (1) residual against the ORACLE's independently assembled system, frames 0 and 32
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    assert abs(a2.tocsr() - a2o).max() <= 1e-13 * abs(a2o).max()
+    for k in (0, 32):
+        a1, f = mof_oracle.assemble_frame(gwo, eo, into, tris, areas, t_k[k + 1] - t_k[k], I[k], I[k + 1])
+        A = mof_oracle.system_matrix(a1, a2o, 0.01)
+        assert np.linalg.norm(A @ V_k[k] - f) / np.linalg.norm(f) <= 1e-11
+    # (2) linearity in the rhs: doubling every time step halves the field (f ~ 1/dt)
+    t2 = [2.0 * t for t in t_k]
+    Vh = cof.worker(5, a2, gw, e, integ, tris, t2, areas, 0.01, I[5], I[6])
+    assert rel_l2(2.0 * Vh, V_k[5]) <= 1e-9
+    # (3) batch independence (deterministic, lane-private reductions): frame alone == frame in batch
+    V5 = cof.worker(5, a2, gw, e, integ, tris, t_k, areas, 0.01, I[5], I[6])
+    assert np.array_equal(V5, V_k[5])
+    # (4) one full-size frame against the reference algorithm's direct solve (SuperLU, ~40 s)
+    Vo = mof_oracle.worker(0, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[0], I[1])
+    assert rel_l2(V_k[0], Vo) <= V_TOL
+    # (5) detection at full size against the oracle (reference lstsq decisions), exact index lists
+    Vx = fsp.process_V_k(V_k[:4], e)
+    assert np.array_equal(Vx, mof_oracle.process_V_k(V_k[:4], e))
+    s = fsp.detect_singularities(Vx, coords, tris, 1e-4)
+    for k in range(4):
+        vi, fi, lm, P, idx = s.frame(k)
+        assert np.all((lm >= 0) & (lm.sum(axis=1, keepdims=True) <= 1)) and len(fi) >= 2
+    for k in (0, 3):
+        vio, fio, lmo, Po, vmaxo = mof_oracle.find_singularity_points(coords, tris, Vx[k], 1e-4)
+        vi, fi, lm, P, idx = s.frame(k)
+        assert np.array_equal(vi, vio) and np.array_equal(fi, fio) and s.v_length_max[k] == vmaxo
+        assert np.allclose(lm, lmo, rtol=0, atol=1e-10)
+        assert np.array_equal(idx, mof_oracle.face_poincare_index(coords, tris, Vx[k], fio))
+    torch.cuda.empty_cache()

@@ -29,12 +29,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.mof_version() >= 100
     assert lib.mof_num_tiles(129) == 3
-    assert lib.mof_state_ints(2) == 2 * 4 * 32 + 2 * 2 + 1
+    assert lib.mof_state_ints(2) == 2 * 4 * 32 + 2 * 2 + 2
 
 
 def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8
     assert ctypes.sizeof(_lib.BatchDev) == 8 + 13 * 8
+    assert ctypes.sizeof(_lib.PcgProfile) == 8 * 8
 
 
 @pytest.mark.parametrize("reorder", [False, True])
