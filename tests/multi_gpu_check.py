@@ -1,0 +1,69 @@
+"""Multi-GPU check, run under torchrun on the GPU box (not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multi_gpu_check.py
+
+Every rank calls the reference-shaped compute_velocity_field with the full signal; frames are
+sharded by rank, solved, and all-gathered over NCCL.  The result must equal the oracle to the
+parity tolerance and -- because every frame's arithmetic is lane-private and its reductions
+are deterministic -- be bit-identical to what a single GPU computes for the same frames.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof  # noqa: E402
+from manifold_based_optical_flow_method_b200 import distributed as mdist  # noqa: E402
+from manifold_based_optical_flow_method_b200 import synthetic  # noqa: E402
+from oracle import mof_oracle  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    coords, tris, normals, areas = synthetic.icosphere(4)
+    T = 71                                   # 70 frames: uneven shards for world = 4 / 8
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=3)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    V_k, _ = cof.compute_velocity_field(world, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    assert len(V_k) == T - 1 and cof.last_solve_info.converged and len(cof.last_solve_info.iterations) == T - 1
+    V = np.asarray(V_k)
+    # every rank holds the same gathered field
+    h = torch.from_numpy(V).to(f"cuda:{local}")
+    ref = h.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(h, ref)
+    # the rank's own shard solved locally without torch.distributed: bit-identical
+    k0, k1 = mdist.shard_range(T - 1, world, rank)
+    I_dev = torch.from_numpy(I).to(f"cuda:{local}")
+    V_loc, _ = cof.solve_on_device(a2, I_dev, I_dev, t_k, 0.01, 0, T - 1)
+    assert torch.equal(V_loc[k0:k1], h[k0:k1]), "sharded result differs from the single-GPU result"
+    assert torch.equal(V_loc, h), "sharding changed a frame's bits"
+    # root gather
+    out, info = mdist.compute_velocity_field_sharded(a2, T - 1, t_k, 0.01, I, I, gather="root")
+    if rank == 0:
+        assert np.array_equal(out, V)
+    else:
+        assert out is None
+    if rank == 0:
+        a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+        for k in (0, 17, 35, 69):
+            Vo = mof_oracle.worker(k, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[k], I[k + 1])
+            rel = np.linalg.norm(V[k] - Vo) / np.linalg.norm(Vo)
+            assert rel <= 1e-8, (k, rel)
+        print(f"multi_gpu_check OK: world={world} frames={T - 1} shards={mdist.shard_counts(T - 1, world)}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
