@@ -309,7 +309,11 @@ def run_b200(args):
     roofline = {
         "kernel": "spmv_kernel<true> (ap = A p, p'Ap, alpha)", "bound": "hbm", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+        # ncu dram__bytes_read+write per launch, scaled from the committed 32-frame capture to this
+        # run's average number of active frames per launch (profiles/spmv_traffic.json)
+        "traffic": (traffic["dram_bytes_per_frame_launch"] * prof.frame_launches / prof.samples)
+        if (traffic and prof.samples) else None,
+        "algorithmic_bytes_per_launch": spmv_bytes / prof.samples if prof.samples else None,
         "peak_source": peak_src, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
         "algorithmic_bytes_per_frame_launch": 32.0 * nb + 32.0 * N, "sampled_launches": int(prof.samples),
         "avg_launch_ms": prof.ms_spmv / prof.samples if prof.samples else None,
