@@ -99,14 +99,26 @@ def _upload_signals(op, I_k, I_k_2, n, first=0):
     return rows(I_k, first, first + n, "I_k"), rows(I_k_2, first, first + n + 1, "I_k_2")
 
 
-def solve_on_device(op, I_dev, I2_dev, t_k, lambda_, k0, k1, V_dev=None):
+def solve_on_device(op, I_dev, I2_dev, t_k, lambda_, k0, k1, V_dev=None, on_batch=None):
     """Frames k0..k1-1 from device-resident signals (rows are absolute frame indices).
     -> (V_dev (k1-k0, 2N) device tensor, SolveInfo).  Used by bench.py (inputs resident in
     HBM) and by distributed.py."""
     torch = _lib.require_cuda()
     s = _solver(op)
     dt = torch.from_numpy(frame_dt(t_k, k0, k1)).to(op.device)
-    return s.solve_frames(I_dev[k0:k1 + 1], I2_dev[k0:k1 + 1], dt, lambda_, V_dev)
+    return s.solve_frames(I_dev[k0:k1 + 1], I2_dev[k0:k1 + 1], dt, lambda_, V_dev, on_batch=on_batch)
+
+
+def solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n):
+    """solve_on_device for frames 0..n-1 with the results drained to a host array batch by
+    batch, overlapped with the solve of the next batch.  -> (V (n, 2N) numpy, SolveInfo)"""
+    s = _solver(op)
+    V = np.empty((n, 2 * op.n_vertices), dtype=np.float64)
+    drain = s.drain(2 * op.n_vertices)
+    _, info = solve_on_device(op, I_dev, I2_dev, t_k, lambda_, 0, n,
+                              on_batch=lambda k0, k1, Vd: drain.submit(Vd, V[k0:k1]))
+    drain.finish()
+    return V, info
 
 
 def compute_velocity_field(processes_num, time_steps, a2, grad_w, e, integral_wi_wj, triangles, t_k, areas,
@@ -127,8 +139,7 @@ def compute_velocity_field(processes_num, time_steps, a2, grad_w, e, integral_wi
         V, info = distributed.compute_velocity_field_sharded(op, n, t_k, lambda_, I_k, I_k_2)
     else:
         I_dev, I2_dev = _upload_signals(op, I_k, I_k_2, n)
-        V_dev, info = solve_on_device(op, I_dev, I2_dev, t_k, lambda_, 0, n)
-        V = V_dev.cpu().numpy()
+        V, info = solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n)
     execution_time = time.time() - start_time
     info.seconds = execution_time
     last_solve_info = info

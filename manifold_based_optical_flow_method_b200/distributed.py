@@ -81,22 +81,60 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
     r = rank()
     n_loc = counts[r] if len(counts) > 1 else len(t_k_shard) - 1
     N = op.n_vertices
+    world = len(counts)
+    width = 2 * N
+    # Host delivery with equal shards: gather every finished batch over NCCL on a side stream and
+    # drain it to the host while the next batch is being solved.
+    pipelined = to_host and world > 1 and gather in ("all", "root") and len(set(counts)) == 1 and n_loc > 0
+    V_host = None
+    if pipelined:
+        dist = _dist()
+        root = 0 if gather == "root" else None
+        receives = root is None or r == root
+        if receives:
+            V_host = np.empty((sum(counts), width), dtype=np.float64)
+        drain = cof._solver(op).drain(width)
+
+        def on_batch(k0, k1, Vd):
+            def collect():
+                if root is None:
+                    out = torch.empty((world, k1 - k0, width), dtype=Vd.dtype, device=Vd.device)
+                    dist.all_gather_into_tensor(out.view(world * (k1 - k0), width), Vd.contiguous())
+                    return out
+                out = torch.empty((world, k1 - k0, width), dtype=Vd.dtype, device=Vd.device) if receives else None
+                dist.gather(Vd.contiguous(), list(out.unbind(0)) if receives else None, dst=root)
+                return out
+            out = drain.on_side_stream(collect)
+            if receives:
+                for q in range(world):
+                    drain.submit(out[q], V_host[q * n_loc + k0:q * n_loc + k1])
+    else:
+        on_batch = None
+
     if n_loc > 0:
         I_dev, I2_dev = cof._upload_signals(op, I_shard, I2_shard, n_loc)
-        V_loc, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc)
+        V_loc, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc, on_batch=on_batch)
         rep = np.stack([info.iterations.astype(np.float64), info.relres, info.status.astype(np.float64)], axis=1)
     else:
-        V_loc = torch.empty((0, 2 * N), dtype=torch.float64, device=op.device)
+        V_loc = torch.empty((0, width), dtype=torch.float64, device=op.device)
         rep = np.zeros((0, 3))
     rep_dev = torch.from_numpy(rep).to(op.device)
-    if gather == "none" or len(counts) == 1:
+    if pipelined:
+        drain.finish()
+        torch.cuda.current_stream(op.device).wait_stream(drain.stream)
+        rep_all = gather_rows(rep_dev, counts, root=0 if gather == "root" else None)
+        if rep_all is None:
+            return None, SolveInfo(info.iterations, info.relres, info.status)
+        rep_np = rep_all.cpu().numpy()
+        return V_host, SolveInfo(rep_np[:, 0].astype(np.int32), rep_np[:, 1].copy(), rep_np[:, 2].astype(np.int32))
+    if gather == "none" or world == 1:
         V_all, rep_all = V_loc, rep_dev
     else:
         root = 0 if gather == "root" else None
         V_all = gather_rows(V_loc, counts, root=root)
         rep_all = gather_rows(rep_dev, counts, root=root)
     if V_all is None:
-        return None, SolveInfo(info.iterations, info.relres, info.status) if n_loc > 0 else None
+        return None, (SolveInfo(info.iterations, info.relres, info.status) if n_loc > 0 else None)
     rep_np = rep_all.cpu().numpy()
     info = SolveInfo(rep_np[:, 0].astype(np.int32), rep_np[:, 1].copy(), rep_np[:, 2].astype(np.int32))
     return (V_all.cpu().numpy() if to_host else V_all), info

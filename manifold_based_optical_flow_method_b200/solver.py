@@ -16,7 +16,7 @@ DEFAULT_TOL = 1e-12          # ||b - A x|| / ||b||, north-star parity setting
 DEFAULT_MAX_ITER = 20000
 DEFAULT_CHECK_EVERY = 32
 DEFAULT_MAX_RESTARTS = 3
-DEFAULT_BATCH_GROUPS = 8     # 8 x 32 = 256 frames per launch (~15 GB at 164k vertices)
+DEFAULT_BATCH_GROUPS = 16    # 16 x 32 = 512 frames per launch (~30 GB at 164k vertices)
 
 
 @dataclasses.dataclass
@@ -98,6 +98,7 @@ class VelocitySolver:
             batch_groups = max(1, min(DEFAULT_BATCH_GROUPS, int(0.6 * free) // max(per_group, 1)))
         self.batch_groups = int(batch_groups)
         self._batch = None
+        self._drain = None
         self.profile = None          # set to _lib.PcgProfile() to accumulate sampled kernel timings
         self.aux_launches = 0        # pack / assemble / unpack launches issued so far
 
@@ -106,6 +107,13 @@ class VelocitySolver:
             self._batch = None
             self._batch = FrameBatch(self.op, n_groups)
         return self._batch
+
+    def drain(self, width, rows=None):
+        """Cached HostDrain with staging buffers of (rows or one batch) x width doubles."""
+        rows = int(rows or self.batch_groups * GROUP)
+        if self._drain is None or not self._drain.fits(rows, width):
+            self._drain = HostDrain(self.torch, self.op.device, rows, width)
+        return self._drain
 
     def assemble(self, batch, I_now, I_next, dt, lambda_, n_frames):
         """pack + K1 for the first n_frames rows of I_now / I_next (device, (>=n_frames, N))."""
@@ -140,9 +148,11 @@ class VelocitySolver:
         _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
         return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames])
 
-    def solve_frames(self, I_dev, I2_dev, dt_dev, lambda_, V_dev=None):
+    def solve_frames(self, I_dev, I2_dev, dt_dev, lambda_, V_dev=None, on_batch=None):
         """All frames k = 0 .. n-1 with (I_dev[k], I2_dev[k+1]) (compute_optical_flow.py:174-175).
         I_dev, I2_dev: device (>= n+1, N) float64 (may be the same tensor); dt_dev: device (n,).
+        on_batch(k0, k1, V_dev[k0:k1]) is called after each batch has been queued on the stream
+        (used to drain results to the host while the next batch is being solved).
         -> (V_dev (n, 2N) device, SolveInfo)"""
         torch, op = self.torch, self.op
         n = int(dt_dev.shape[0])
@@ -153,12 +163,96 @@ class VelocitySolver:
         for k0 in range(0, n, step):
             k1 = min(n, k0 + step)
             infos.append(self.solve_batch(I_dev[k0:k1], I2_dev[k0 + 1:k1 + 1], dt_dev[k0:k1], lambda_, V_dev[k0:k1]))
+            if on_batch is not None:
+                on_batch(k0, k1, V_dev[k0:k1])
         if infos:
             info = SolveInfo(np.concatenate([i.iterations for i in infos]), np.concatenate([i.relres for i in infos]),
                              np.concatenate([i.status for i in infos]))
         else:
             info = SolveInfo(np.zeros(0, np.int32), np.zeros(0), np.zeros(0, np.int32))
         return V_dev, info
+
+
+class HostDrain:
+    """Device -> host pipeline that overlaps the D2H copy of finished batches with the solve
+    of the next one: rows are copied on a side stream into a ring of pinned staging buffers
+    and a worker thread moves them into the caller's (pageable) numpy array.  The solver's
+    host thread sits inside libmof_b200 (GIL released) meanwhile."""
+
+    def __init__(self, torch, device, max_rows, width, n_stages=2, copy_threads=4):
+        import queue
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.torch, self.device = torch, device
+        self.max_rows, self.width = int(max_rows), int(width)
+        self.stages = [torch.empty((self.max_rows, self.width), dtype=torch.float64).pin_memory() for _ in range(n_stages)]
+        self.free = [threading.Event() for _ in range(n_stages)]
+        for f in self.free:
+            f.set()
+        self.stream = torch.cuda.Stream(device=device)
+        self.queue = queue.Queue()
+        self.pool = ThreadPoolExecutor(copy_threads)
+        self.copy_threads = copy_threads
+        self.count = 0
+        self.error = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def fits(self, rows, width):
+        return rows <= self.max_rows and width == self.width
+
+    def on_side_stream(self, fn):
+        """Run ``fn()`` with the side stream current, after everything queued so far on the
+        compute stream (used for the per-batch NCCL gather).  Returns fn's result."""
+        torch = self.torch
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            return fn()
+
+    def submit(self, src_dev, dst_host):
+        """Queue rows ``src_dev`` (device (r, width), produced on the current stream or on the
+        side stream) for delivery into ``dst_host`` (numpy (r, width))."""
+        torch = self.torch
+        i = self.count % len(self.stages)
+        self.count += 1
+        self.free[i].wait()
+        self.free[i].clear()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            r = int(src_dev.shape[0])
+            self.stages[i][:r].copy_(src_dev, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.queue.put((i, r, dst_host, done, src_dev))
+
+    def _run(self):
+        while True:
+            item = self.queue.get()
+            if item is None:
+                self.queue.task_done()
+                return
+            i, r, dst, done, _keep = item
+            try:
+                done.synchronize()
+                src = self.stages[i][:r].numpy()
+                parts = max(1, min(self.copy_threads, r))
+                edges = [r * q // parts for q in range(parts + 1)]
+                list(self.pool.map(lambda ab: np.copyto(dst[ab[0]:ab[1]], src[ab[0]:ab[1]]), zip(edges[:-1], edges[1:])))
+            except Exception as exc:   # surfaced by finish()
+                self.error = exc
+            finally:
+                self.free[i].set()
+                self.queue.task_done()
+
+    def finish(self):
+        self.queue.join()
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise err
 
 
 def frame_dt(t_k, k0, k1):
