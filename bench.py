@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=1000, help="frames of signal per GPU (frames-1 solves per step)")
     ap.add_argument("--batch-groups", type=int, default=None)
     ap.add_argument("--tol", type=float, default=1e-12)
+    ap.add_argument("--precond", default=None, choices=["ssor", "jacobi"], help="default: the package default")
+    ap.add_argument("--omega", type=float, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=None)
@@ -270,6 +272,10 @@ def run_b200(args):
     del I_np
     cof.settings["tol"] = args.tol
     cof.settings["batch_groups"] = args.batch_groups
+    if args.precond:
+        cof.settings["precond"] = args.precond
+    if args.omega:
+        cof.settings["omega"] = args.omega
     t0 = time.time()
     op, grad_w, e, integral, geom_s = cof.compute_geometrical_quantities(coords, normals, tris, areas)
     nb = op.n_blocks
@@ -298,34 +304,67 @@ def run_b200(args):
     converged = bool(info.converged)
     value = world * n * args.steps / (ms_total * 1e-3)
 
-    # ---- roofline of the dominant kernel (SpMV), sampled live inside the timed region
+    # ---- roofline of the dominant kernel(s), sampled live inside the timed region
     peak, peak_src = peaks()
-    spmv_bytes = prof.frame_launches * (32.0 * nb + 32.0 * N) + prof.group_launches * (4.0 * nb + 4.0 * (N + 1))
-    upd_bytes = prof.frame_launches * (64.0 + 24.0 + 48.0) * N
-    pup_bytes = prof.frame_launches * 48.0 * N
     gbs = lambda b, ms: (b / (ms * 1e-3) / 1e9) if ms > 0 else None
-    achieved = gbs(spmv_bytes, prof.ms_spmv)
-    traffic = ncu_traffic()
+    fl, gl, smp = prof.frame_launches, prof.group_launches, max(prof.samples, 1)
+    idx_bytes = gl * (4.0 * nb + 4.0 * (N + 1))
+    ms_iter = prof.ms_spmv + prof.ms_update + prof.ms_pupdate
+    if solver.precond == "jacobi":
+        # spmv: values 32 nb + p 16 N + ap 16 N ; update: read p, ap, x, r, minv, write x, r, z ; pupdate: z, p -> p
+        per_frame = {"spmv": 32.0 * nb + 32.0 * N, "update": (64.0 + 24.0 + 48.0) * N, "pupdate": 48.0 * N}
+        dom_name = "spmv_kernel<true> (ap = A p, p'Ap, alpha)"
+        dom_bytes, dom_ms = fl * per_frame["spmv"] + idx_bytes, prof.ms_spmv
+        others = {"update_kernel": {"achieved": gbs(fl * per_frame["update"], prof.ms_update), "avg_ms": prof.ms_update / smp},
+                  "pupdate_kernel": {"achieved": gbs(fl * per_frame["pupdate"], prof.ms_pupdate), "avg_ms": prof.ms_pupdate / smp}}
+        traffic = ncu_traffic()
+        traffic_val = traffic["dram_bytes_per_frame_launch"] * fl / smp if traffic else None
+    else:
+        # backward sweeps: U blocks 16 (nb-N) + Dt 24 N + read z, p + write p, t (64 N)
+        # forward  sweeps: L blocks 16 (nb-N) + Dt 24 N + read p, t + write w (48 N)
+        # update         : read p, w, t, x, r (80 N) + Dt 24 N, write x, r, z (48 N)
+        per_frame = {"sweep_back": 16.0 * (nb - N) + 88.0 * N, "sweep_fwd": 16.0 * (nb - N) + 72.0 * N,
+                     "update": 152.0 * N}
+        dom_name = "sweep_back_kernel<0> + sweep_fwd_kernel<0> (Eisenstat SSOR operator, all colours of one iteration)"
+        dom_bytes = fl * (per_frame["sweep_back"] + per_frame["sweep_fwd"]) + 2 * idx_bytes
+        dom_ms = prof.ms_spmv + prof.ms_pupdate
+        others = {"sweep_back (all colours)": {"achieved": gbs(fl * per_frame["sweep_back"] + idx_bytes, prof.ms_spmv), "avg_ms": prof.ms_spmv / smp},
+                  "sweep_fwd (all colours)": {"achieved": gbs(fl * per_frame["sweep_fwd"] + idx_bytes, prof.ms_pupdate), "avg_ms": prof.ms_pupdate / smp},
+                  "update_kernel": {"achieved": gbs(fl * per_frame["update"], prof.ms_update), "avg_ms": prof.ms_update / smp}}
+        traffic_val = None
+    achieved = gbs(dom_bytes, dom_ms)
     roofline = {
-        "kernel": "spmv_kernel<true> (ap = A p, p'Ap, alpha)", "bound": "hbm", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        # ncu dram__bytes_read+write per launch, scaled from the committed 32-frame capture to this
-        # run's average number of active frames per launch (profiles/spmv_traffic.json)
-        "traffic": (traffic["dram_bytes_per_frame_launch"] * prof.frame_launches / prof.samples)
-        if (traffic and prof.samples) else None,
-        "algorithmic_bytes_per_launch": spmv_bytes / prof.samples if prof.samples else None,
-        "peak_source": peak_src, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-        "algorithmic_bytes_per_frame_launch": 32.0 * nb + 32.0 * N, "sampled_launches": int(prof.samples),
-        "avg_launch_ms": prof.ms_spmv / prof.samples if prof.samples else None,
-        "avg_active_frames_per_launch": prof.frame_launches / prof.samples if prof.samples else None,
-        "other_kernels": {
-            "update_kernel": {"achieved": gbs(upd_bytes, prof.ms_update), "avg_launch_ms": prof.ms_update / max(prof.samples, 1)},
-            "pupdate_kernel": {"achieved": gbs(pup_bytes, prof.ms_pupdate), "avg_launch_ms": prof.ms_pupdate / max(prof.samples, 1)},
-        },
-        "pcg_time_share": {"spmv": prof.ms_spmv / max(prof.ms_spmv + prof.ms_update + prof.ms_pupdate, 1e-9),
-                           "update": prof.ms_update / max(prof.ms_spmv + prof.ms_update + prof.ms_pupdate, 1e-9),
-                           "pupdate": prof.ms_pupdate / max(prof.ms_spmv + prof.ms_update + prof.ms_pupdate, 1e-9)},
+        "kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": traffic_val,
+        "algorithmic_bytes_per_launch": dom_bytes / smp, "peak_source": peak_src,
+        "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
+        "algorithmic_bytes_per_frame_iteration": per_frame, "sampled_iterations": int(prof.samples),
+        "avg_active_frames_per_launch": fl / smp, "other_kernels": others,
+        "iteration_time_share": {"dominant": dom_ms / max(ms_iter, 1e-9), "rest": 1.0 - dom_ms / max(ms_iter, 1e-9)},
     }
+
+    # ---- SpMV micro-measurement (BASELINE.json names "SpMV HBM GB/s"): the solver's SpMV kernel on
+    # the last assembled batch, K launches back to back
+    batch = solver._batch
+    ms_, bs_ = op.struct(), batch.struct()
+    stream = torch.cuda.current_stream().cuda_stream
+    sp0, sp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import ctypes as _ct
+    for _ in range(3):
+        _lib.check(_lib.load().mof_spmv_batch(_ct.byref(ms_), _ct.byref(bs_), batch.z.data_ptr(), batch.ap.data_ptr(), stream))
+    sp0.record()
+    n_sp = 20
+    for _ in range(n_sp):
+        _lib.check(_lib.load().mof_spmv_batch(_ct.byref(ms_), _ct.byref(bs_), batch.z.data_ptr(), batch.ap.data_ptr(), stream))
+    sp1.record()
+    torch.cuda.synchronize()
+    sp_groups = bs_.n_groups
+    sp_bytes = sp_groups * (32 * (32.0 * nb + 32.0 * N) + 4.0 * nb + 4.0 * (N + 1))
+    spmv_gbs = sp_bytes * n_sp / (sp0.elapsed_time(sp1) * 1e-3) / 1e9
+    roofline["spmv"] = {"achieved": spmv_gbs, "frac": spmv_gbs / peak, "frac_of_nominal_8TBs": spmv_gbs / 8000.0,
+                        "frames_per_launch": sp_groups * 32, "launches": n_sp,
+                        "note": "mof_spmv_batch (block-CSR, frame-minor) on the assembled batch; in-solver use: "
+                                + ("every iteration" if solver.precond == "jacobi" else "true-residual verification")}
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the reference-shaped API
     e2e = None
@@ -361,6 +400,8 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "n_vertices": N, "n_faces": len(tris), "n_blocks": nb,
                        "frames_per_step": world * n, "batch_frames": solver.batch_groups * 32,
+                       "preconditioner": solver.precond + (f" (omega={solver.omega})" if solver.precond == "ssor" else ""),
+                       "ordering": "block multicolour (RCB patches of 64)" if op.pattern.n_colors else "Cuthill-McKee",
                        "l2": "no flush: the per-step working set (1.17 GB of matrix values per 32-frame group) is >> 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), one process per GPU"},
             "clocks": clock_report, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

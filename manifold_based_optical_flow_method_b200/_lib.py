@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(HERE, "csrc", "libmof_b200.so")
 GROUP = 32           # MOF_GROUP
 TILE_ROWS = 64       # MOF_TILE_ROWS
 DETECT_CHUNK = 1024  # MOF_DETECT_CHUNK
+MAX_COLORS = 16      # MOF_MAX_COLORS
+SCAL_SLOTS = 12      # MOF_SCAL_SLOTS
 
 STATUS_CONVERGED, STATUS_MAXITER, STATUS_BREAKDOWN, STATUS_ZERO_RHS = 0, 1, 2, 3
 
@@ -21,7 +23,7 @@ STATUS_CONVERGED, STATUS_MAXITER, STATUS_BREAKDOWN, STATUS_ZERO_RHS = 0, 1, 2, 3
 EXPORTS = [
     "mof_last_error_string", "mof_version",
     "mof_pattern_create", "mof_pattern_destroy", "mof_pattern_num_blocks", "mof_pattern_num_contrib",
-    "mof_pattern_max_row_blocks", "mof_pattern_bandwidth", "mof_pattern_export",
+    "mof_pattern_max_row_blocks", "mof_pattern_bandwidth", "mof_pattern_export", "mof_pattern_colors",
     "mof_num_tiles", "mof_state_ints",
     "mof_geom_basis", "mof_geom_gradw", "mof_geom_a2",
     "mof_pack_frames", "mof_assemble_batch",
@@ -43,6 +45,7 @@ class MeshDev(Structure):
         ("perm", c_void_p), ("rowptr", c_void_p), ("col", c_void_p), ("diag", c_void_p),
         ("cptr", c_void_p), ("centry", c_void_p), ("tri", c_void_p),
         ("e", c_void_p), ("grad_w", c_void_p), ("integral", c_void_p), ("areas", c_void_p), ("a2v", c_void_p),
+        ("n_colors", c_int32), ("color_tile_ptr", c_int32 * (MAX_COLORS + 1)),
     ]
 
 
@@ -51,7 +54,7 @@ class BatchDev(Structure):
     _fields_ = [
         ("n_groups", c_int32), ("n_frames", c_int32),
         ("It", c_void_p), ("dIt", c_void_p), ("vals", c_void_p), ("rhs", c_void_p), ("minv", c_void_p),
-        ("x", c_void_p), ("r", c_void_p), ("z", c_void_p), ("p", c_void_p), ("ap", c_void_p),
+        ("x", c_void_p), ("r", c_void_p), ("z", c_void_p), ("p", c_void_p), ("ap", c_void_p), ("t", c_void_p),
         ("partial", c_void_p), ("scal", c_void_p), ("state", c_void_p),
     ]
 
@@ -74,7 +77,9 @@ def _declare(lib):
     lib.mof_last_error_string.argtypes = []
     lib.mof_version.restype = c_int
     lib.mof_pattern_create.restype = c_int
-    lib.mof_pattern_create.argtypes = [c_int64, c_int64, P, c_int, POINTER(c_void_p)]
+    lib.mof_pattern_create.argtypes = [c_int64, c_int64, P, c_int, P, POINTER(c_void_p)]
+    lib.mof_pattern_colors.restype = c_int
+    lib.mof_pattern_colors.argtypes = [P, POINTER(c_int32), P]
     lib.mof_pattern_destroy.restype = None
     lib.mof_pattern_destroy.argtypes = [P]
     for name in ("mof_pattern_num_blocks", "mof_pattern_num_contrib", "mof_pattern_max_row_blocks", "mof_pattern_bandwidth"):
@@ -95,11 +100,11 @@ def _declare(lib):
     lib.mof_pack_frames.restype = c_int
     lib.mof_pack_frames.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, P, c_int64, P, P]
     lib.mof_assemble_batch.restype = c_int
-    lib.mof_assemble_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, P]
+    lib.mof_assemble_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, c_double, P]
     lib.mof_spmv_batch.restype = c_int
     lib.mof_spmv_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, P, P]
     lib.mof_pcg_solve_batch.restype = c_int
-    lib.mof_pcg_solve_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, c_int32, c_int32, c_int32, P, P, P,
+    lib.mof_pcg_solve_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, c_double, c_int32, c_int32, c_int32, P, P, P,
                                         POINTER(PcgProfile), P]
     lib.mof_unpack_solution.restype = c_int
     lib.mof_unpack_solution.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, c_int64, P]

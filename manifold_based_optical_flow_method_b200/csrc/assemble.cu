@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) pack_kernel(int64_t N, int32_t n_frames, 
     }
 }
 
-__global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_) {
+__global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, double diag_scale) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = blockIdx.y;
     const int64_t N = M.n_vertices, nb = M.n_blocks;
@@ -66,7 +66,13 @@ __global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch
             if (b == bd) {
                 mof_assemble_block_body<true>(M, v, b, It_l, dIt_l, lambda_, a, f);
                 double mi[3];
-                mof_inv2_body(a, mi);
+                if (diag_scale == 0.0) {
+                    mof_inv2_body(a, mi);                      // block-Jacobi: D^-1
+                } else {                                       // SSOR: Dt = D / omega
+                    mi[0] = a[0] * diag_scale;
+                    mi[1] = 0.5 * (a[1] + a[2]) * diag_scale;
+                    mi[2] = a[3] * diag_scale;
+                }
                 B.rhs[mof_ix_vec(N, g, v, 0) + lane] = f[0];
                 B.rhs[mof_ix_vec(N, g, v, 1) + lane] = f[1];
                 B.minv[mof_ix_minv(N, g, v, 0) + lane] = mi[0];
@@ -102,11 +108,12 @@ extern "C" int mof_pack_frames(const mof_mesh_dev* mesh, const mof_batch_dev* ba
 }
 
 extern "C" int mof_assemble_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double lambda_,
-                                  void* stream) {
+                                  double omega, void* stream) {
     MOF_REQUIRE(mesh && batch, "NULL argument");
+    MOF_REQUIRE(omega >= 0.0 && omega < 2.0, "omega must be 0 (block Jacobi) or in (0,2) (SSOR)");
     MOF_REQUIRE(batch->It && batch->dIt && batch->vals && batch->rhs && batch->minv, "batch buffers missing");
     dim3 grid((unsigned)mof_num_tiles(mesh->n_vertices), batch->n_groups);
-    assemble_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch, lambda_);
+    assemble_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch, lambda_, omega > 0.0 ? 1.0 / omega : 0.0);
     MOF_LAUNCH_CHECK("assemble_kernel");
     return 0;
 }

@@ -34,8 +34,12 @@ static inline cudaStream_t mof_stream(void* s) { return reinterpret_cast<cudaStr
 static inline unsigned mof_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // scal[g][MOF_S_*][32]
+//   RZ r'z, PAP p'Ap, RR r'r (recurrence), BB ||r0||^2 of the iterated (possibly transformed) system,
+//   ALPHA/BETA/ZS step scalars (frozen frame: 0 / 1 / 0), RRTRUE ||b - A x||^2, BBT ||b||^2,
+//   THR per-frame threshold on RR/BB, BETA_SAVED beta of a frozen frame for an exact resume
 enum { MOF_S_RZ = 0, MOF_S_PAP = 1, MOF_S_RR = 2, MOF_S_BB = 3, MOF_S_ALPHA = 4, MOF_S_BETA = 5,
-       MOF_S_RRTRUE = 6, MOF_S_SPARE = 7, MOF_S_COUNT = 8 };
+       MOF_S_RRTRUE = 6, MOF_S_BBT = 7, MOF_S_THR = 8, MOF_S_ZS = 9, MOF_S_BETA_SAVED = 10, MOF_S_SPARE = 11,
+       MOF_S_COUNT = 12 };
 // state[g][MOF_I_*][32], then group_done[G], ticket[G], groups_active[1]
 enum { MOF_I_ACTIVE = 0, MOF_I_ITERS = 1, MOF_I_STATUS = 2, MOF_I_SPARE = 3, MOF_I_COUNT = 4 };
 #define MOF_STATUS_PENDING (-1)

@@ -22,6 +22,7 @@
 struct mof_pattern {
     int64_t N = 0, F = 0;
     std::vector<int32_t> perm, rowptr, col, diag, cptr, centry, tri;
+    std::vector<int32_t> color_tile_ptr;     // block-multicolor ordering only: tiles of colour c
     int64_t max_row = 0, bandwidth = 0;
 };
 
@@ -67,10 +68,96 @@ int32_t bfs_far(int32_t start, const std::vector<int64_t>& aptr, const std::vect
     return q.back();
 }
 
+// Recursive coordinate bisection of the vertex set into patches of exactly `tile` vertices
+// (one remainder patch at most): split along the longest box axis at a multiple of `tile`.
+void rcb(std::vector<int32_t>& ids, size_t lo, size_t hi, const double* xyz, size_t tile,
+         std::vector<std::pair<size_t, size_t>>& leaves) {
+    const size_t n = hi - lo;
+    if (n <= tile) { leaves.emplace_back(lo, hi); return; }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (size_t q = lo; q < hi; ++q)
+        for (int a = 0; a < 3; ++a) {
+            double c = xyz[3 * size_t(ids[q]) + a];
+            mn[a] = std::min(mn[a], c);
+            mx[a] = std::max(mx[a], c);
+        }
+    int ax = 0;
+    for (int a = 1; a < 3; ++a) if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
+    size_t half = ((n / 2 + tile - 1) / tile) * tile;
+    if (half >= n) half = n - (n % tile ? n % tile : tile);
+    std::nth_element(ids.begin() + lo, ids.begin() + lo + half, ids.begin() + hi, [&](int32_t a, int32_t b) {
+        double ca = xyz[3 * size_t(a) + ax], cb = xyz[3 * size_t(b) + ax];
+        return ca != cb ? ca < cb : a < b;
+    });
+    rcb(ids, lo, lo + half, xyz, tile, leaves);
+    rcb(ids, lo + half, hi, xyz, tile, leaves);
+}
+
+// Block-multicolour ordering for the SSOR sweeps: RCB patches of MOF_TILE_ROWS vertices,
+// greedy colouring of the patch graph, numbering colour-major; inside a patch vertices keep
+// their Cuthill-McKee rank order.  cm_rank[v] = position of reference vertex v in the CM order.
+void block_multicolor(int64_t N, const double* xyz, const std::vector<int64_t>& aptr, const std::vector<int32_t>& adj,
+                      const std::vector<int32_t>& cm_rank, std::vector<int32_t>& perm,
+                      std::vector<int32_t>& color_tile_ptr) {
+    const size_t tile = MOF_TILE_ROWS;
+    std::vector<int32_t> ids(N);
+    for (int64_t v = 0; v < N; ++v) ids[v] = int32_t(v);
+    std::vector<std::pair<size_t, size_t>> leaves;
+    rcb(ids, 0, size_t(N), xyz, tile, leaves);
+    const int32_t np = int32_t(leaves.size());
+    std::vector<int32_t> pid(N);
+    for (int32_t k = 0; k < np; ++k)
+        for (size_t q = leaves[k].first; q < leaves[k].second; ++q) pid[ids[q]] = k;
+    // greedy colouring of the patch adjacency graph in RCB (space-filling) order
+    std::vector<int32_t> color(np, -1);
+    std::vector<uint8_t> used;
+    int32_t ncol = 0;
+    for (int32_t k = 0; k < np; ++k) {
+        used.assign(size_t(ncol) + 1, 0);
+        for (size_t q = leaves[k].first; q < leaves[k].second; ++q) {
+            int32_t v = ids[q];
+            for (int64_t e = aptr[v]; e < aptr[v + 1]; ++e) {
+                int32_t c = color[pid[adj[e]]];
+                if (c >= 0 && pid[adj[e]] != k) used[c] = 1;
+            }
+        }
+        int32_t c = 0;
+        while (c < ncol && used[c]) ++c;
+        color[k] = c;
+        if (c == ncol) ++ncol;
+    }
+    // the (single) short patch must be the very last tile: make its colour class the last one
+    int32_t short_patch = -1;
+    for (int32_t k = 0; k < np; ++k)
+        if (leaves[k].second - leaves[k].first != tile) short_patch = k;
+    std::vector<int32_t> class_order(ncol);
+    for (int32_t c = 0; c < ncol; ++c) class_order[c] = c;
+    if (short_patch >= 0) std::swap(class_order[color[short_patch]], class_order[ncol - 1]);
+    // class_order[c] = position of colour c; invert to iterate positions
+    std::vector<int32_t> at(ncol);
+    for (int32_t c = 0; c < ncol; ++c) at[class_order[c]] = c;
+    perm.clear();
+    perm.reserve(N);
+    color_tile_ptr.assign(1, 0);
+    int32_t tiles = 0;
+    for (int32_t pos = 0; pos < ncol; ++pos) {
+        const int32_t c = at[pos];
+        for (int pass = 0; pass < 2; ++pass)          // the short patch goes last inside its class
+            for (int32_t k = 0; k < np; ++k) {
+                if (color[k] != c || ((k == short_patch) != (pass == 1))) continue;
+                size_t b = perm.size();
+                for (size_t q = leaves[k].first; q < leaves[k].second; ++q) perm.push_back(ids[q]);
+                std::sort(perm.begin() + b, perm.end(), [&](int32_t a, int32_t d) { return cm_rank[a] < cm_rank[d]; });
+                ++tiles;
+            }
+        color_tile_ptr.push_back(tiles);
+    }
+}
+
 }  // namespace
 
 extern "C" int mof_pattern_create(int64_t N, int64_t F, const int64_t* triangles, int reorder,
-                                  mof_pattern** out) {
+                                  const double* coords, mof_pattern** out) {
     if (!out) return mof_set_error(-1, "mof_pattern_create: out is NULL");
     *out = nullptr;
     if (N <= 0 || F < 0 || !triangles) return mof_set_error(-1, "mof_pattern_create: bad sizes");
@@ -112,6 +199,10 @@ extern "C" int mof_pattern_create(int64_t N, int64_t F, const int64_t* triangles
         std::vector<uint64_t>().swap(edges);
 
         // --- renumbering
+        if (reorder == 2 && !coords) {
+            delete P;
+            return mof_set_error(-1, "mof_pattern_create: reorder = 2 (block multicolour) needs coordinates");
+        }
         P->perm.resize(N);
         if (reorder) {
             std::vector<uint8_t> seen(N, 0);
@@ -125,6 +216,13 @@ extern "C" int mof_pattern_create(int64_t N, int64_t F, const int64_t* triangles
                 cm_bfs(b, aptr, adj, seen, order, scratch);
             }
             P->perm.swap(order);
+            if (reorder == 2) {
+                std::vector<int32_t> cm_rank(N);
+                for (int64_t v = 0; v < N; ++v) cm_rank[P->perm[v]] = int32_t(v);
+                std::vector<int32_t> bm;
+                block_multicolor(N, coords, aptr, adj, cm_rank, bm, P->color_tile_ptr);
+                P->perm.swap(bm);
+            }
         } else {
             for (int64_t v = 0; v < N; ++v) P->perm[v] = int32_t(v);
         }
@@ -187,6 +285,16 @@ extern "C" int64_t mof_pattern_num_blocks(const mof_pattern* p) { return p ? int
 extern "C" int64_t mof_pattern_num_contrib(const mof_pattern* p) { return p ? int64_t(p->centry.size()) : -1; }
 extern "C" int64_t mof_pattern_max_row_blocks(const mof_pattern* p) { return p ? p->max_row : -1; }
 extern "C" int64_t mof_pattern_bandwidth(const mof_pattern* p) { return p ? p->bandwidth : -1; }
+
+extern "C" int mof_pattern_colors(const mof_pattern* p, int32_t* n_colors, int32_t* color_tile_ptr) {
+    if (!p || !n_colors) return mof_set_error(-1, "mof_pattern_colors: NULL argument");
+    const int32_t nc = p->color_tile_ptr.empty() ? 0 : int32_t(p->color_tile_ptr.size()) - 1;
+    if (nc > MOF_MAX_COLORS) return mof_set_error(-2, "mof_pattern_colors: %d colours exceed MOF_MAX_COLORS", nc);
+    *n_colors = nc;
+    if (color_tile_ptr)
+        for (int32_t c = 0; c <= nc && nc > 0; ++c) color_tile_ptr[c] = p->color_tile_ptr[c];
+    return 0;
+}
 
 extern "C" int mof_pattern_export(const mof_pattern* p, int32_t* perm, int32_t* rowptr, int32_t* col,
                                   int32_t* diag, int32_t* cptr, int32_t* centry, int32_t* tri) {

@@ -46,6 +46,30 @@ __device__ __forceinline__ int32_t* ticket_ptr(int32_t* st, int G) { return grou
 __device__ __forceinline__ int32_t* groups_active_ptr(int32_t* st, int G) { return group_done_ptr(st, G) + 2 * G; }
 __device__ __forceinline__ int32_t* lanes_active_ptr(int32_t* st, int G) { return group_done_ptr(st, G) + 2 * G + 1; }
 
+// Sum the per-tile partials of group g in tile-index order (8 warps take strided subsets, then
+// are combined in warp order).  Called by every thread of the last CTA; `tot` valid in warp 0.
+template <int NV>
+__device__ __forceinline__ void reduce_all_tiles(const double* __restrict__ partial_g, int ntiles, double (&tot)[NV],
+                                                 double (*red)[NV][MOF_W]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double acc = 0.0;
+        for (int t = warp; t < ntiles; t += kWarps) acc += __ldcg(partial_g + ((size_t)t * 2 + k) * MOF_W + lane);
+        red[warp][k][lane] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = red[0][k][lane];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s += red[w][k][lane];
+            tot[k] = s;
+        }
+    }
+}
+
 // Deterministic CTA + cross-tile reduction of NV per-lane values.  Returns true (for every
 // thread of the CTA) in the last CTA of group g; there `tot` holds the totals in warp 0.
 template <int NV>
@@ -72,24 +96,27 @@ __device__ __forceinline__ bool tile_reduce(const double (&val)[NV], double* __r
     __syncthreads();
     if (!s_last) return false;
     __threadfence();
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        double acc = 0.0;
-        for (int t = warp; t < ntiles; t += kWarps) acc += __ldcg(partial_g + ((size_t)t * 2 + k) * MOF_W + lane);
-        red[warp][k][lane] = acc;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double s = red[0][k][lane];
-#pragma unroll
-            for (int w = 1; w < kWarps; ++w) s += red[w][k][lane];
-            tot[k] = s;
-        }
-    }
+    reduce_all_tiles<NV>(partial_g, ntiles, tot, red);
     if (threadIdx.x == 0) *ticket_g = 0;
     return true;
+}
+
+// alpha = r'z / p'Ap for the frames still iterating (0 for the others); p'Ap <= 0 / NaN -> breakdown
+__device__ __forceinline__ void finalize_alpha(double pap, double* scal, int32_t* state, int64_t g, int G, int lane) {
+    int32_t* active = state_ptr(state, g, MOF_I_ACTIVE);
+    double alpha = 0.0;
+    if (active[lane]) {
+        const double rz = scal_ptr(scal, g, MOF_S_RZ)[lane];
+        if (!(pap > 0.0) || isinf(pap)) {          // not SPD / NaN / overflow
+            state_ptr(state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
+            active[lane] = 0;
+            atomicSub(lanes_active_ptr(state, G), 1);
+        } else {
+            alpha = rz / pap;
+        }
+    }
+    scal_ptr(scal, g, MOF_S_PAP)[lane] = pap;
+    scal_ptr(scal, g, MOF_S_ALPHA)[lane] = alpha;
 }
 
 // ---------------------------------------------------------------------------------
@@ -162,29 +189,19 @@ __global__ void __launch_bounds__(256) spmv_kernel(const int32_t* __restrict__ r
     double val[1] = {dot}, tot[1];
     if (!tile_reduce<1>(val, partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(state, G) + g, tot))
         return;
-    if (warp == 0) {
-        int32_t* active = state_ptr(state, g, MOF_I_ACTIVE);
-        double alpha = 0.0;
-        if (active[lane]) {
-            const double pap = tot[0];
-            const double rz = scal_ptr(scal, g, MOF_S_RZ)[lane];
-            if (!(pap > 0.0) || isinf(pap)) {          // not SPD / NaN / overflow
-                state_ptr(state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
-                active[lane] = 0;
-                atomicSub(lanes_active_ptr(state, G), 1);
-            } else {
-                alpha = rz / pap;
-            }
-        }
-        scal_ptr(scal, g, MOF_S_PAP)[lane] = tot[0];
-        scal_ptr(scal, g, MOF_S_ALPHA)[lane] = alpha;
-    }
+    if (warp == 0) finalize_alpha(tot[0], scal, state, g, G, lane);
 }
 
 // ---------------------------------------------------------------------------------
-// K3a: x += alpha p ; r -= alpha ap ; z = Minv r ; r'z, r'r ; beta and convergence.
+// K3a: x += alpha p ; r -= alpha q ; z = M r ; r'z, r'r ; beta and convergence.
+//   block Jacobi: q = ap = A p,            M = D^-1  (both in B.ap / B.minv)
+//   SSOR:         q = t + w = At p (B.t + B.ap), M = Dt = D/omega
+// A frame that meets its threshold is frozen with (alpha, beta, zscale) = (0, 1, 0), which
+// leaves x, r, z, p and r'z untouched, so that it can resume exactly where it stopped if the
+// true-residual check (init_kernel, MODE_VERIFY) asks for more iterations.
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N, int ntiles, double tol2) {
+template <bool SSOR>
+__global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N, int ntiles) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     if (group_done_ptr(B.state, G)[g]) return;
@@ -200,7 +217,8 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
         const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
         const size_t im = mof_ix_minv(N, g, v, 0) + lane;
         const double p0 = B.p[i0], p1 = B.p[i1];
-        const double a0 = __ldcs(B.ap + i0), a1 = __ldcs(B.ap + i1);
+        double a0 = __ldcs(B.ap + i0), a1 = __ldcs(B.ap + i1);
+        if (SSOR) { a0 += __ldcs(B.t + i0); a1 += __ldcs(B.t + i1); }
         double x0 = B.x[i0], x1 = B.x[i1];
         double r0 = B.r[i0], r1 = B.r[i1];
         const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
@@ -221,27 +239,31 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
         return;
     if (warp == 0) {
         int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
-        double beta = 0.0;
+        double beta = 1.0, zs = 0.0;                // frozen: p stays as it is
         int act = active[lane];
         const int was = act;
         if (act) {
             const double rz_old = scal_ptr(B.scal, g, MOF_S_RZ)[lane];
             const double bb = scal_ptr(B.scal, g, MOF_S_BB)[lane];
+            const double thr = scal_ptr(B.scal, g, MOF_S_THR)[lane];
             state_ptr(B.state, g, MOF_I_ITERS)[lane] += 1;
             scal_ptr(B.scal, g, MOF_S_RZ)[lane] = tot[0];
             scal_ptr(B.scal, g, MOF_S_RR)[lane] = tot[1];
             if (!isfinite(tot[0]) || !isfinite(tot[1])) {
                 state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
                 act = 0;
-            } else if (tot[1] <= tol2 * bb) {
+            } else if (tot[1] <= thr * bb) {
                 state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_CONVERGED;
+                scal_ptr(B.scal, g, MOF_S_BETA_SAVED)[lane] = tot[0] / rz_old;   // used if the frame resumes
                 act = 0;
             } else {
                 beta = tot[0] / rz_old;
+                zs = 1.0;
             }
             active[lane] = act;
         }
         scal_ptr(B.scal, g, MOF_S_BETA)[lane] = beta;
+        scal_ptr(B.scal, g, MOF_S_ZS)[lane] = zs;
         const int any = __any_sync(kFull, act);
         const int dropped = __popc(__ballot_sync(kFull, was && !act));
         if (lane == 0) {
@@ -254,27 +276,108 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
     }
 }
 
-// K3b: p = z + beta p
+// K3b (block Jacobi): p = zs z + beta p at the start of an iteration
 __global__ void __launch_bounds__(256) pupdate_kernel(mof_batch_dev B, int64_t N) {
     const int64_t g = blockIdx.y;
     if (group_done_ptr(B.state, B.n_groups)[g]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
     const double beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
+    const double zs = scal_ptr(B.scal, g, MOF_S_ZS)[lane];
 #pragma unroll 4
     for (int q = 0; q < kRowsPerWarp; ++q) {
         const int64_t v = row0 + q;
         if (v >= N) break;
         const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
         const double z0 = __ldcs(B.z + i0), z1 = __ldcs(B.z + i1);
-        B.p[i0] = fma(beta, B.p[i0], z0);
-        B.p[i1] = fma(beta, B.p[i1], z1);
+        B.p[i0] = fma(beta, B.p[i0], zs * z0);
+        B.p[i1] = fma(beta, B.p[i1], zs * z1);
     }
 }
 
-// Start (mode 0: x = 0, r = b) or verification / restart (mode 1: r = b - ap with
-// ap = A x already computed): z = Minv r, p = z, r'z, r'r and per-frame bookkeeping.
-__global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, int ntiles, int mode, double tol2) {
+// ---------------------------------------------------------------------------------
+// SSOR sweeps: one warp = one patch (tile) of the launch's colour, lane = frame.  The rows of
+// a patch are solved sequentially by the warp (mof_sweep_*_body); patches of one colour do not
+// touch each other, earlier colours are complete because they ran in earlier launches.
+// ---------------------------------------------------------------------------------
+// MODE 0: iteration (p <- zs z + beta p fused in, t = (Dt+U)^-1 p).  MODE 1: t = (Dt+U)^-1 pvec.
+template <int MODE>
+__global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                         const int32_t* __restrict__ diag, mof_batch_dev B, double* pvec,
+                                                         double* tout, int64_t N, int64_t nb, int tile0, int tile1) {
+    const int64_t g = blockIdx.y;
+    const int G = B.n_groups;
+    if (MODE == 0 && group_done_ptr(B.state, G)[g]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = tile0 + blockIdx.x * kWarps + warp;
+    if (tile >= tile1) return;
+    const int64_t r0 = (int64_t)tile * MOF_TILE_ROWS;
+    const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
+    double beta = 0.0, zs = 1.0;
+    if (MODE == 0) {
+        beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
+        zs = scal_ptr(B.scal, g, MOF_S_ZS)[lane];
+    }
+    mof_sweep_back_body(rowptr, col, diag, B.vals + (size_t)g * nb * 4 * MOF_W + lane,
+                        B.minv + (size_t)g * N * 3 * MOF_W + lane, B.z + (size_t)g * N * 2 * MOF_W + lane,
+                        pvec + (size_t)g * N * 2 * MOF_W + lane, tout + (size_t)g * N * 2 * MOF_W + lane, r0, r1, beta, zs, MODE);
+}
+
+// MODE 0: iteration (w = (Dt+L)^-1 (p - (2-omega) Dt t), p'(t+w) -> alpha in the last CTA of the
+// last colour).  MODE 1: wout = (Dt+L)^-1 pin.
+template <int MODE>
+__global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                        const int32_t* __restrict__ diag, mof_batch_dev B, const double* pin,
+                                                        double* wout, int64_t N, int64_t nb, int tile0, int tile1,
+                                                        int ntiles, double omega) {
+    const int64_t g = blockIdx.y;
+    const int G = B.n_groups;
+    if (MODE == 0 && group_done_ptr(B.state, G)[g]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = tile0 + blockIdx.x * kWarps + warp;
+    const bool valid = tile < tile1;
+    double dot = 0.0;
+    if (valid) {
+        const int64_t r0 = (int64_t)tile * MOF_TILE_ROWS;
+        const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
+        dot = mof_sweep_fwd_body(rowptr, col, diag, B.vals + (size_t)g * nb * 4 * MOF_W + lane,
+                                 B.minv + (size_t)g * N * 3 * MOF_W + lane, pin + (size_t)g * N * 2 * MOF_W + lane,
+                                 B.t + (size_t)g * N * 2 * MOF_W + lane, wout + (size_t)g * N * 2 * MOF_W + lane, r0, r1,
+                                 omega, MODE);
+    }
+    if (MODE != 0) return;
+    // one partial per patch; the CTA that completes the count over all colours reduces them
+    __shared__ double red[kWarps][1][MOF_W];
+    __shared__ int s_last;
+    double* partial_g = B.partial + (size_t)g * ntiles * 2 * MOF_W;
+    if (valid) partial_g[(size_t)tile * 2 * MOF_W + lane] = dot;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int cnt = min(kWarps, tile1 - (tile0 + (int)blockIdx.x * kWarps));
+        s_last = (atomicAdd(ticket_ptr(B.state, G) + g, cnt) + cnt == ntiles);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double tot[1];
+    reduce_all_tiles<1>(partial_g, ntiles, tot, red);
+    if (threadIdx.x == 0) ticket_ptr(B.state, G)[g] = 0;
+    if (warp == 0) finalize_alpha(tot[0], B.scal, B.state, g, G, lane);
+}
+
+// ---------------------------------------------------------------------------------
+// Start / verification kernel.
+//   MODE_START_JACOBI : x = 0, r = rhs, z = D^-1 r, p = 0 ; ||b||^2 ; per-frame bookkeeping
+//   MODE_NORM         : ||rhs||^2 -> BBT (true rhs norm for the SSOR path)
+//   MODE_START_SSOR   : r (= (Dt+L)^-1 rhs, already in B.r) ; x = 0, z = Dt r, p = 0 ; bookkeeping
+//   MODE_VERIFY       : true residual ||rhs - ap||^2 with ap = A x ; frames that were frozen on
+//                       the recurrence residual but miss tol get a tighter threshold and resume
+// ---------------------------------------------------------------------------------
+enum { MODE_START_JACOBI = 0, MODE_NORM = 1, MODE_START_SSOR = 2, MODE_VERIFY = 3 };
+
+__global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, int ntiles, int mode, double tol2,
+                                                   int last_round) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -285,62 +388,81 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
         const int64_t v = row0 + q;
         if (v >= N) break;
         const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
-        const size_t im = mof_ix_minv(N, g, v, 0) + lane;
-        double r0 = B.rhs[i0], r1 = B.rhs[i1];
-        if (mode == 0) {
+        double r0, r1;
+        if (mode == MODE_START_SSOR) { r0 = B.r[i0]; r1 = B.r[i1]; }
+        else                         { r0 = B.rhs[i0]; r1 = B.rhs[i1]; }
+        if (mode == MODE_VERIFY) { r0 -= B.ap[i0]; r1 -= B.ap[i1]; }
+        if (mode == MODE_START_JACOBI || mode == MODE_START_SSOR) {
+            const size_t im = mof_ix_minv(N, g, v, 0) + lane;
+            const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
+            const double z0 = m0 * r0 + m1 * r1;
+            const double z1 = m1 * r0 + m2 * r1;
             B.x[i0] = 0.0; B.x[i1] = 0.0;
-        } else {
-            r0 -= B.ap[i0]; r1 -= B.ap[i1];
+            B.p[i0] = 0.0; B.p[i1] = 0.0;
+            if (mode == MODE_START_JACOBI) { B.r[i0] = r0; B.r[i1] = r1; }
+            B.z[i0] = z0; B.z[i1] = z1;
+            rz = fma(r0, z0, rz); rz = fma(r1, z1, rz);
         }
-        const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
-        const double z0 = m0 * r0 + m1 * r1;
-        const double z1 = m1 * r0 + m2 * r1;
-        B.r[i0] = r0; B.r[i1] = r1;
-        B.z[i0] = z0; B.z[i1] = z1;
-        B.p[i0] = z0; B.p[i1] = z1;
-        rz = fma(r0, z0, rz); rz = fma(r1, z1, rz);
         rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
     }
     double val[2] = {rz, rr}, tot[2];
     if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
         return;
-    if (warp == 0) {
-        int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
-        int32_t* status = state_ptr(B.state, g, MOF_I_STATUS);
-        int act;
-        const int was = mode == 0 ? 0 : active[lane];
-        if (mode == 0) {
-            const bool valid = g * MOF_W + lane < B.n_frames;
-            scal_ptr(B.scal, g, MOF_S_BB)[lane] = tot[1];
-            scal_ptr(B.scal, g, MOF_S_RRTRUE)[lane] = tot[1];
-            state_ptr(B.state, g, MOF_I_ITERS)[lane] = 0;
-            if (!valid || tot[1] == 0.0) { act = 0; status[lane] = MOF_STATUS_ZERO_RHS; }
-            else if (!isfinite(tot[1]) || !isfinite(tot[0])) { act = 0; status[lane] = MOF_STATUS_BREAKDOWN; }
-            else { act = 1; status[lane] = MOF_STATUS_PENDING; }
-        } else {
-            const double bb = scal_ptr(B.scal, g, MOF_S_BB)[lane];
-            scal_ptr(B.scal, g, MOF_S_RRTRUE)[lane] = tot[1];
-            act = active[lane];
-            if (status[lane] == MOF_STATUS_CONVERGED && !(tot[1] <= tol2 * bb)) {
-                act = 1;                                   // recurrence drifted: restart from the true residual
+    if (warp != 0) return;
+    int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
+    int32_t* status = state_ptr(B.state, g, MOF_I_STATUS);
+    if (mode == MODE_NORM) {
+        scal_ptr(B.scal, g, MOF_S_BBT)[lane] = tot[1];
+        return;
+    }
+    int act;
+    const int was = (mode == MODE_VERIFY) ? active[lane] : 0;
+    if (mode == MODE_VERIFY) {
+        const double bbt = scal_ptr(B.scal, g, MOF_S_BBT)[lane];
+        scal_ptr(B.scal, g, MOF_S_RRTRUE)[lane] = tot[1];
+        act = was;
+        if (status[lane] == MOF_STATUS_CONVERGED && !(tot[1] <= tol2 * bbt)) {
+            if (last_round || !isfinite(tot[1])) {
+                status[lane] = MOF_STATUS_MAXITER;          // still short of tol after the allowed rounds
+            } else {
+                // true / recurrence residual ratio is stable along a run: rescale the threshold
+                double* thr = scal_ptr(B.scal, g, MOF_S_THR) + lane;
+                *thr = *thr * (tol2 * bbt / tot[1]) * 0.5;
+                scal_ptr(B.scal, g, MOF_S_BETA)[lane] = scal_ptr(B.scal, g, MOF_S_BETA_SAVED)[lane];
+                scal_ptr(B.scal, g, MOF_S_ZS)[lane] = 1.0;
                 status[lane] = MOF_STATUS_PENDING;
+                act = 1;
             }
         }
+    } else {
+        const bool valid = g * MOF_W + lane < B.n_frames;
+        if (mode == MODE_START_JACOBI) scal_ptr(B.scal, g, MOF_S_BBT)[lane] = tot[1];
+        scal_ptr(B.scal, g, MOF_S_BB)[lane] = tot[1];
+        scal_ptr(B.scal, g, MOF_S_RRTRUE)[lane] = scal_ptr(B.scal, g, MOF_S_BBT)[lane];
         scal_ptr(B.scal, g, MOF_S_RZ)[lane] = tot[0];
         scal_ptr(B.scal, g, MOF_S_RR)[lane] = tot[1];
-        active[lane] = act;
-        const int any = __any_sync(kFull, act);
-        const int gained = __popc(__ballot_sync(kFull, act && !was));
-        if (lane == 0) {
-            if (gained) atomicAdd(lanes_active_ptr(B.state, G), gained);
-            int32_t* done = group_done_ptr(B.state, G) + g;
-            if (mode == 0) {
-                *done = any ? 0 : 1;
-                if (any) atomicAdd(groups_active_ptr(B.state, G), 1);
-            } else if (any && *done) {
-                *done = 0;
-                atomicAdd(groups_active_ptr(B.state, G), 1);
-            }
+        scal_ptr(B.scal, g, MOF_S_THR)[lane] = tol2;
+        scal_ptr(B.scal, g, MOF_S_ALPHA)[lane] = 0.0;
+        scal_ptr(B.scal, g, MOF_S_BETA)[lane] = 0.0;      // first p-update: p = z
+        scal_ptr(B.scal, g, MOF_S_ZS)[lane] = 1.0;
+        scal_ptr(B.scal, g, MOF_S_BETA_SAVED)[lane] = 0.0;
+        state_ptr(B.state, g, MOF_I_ITERS)[lane] = 0;
+        if (!valid || tot[1] == 0.0) { act = 0; status[lane] = MOF_STATUS_ZERO_RHS; }
+        else if (!isfinite(tot[1]) || !isfinite(tot[0])) { act = 0; status[lane] = MOF_STATUS_BREAKDOWN; }
+        else { act = 1; status[lane] = MOF_STATUS_PENDING; }
+    }
+    active[lane] = act;
+    const int any = __any_sync(kFull, act);
+    const int gained = __popc(__ballot_sync(kFull, act && !was));
+    if (lane == 0) {
+        if (gained) atomicAdd(lanes_active_ptr(B.state, G), gained);
+        int32_t* done = group_done_ptr(B.state, G) + g;
+        if (mode != MODE_VERIFY) {
+            *done = any ? 0 : 1;
+            if (any) atomicAdd(groups_active_ptr(B.state, G), 1);
+        } else if (any && *done) {
+            *done = 0;
+            atomicAdd(groups_active_ptr(B.state, G), 1);
         }
     }
 }
@@ -409,7 +531,7 @@ extern "C" int mof_unpack_solution(const mof_mesh_dev* mesh, const mof_batch_dev
     return 0;
 }
 
-extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double tol,
+extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double tol, double omega,
                                    int32_t max_iter, int32_t check_every, int32_t max_restarts, int32_t* iters,
                                    double* relres, int32_t* status, mof_pcg_profile* prof, void* stream) {
     if (int rc = check_batch(mesh, batch)) return rc;
@@ -417,7 +539,17 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     MOF_REQUIRE(B.vals && B.rhs && B.minv && B.x && B.r && B.z && B.p && B.ap && B.partial && B.scal && B.state,
                 "batch buffers missing");
     MOF_REQUIRE(tol > 0 && max_iter >= 0, "bad tol / max_iter");
-    if (check_every <= 0) check_every = 25;
+    MOF_REQUIRE(omega >= 0.0 && omega < 2.0, "omega must be 0 (block Jacobi) or in (0,2) (SSOR)");
+    const bool ssor = omega > 0.0;
+    const int C = mesh->n_colors;
+    if (ssor) {
+        MOF_REQUIRE(C > 0 && C <= MOF_MAX_COLORS, "SSOR needs a mesh built with the block-multicolour ordering (reorder = 2)");
+        MOF_REQUIRE(B.t && mesh->diag, "SSOR needs batch->t and mesh->diag");
+        MOF_REQUIRE(mesh->color_tile_ptr[0] == 0 && mesh->color_tile_ptr[C] == mof_num_tiles(mesh->n_vertices),
+                    "colour tile ranges do not cover the mesh");
+    }
+    if (check_every <= 0) check_every = 32;
+    if (max_restarts < 0) max_restarts = 0;
     cudaStream_t st = mof_stream(stream);
     const int64_t N = mesh->n_vertices, nb = mesh->n_blocks;
     const int G = B.n_groups;
@@ -425,11 +557,41 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     const double tol2 = tol * tol;
     dim3 grid(ntiles, G);
     int32_t* d_active_groups = B.state + (size_t)G * MOF_I_COUNT * MOF_W + 2 * (size_t)G;
+    int64_t launches = 0;
+
+    auto sweep_back = [&](int mode, double* pvec, double* tout) {
+        for (int c = C - 1; c >= 0; --c) {
+            const int t0 = mesh->color_tile_ptr[c], t1 = mesh->color_tile_ptr[c + 1];
+            if (t1 <= t0) continue;
+            dim3 gs(mof_cdiv(t1 - t0, kWarps), G);
+            if (mode == 0) sweep_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1);
+            else           sweep_back_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1);
+            ++launches;
+        }
+    };
+    auto sweep_fwd = [&](int mode, const double* pin, double* wout) {
+        for (int c = 0; c < C; ++c) {
+            const int t0 = mesh->color_tile_ptr[c], t1 = mesh->color_tile_ptr[c + 1];
+            if (t1 <= t0) continue;
+            dim3 gs(mof_cdiv(t1 - t0, kWarps), G);
+            if (mode == 0) sweep_fwd_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, N, nb, t0, t1, ntiles, omega);
+            else           sweep_fwd_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, N, nb, t0, t1, ntiles, omega);
+            ++launches;
+        }
+    };
 
     // group_done, tickets, groups_active, lanes_active <- 0
     MOF_CUDA_TRY(cudaMemsetAsync(B.state + (size_t)G * MOF_I_COUNT * MOF_W, 0, (2 * (size_t)G + 2) * sizeof(int32_t), st));
-    init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, 0, tol2);
-    MOF_LAUNCH_CHECK("init_kernel");
+    if (!ssor) {
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_JACOBI, tol2, 0);
+        launches += 1;
+    } else {
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_NORM, tol2, 0);
+        sweep_fwd(1, B.rhs, B.r);                                   // r = (Dt+L)^-1 b
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_SSOR, tol2, 0);
+        launches += 2;
+    }
+    MOF_LAUNCH_CHECK("pcg start kernels");
 
     // optional sampled per-kernel timing (one iteration per check interval) for the roofline report
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -440,24 +602,34 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         ~EventGuard() { for (int q = 0; q < 4; ++q) if (e[q]) cudaEventDestroy(e[q]); }
     } guard{ev};
 
-    int32_t h_act[2] = {0, 0};          // groups, lanes still iterating
+    int32_t h_act[2] = {0, 0};          // groups, frames still iterating
     int32_t& h_active = h_act[0];
     MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MOF_CUDA_TRY(cudaStreamSynchronize(st));
-    if (prof) prof->launches_total += 1;
-    int it = 0, restarts = 0;
+    int it = 0, rounds = 0;
+    double* xphys = ssor ? B.t : B.x;   // where the solution of A x = b lives at verification time
     for (;;) {
         while (h_active > 0 && it < max_iter) {
             const int n = (max_iter - it) < check_every ? (max_iter - it) : check_every;
             for (int q = 0; q < n; ++q) {
                 const bool sample = prof && q == 0;
                 if (sample) cudaEventRecord(ev[0], st);
-                spmv_kernel<true><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.p, B.ap, N, nb, ntiles,
-                                                       B.partial, B.scal, B.state, G);
-                if (sample) cudaEventRecord(ev[1], st);
-                update_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, tol2);
-                if (sample) cudaEventRecord(ev[2], st);
-                pupdate_kernel<<<grid, 256, 0, st>>>(B, N);
+                if (!ssor) {
+                    pupdate_kernel<<<grid, 256, 0, st>>>(B, N);
+                    if (sample) cudaEventRecord(ev[1], st);
+                    spmv_kernel<true><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.p, B.ap, N, nb, ntiles,
+                                                           B.partial, B.scal, B.state, G);
+                    if (sample) cudaEventRecord(ev[2], st);
+                    update_kernel<false><<<grid, 256, 0, st>>>(B, N, ntiles);
+                    launches += 3;
+                } else {
+                    sweep_back(0, B.p, B.t);                        // p <- zs z + beta p ; t = (Dt+U)^-1 p
+                    if (sample) cudaEventRecord(ev[1], st);
+                    sweep_fwd(0, B.p, B.ap);                        // w ; alpha
+                    if (sample) cudaEventRecord(ev[2], st);
+                    update_kernel<true><<<grid, 256, 0, st>>>(B, N, ntiles);
+                    launches += 1;
+                }
                 if (sample) cudaEventRecord(ev[3], st);
             }
             MOF_LAUNCH_CHECK("pcg iteration kernels");
@@ -468,27 +640,32 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
             if (prof) {
                 float ms[3] = {0, 0, 0};
                 for (int q = 0; q < 3; ++q) MOF_CUDA_TRY(cudaEventElapsedTime(&ms[q], ev[q], ev[q + 1]));
-                prof->ms_spmv += ms[0];
-                prof->ms_update += ms[1];
-                prof->ms_pupdate += ms[2];
+                // block Jacobi: [pupdate, spmv, update]; SSOR: [backward sweeps, forward sweeps, update]
+                prof->ms_spmv += ssor ? ms[0] : ms[1];
+                prof->ms_pupdate += ssor ? ms[1] : ms[0];
+                prof->ms_update += ms[2];
                 prof->samples += 1;
                 prof->group_launches += groups_before;
                 prof->frame_launches += lanes_before;
                 prof->iterations_total += n;
-                prof->launches_total += 3 * (int64_t)n;
             }
         }
-        // confirm on the true residual b - A x; frames whose recurrence drifted restart
-        spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.x, B.ap, N, nb, ntiles, nullptr,
+        // confirm on the true residual b - A x; frames that miss tol resume with a tighter threshold
+        if (ssor) sweep_back(1, B.x, B.t);                           // x = (Dt+U)^-1 xhat
+        spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, xphys, B.ap, N, nb, ntiles, nullptr,
                                                 nullptr, nullptr, G);
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, 1, tol2);
+        const int last_round = (rounds >= max_restarts || it >= max_iter) ? 1 : 0;
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_VERIFY, tol2, last_round);
+        launches += 2;
         MOF_LAUNCH_CHECK("verification kernels");
-        if (prof) prof->launches_total += 2;
         MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         MOF_CUDA_TRY(cudaStreamSynchronize(st));
-        if (h_active <= 0 || it >= max_iter || restarts >= max_restarts) break;
-        ++restarts;
+        if (h_active <= 0 || last_round) break;
+        ++rounds;
     }
+    if (ssor)   // hand the physical solution back in batch->x (mof_unpack_solution reads it)
+        MOF_CUDA_TRY(cudaMemcpyAsync(B.x, B.t, (size_t)G * N * 2 * MOF_W * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (prof) prof->launches_total += launches;
 
     // per-frame report
     const size_t nf = (size_t)G * MOF_W;
@@ -505,7 +682,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                 const size_t k = (size_t)g * MOF_W + l;
                 int32_t s = h_state[((size_t)g * MOF_I_COUNT + MOF_I_STATUS) * MOF_W + l];
                 if (s == MOF_STATUS_PENDING) s = MOF_STATUS_MAXITER;
-                const double bb = h_scal[((size_t)g * MOF_S_COUNT + MOF_S_BB) * MOF_W + l];
+                const double bb = h_scal[((size_t)g * MOF_S_COUNT + MOF_S_BBT) * MOF_W + l];
                 const double rt = h_scal[((size_t)g * MOF_S_COUNT + MOF_S_RRTRUE) * MOF_W + l];
                 if (iters) iters[k] = h_state[((size_t)g * MOF_I_COUNT + MOF_I_ITERS) * MOF_W + l];
                 if (relres) relres[k] = bb > 0 ? sqrt(rt / bb) : 0.0;

@@ -30,15 +30,29 @@ class Pattern:
     Attributes (numpy int32): perm, iperm, rowptr, col, diag, cptr, centry, tri; ints
     n_vertices, n_faces, n_blocks, n_contrib, max_row_blocks, bandwidth."""
 
-    def __init__(self, n_vertices, triangles, reorder=True):
+    def __init__(self, n_vertices, triangles, reorder=True, coordinates=None):
+        """reorder: False/0 identity, True/1 Cuthill-McKee, 2 block multicolour (needs coordinates)."""
         lib = _lib.load()
         tri64 = np.ascontiguousarray(np.asarray(triangles), dtype=np.int64)
         if tri64.ndim != 2 or tri64.shape[1] != 3:
             raise ValueError(f"triangles must have shape (F, 3), got {tri64.shape}")
         N, F = int(n_vertices), int(tri64.shape[0])
         handle = ctypes.c_void_p()
-        _lib.check(lib.mof_pattern_create(N, F, tri64.ctypes.data, 1 if reorder else 0, ctypes.byref(handle)))
+        mode = int(reorder)
+        xyz = None
+        if coordinates is not None:
+            xyz = np.ascontiguousarray(np.asarray(coordinates, dtype=np.float64))
+            if xyz.shape != (N, 3):
+                raise ValueError(f"coordinates must have shape ({N}, 3), got {xyz.shape}")
+        _lib.check(lib.mof_pattern_create(N, F, tri64.ctypes.data, mode, xyz.ctypes.data if xyz is not None else None,
+                                          ctypes.byref(handle)))
+        self.reorder = mode
         try:
+            nc = ctypes.c_int32(0)
+            ctp = (ctypes.c_int32 * (_lib.MAX_COLORS + 1))()
+            _lib.check(lib.mof_pattern_colors(handle, ctypes.byref(nc), ctp))
+            self.n_colors = int(nc.value)
+            self.color_tile_ptr = np.array(list(ctp)[:self.n_colors + 1], dtype=np.int32) if self.n_colors else np.zeros(1, np.int32)
             nb = int(lib.mof_pattern_num_blocks(handle))
             nc = int(lib.mof_pattern_num_contrib(handle))
             self.n_vertices, self.n_faces, self.n_blocks, self.n_contrib = N, F, nb, nc
@@ -99,7 +113,7 @@ class MeshOperator:
     consumers of ``a2`` are ``worker`` / ``compute_velocity_field``, which accept this
     handle.  ``tocsr()`` gives the same matrix as the reference's for comparison."""
 
-    def __init__(self, coordinates, normals, triangles, areas, device=None, reorder=True):
+    def __init__(self, coordinates, normals, triangles, areas, device=None, reorder=2):
         torch = _lib.require_cuda()
         lib = _lib.load()
         t0 = time.time()
@@ -110,7 +124,7 @@ class MeshOperator:
         N = coords.shape[0]
         if nrm.shape[0] != N:
             raise ValueError("normals and coordinates differ in length")
-        self.pattern = P = Pattern(N, triangles, reorder=reorder)
+        self.pattern = P = Pattern(N, triangles, reorder=reorder, coordinates=coords)
         if ar.shape[0] != P.n_faces:
             raise ValueError("areas and triangles differ in length")
         self.n_vertices, self.n_faces, self.n_blocks = N, P.n_faces, P.n_blocks
@@ -154,7 +168,8 @@ class MeshOperator:
             self.d_perm.data_ptr(), self.d_rowptr.data_ptr(), self.d_col.data_ptr(), self.d_diag.data_ptr(),
             self.d_cptr.data_ptr(), self.d_centry.data_ptr(), self.d_tri.data_ptr(),
             self.d_e.data_ptr(), self.d_grad_w.data_ptr(), self.d_integral.data_ptr(), self.d_areas.data_ptr(),
-            self.d_a2v.data_ptr())
+            self.d_a2v.data_ptr(), P.n_colors,
+            (ctypes.c_int32 * (_lib.MAX_COLORS + 1))(*([int(x) for x in P.color_tile_ptr] + [0] * (_lib.MAX_COLORS - P.n_colors))))
 
     # -- reference-compatible views ----------------------------------------------------
     def tocsr(self):

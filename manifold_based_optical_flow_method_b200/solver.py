@@ -16,6 +16,8 @@ DEFAULT_TOL = 1e-12          # ||b - A x|| / ||b||, north-star parity setting
 DEFAULT_MAX_ITER = 20000
 DEFAULT_CHECK_EVERY = 32
 DEFAULT_MAX_RESTARTS = 3
+DEFAULT_PRECOND = "ssor"     # "ssor" (block-multicolour SSOR, Eisenstat form) or "jacobi" (2x2 block Jacobi)
+DEFAULT_OMEGA = 1.4          # SSOR relaxation factor
 DEFAULT_BATCH_GROUPS = 16    # 16 x 32 = 512 frames per launch (~30 GB at 164k vertices)
 
 
@@ -43,7 +45,7 @@ class UnconvergedError(RuntimeError):
 class FrameBatch:
     """Device buffers of one batch of ``n_groups`` x 32 frames (mof_batch_dev)."""
 
-    def __init__(self, op, n_groups):
+    def __init__(self, op, n_groups, with_t=True):
         torch = _lib.require_cuda()
         lib = _lib.load()
         self.op, self.n_groups = op, int(n_groups)
@@ -61,8 +63,9 @@ class FrameBatch:
         self.z = torch.empty((G, N, 2, W), **f64)
         self.p = torch.empty((G, N, 2, W), **f64)
         self.ap = torch.empty((G, N, 2, W), **f64)
+        self.t = torch.empty((G, N, 2, W), **f64) if with_t else None
         self.partial = torch.zeros((G, self.n_tiles, 2, W), **f64)
-        self.scal = torch.zeros((G, 8, W), **f64)
+        self.scal = torch.zeros((G, _lib.SCAL_SLOTS, W), **f64)
         self.state = torch.zeros((int(lib.mof_state_ints(G)),), dtype=torch.int32, device=dev)
         self.n_frames = 0
 
@@ -76,21 +79,30 @@ class FrameBatch:
         return _lib.BatchDev(
             G, self.n_frames, self.It.data_ptr(), self.dIt.data_ptr(), self.vals.data_ptr(),
             self.rhs.data_ptr(), self.minv.data_ptr(), self.x.data_ptr(), self.r.data_ptr(), self.z.data_ptr(),
-            self.p.data_ptr(), self.ap.data_ptr(), self.partial.data_ptr(), self.scal.data_ptr(), self.state.data_ptr())
+            self.p.data_ptr(), self.ap.data_ptr(), self.t.data_ptr() if self.t is not None else None,
+            self.partial.data_ptr(), self.scal.data_ptr(), self.state.data_ptr())
 
     @staticmethod
     def bytes_per_group(n_vertices, n_blocks):
-        return 8 * GROUP * (4 * n_blocks + n_vertices * (2 + 2 * 6 + 3))
+        return 8 * GROUP * (4 * n_blocks + n_vertices * (2 + 2 * 7 + 3))
 
 
 class VelocitySolver:
     """Solves batches of frames on one GPU.  Buffers are allocated once and reused."""
 
     def __init__(self, op, batch_groups=None, tol=DEFAULT_TOL, max_iter=DEFAULT_MAX_ITER,
-                 check_every=DEFAULT_CHECK_EVERY, max_restarts=DEFAULT_MAX_RESTARTS):
+                 check_every=DEFAULT_CHECK_EVERY, max_restarts=DEFAULT_MAX_RESTARTS, precond=None, omega=DEFAULT_OMEGA):
         self.torch = _lib.require_cuda()
         self.lib = _lib.load()
         self.op = op
+        if precond is None:
+            precond = DEFAULT_PRECOND if op.pattern.n_colors > 0 else "jacobi"
+        if precond not in ("ssor", "jacobi"):
+            raise ValueError(f"precond must be 'ssor' or 'jacobi', got {precond!r}")
+        if precond == "ssor" and op.pattern.n_colors == 0:
+            raise ValueError("the SSOR preconditioner needs a mesh built with the block-multicolour ordering (reorder=2)")
+        self.precond = precond
+        self.omega = float(omega) if precond == "ssor" else 0.0
         self.tol, self.max_iter, self.check_every, self.max_restarts = tol, max_iter, check_every, max_restarts
         if batch_groups is None:
             free, _total = self.torch.cuda.mem_get_info(op.device)
@@ -105,7 +117,7 @@ class VelocitySolver:
     def batch(self, n_groups):
         if self._batch is None or self._batch.n_groups < n_groups:
             self._batch = None
-            self._batch = FrameBatch(self.op, n_groups)
+            self._batch = FrameBatch(self.op, n_groups, with_t=self.precond == "ssor")
         return self._batch
 
     def drain(self, width, rows=None):
@@ -124,7 +136,7 @@ class VelocitySolver:
         assert I_now.stride(0) == I_next.stride(0)
         _lib.check(lib.mof_pack_frames(ctypes.byref(ms), ctypes.byref(bs), I_now.data_ptr(), I_next.data_ptr(),
                                        I_now.stride(0), dt.data_ptr(), st))
-        _lib.check(lib.mof_assemble_batch(ctypes.byref(ms), ctypes.byref(bs), float(lambda_), st))
+        _lib.check(lib.mof_assemble_batch(ctypes.byref(ms), ctypes.byref(bs), float(lambda_), self.omega, st))
         return ms, bs
 
     def solve_batch(self, I_now, I_next, dt, lambda_, V_out):
@@ -138,7 +150,7 @@ class VelocitySolver:
         iters = np.zeros(G * GROUP, np.int32)
         relres = np.zeros(G * GROUP, np.float64)
         status = np.zeros(G * GROUP, np.int32)
-        _lib.check(lib.mof_pcg_solve_batch(ctypes.byref(ms), ctypes.byref(bs), float(self.tol), int(self.max_iter),
+        _lib.check(lib.mof_pcg_solve_batch(ctypes.byref(ms), ctypes.byref(bs), float(self.tol), self.omega, int(self.max_iter),
                                            int(self.check_every), int(self.max_restarts), iters.ctypes.data,
                                            relres.ctypes.data, status.ctypes.data,
                                            ctypes.byref(self.profile) if self.profile is not None else None, st),

@@ -24,12 +24,16 @@ V_TOL = 1e-8
 RES_TOL = 1e-12
 
 
-@pytest.fixture(scope="module")
-def mods():
+@pytest.fixture(scope="module", params=["ssor", "jacobi"])
+def mods(request):
+    """Every test runs with both preconditioners (and therefore both vertex numberings)."""
     import torch
     assert torch.cuda.is_available(), "gpu tests need a CUDA device"
     from manifold_based_optical_flow_method_b200 import compute_optical_flow, find_singularity_point
-    return compute_optical_flow, find_singularity_point
+    old = compute_optical_flow.settings["precond"]
+    compute_optical_flow.settings["precond"] = request.param
+    yield compute_optical_flow, find_singularity_point
+    compute_optical_flow.settings["precond"] = old
 
 
 def _csr(g, prefix, n):
@@ -53,7 +57,7 @@ def _assemble_on_gpu(cof, op, I, t_k, lambda_):
     import torch
     from manifold_based_optical_flow_method_b200.solver import VelocitySolver, frame_dt
     n = len(I) - 1
-    s = VelocitySolver(op, batch_groups=-(-n // W))
+    s = VelocitySolver(op, batch_groups=-(-n // W), precond="jacobi")
     batch = s.batch(-(-n // W))
     I_dev = torch.from_numpy(np.ascontiguousarray(I, dtype=np.float64)).to(op.device)
     dt = torch.from_numpy(frame_dt(list(t_k), 0, n)).to(op.device)
@@ -317,6 +321,7 @@ def test_max_iter_reports_unconverged(mods):
             cof.compute_velocity_field(1, 3, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
         assert np.all(cof.last_solve_info.status == _lib.STATUS_MAXITER)
         assert np.all(cof.last_solve_info.iterations == 5)
+        assert np.all(cof.last_solve_info.relres > 1e-12)
     finally:
         cof.settings["max_iter"] = 20000
 
@@ -354,6 +359,8 @@ def test_c_abi_argument_errors(mods):
 def test_full_size_properties(mods):
     import torch
     cof, fsp = mods
+    if cof.settings["precond"] == "jacobi":
+        pytest.skip("full-size properties run once, with the default preconditioner")
     coords, tris, normals, areas = synthetic.pial_like(7)
     N = len(coords)
     assert N == 163842

@@ -33,8 +33,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8
-    assert ctypes.sizeof(_lib.BatchDev) == 8 + 13 * 8
+    assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8 + 4 + 17 * 4
+    assert ctypes.sizeof(_lib.BatchDev) == 8 + 14 * 8
     assert ctypes.sizeof(_lib.PcgProfile) == 8 * 8
 
 
@@ -111,7 +111,7 @@ class HostMesh:
         self.hc = hostcheck.load()
         self.coords, self.tris = g["coordinates"], g["triangles"]
         N = len(self.coords)
-        self.P = P = Pattern(N, self.tris, reorder=reorder)
+        self.P = P = Pattern(N, self.tris, reorder=reorder, coordinates=self.coords)
         self.areas = np.ascontiguousarray(g["areas"], dtype=np.float64)
         self.e = np.zeros((N, 2, 3))
         self.grad_w = np.zeros((P.n_faces, 3, 3))
@@ -129,9 +129,9 @@ class HostMesh:
         p = lambda a: a.ctypes.data
         return _lib.MeshDev(P.n_vertices, P.n_faces, P.n_blocks, P.n_contrib, p(P.perm), p(P.rowptr), p(P.col), p(P.diag),
                             p(P.cptr), p(P.centry), p(P.tri), p(self.e), p(self.grad_w), p(self.integral), p(self.areas),
-                            p(self.a2v))
+                            p(self.a2v), 0, (ctypes.c_int32 * (_lib.MAX_COLORS + 1))())
 
-    def assemble(self, I, t_k, lambda_):
+    def assemble(self, I, t_k, lambda_, omega=0.0):
         P, hc = self.P, self.hc
         n = len(I) - 1
         G = -(-n // W)
@@ -143,8 +143,8 @@ class HostMesh:
         ms = self.struct()
         hc.hc_pack(ctypes.byref(ms), G, n, I.ctypes.data, I[1:].ctypes.data, ctypes.c_int64(I.shape[1]), dt.ctypes.data,
                    It.ctypes.data, dIt.ctypes.data)
-        hc.hc_assemble(ctypes.byref(ms), G, It.ctypes.data, dIt.ctypes.data, ctypes.c_double(lambda_), vals.ctypes.data,
-                       rhs.ctypes.data, minv.ctypes.data)
+        hc.hc_assemble(ctypes.byref(ms), G, It.ctypes.data, dIt.ctypes.data, ctypes.c_double(lambda_), ctypes.c_double(omega),
+                       vals.ctypes.data, rhs.ctypes.data, minv.ctypes.data)
         return vals, rhs, minv
 
 
@@ -161,7 +161,7 @@ def _frame_vector(P, vec, k):
     return out
 
 
-@pytest.mark.parametrize("reorder", [False, True])
+@pytest.mark.parametrize("reorder", [0, 1, 2])
 def test_bodies_geometry_and_assembly_match_reference(golden, reorder):
     g = golden
     hm = HostMesh(g, reorder)
@@ -215,6 +215,89 @@ def test_bodies_spmv_matches_scipy():
     for k in range(len(g["V_k"])):
         a = _frame_matrix(P, vals, k)
         assert rel_l2(_frame_vector(P, y, k), a @ _frame_vector(P, x, k)) <= 1e-14
+
+
+@pytest.mark.parametrize("case", ["ico2_wave", "patch8_wave", "ico3_phase", "ico4_wave"])
+def test_bodies_ssor_eisenstat_pcg_matches_reference(case):
+    """The SSOR path end to end on the CPU harness: block-multicolour ordering, Dt = D/omega from
+    the assembly body, colour-by-colour backward / forward sweeps (the bodies the CUDA sweep
+    kernels call) inside the same Eisenstat-form PCG the library's host loop runs."""
+    g = load_golden(case)
+    omega, tol = 1.4, 1e-12
+    hm = HostMesh(g, reorder=2)
+    P, hc = hm.P, hm.hc
+    N = P.n_vertices
+    assert P.n_colors >= 1 and P.color_tile_ptr[0] == 0 and P.color_tile_ptr[-1] == -(-N // _lib.TILE_ROWS)
+    # patches of one colour are mutually independent (no block couples two of them)
+    tile_of = np.arange(N) // _lib.TILE_ROWS
+    color_of_tile = np.repeat(np.arange(P.n_colors), np.diff(P.color_tile_ptr))
+    rows, cols = P.block_rows(), P.col.astype(np.int64)
+    cross = tile_of[rows] != tile_of[cols]
+    assert np.all(color_of_tile[tile_of[rows[cross]]] != color_of_tile[tile_of[cols[cross]]])
+    vals, rhs, dt = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]), omega)
+    n = len(g["V_k"])
+    G = vals.shape[0]
+    ms = hm.struct()
+    ptr = [int(x) for x in P.color_tile_ptr]
+    C = P.n_colors
+    ref = ctypes.byref(ms)
+
+    def back(mode, z, p, t, beta=None, zs=None):
+        for c in range(C - 1, -1, -1):
+            hc.hc_sweep_back(ref, G, vals.ctypes.data, dt.ctypes.data, z.ctypes.data, p.ctypes.data, t.ctypes.data, ptr[c], ptr[c + 1],
+                             beta.ctypes.data if beta is not None else None, zs.ctypes.data if zs is not None else None, mode)
+
+    def fwd(mode, pin, t, w, dot=None):
+        for c in range(C):
+            hc.hc_sweep_fwd(ref, G, vals.ctypes.data, dt.ctypes.data, pin.ctypes.data, t.ctypes.data, w.ctypes.data, ptr[c], ptr[c + 1],
+                            omega, mode, dot.ctypes.data if dot is not None else None)
+
+    def apply_dt(r):
+        z = np.empty_like(r)
+        z[:, :, 0] = dt[:, :, 0] * r[:, :, 0] + dt[:, :, 1] * r[:, :, 1]
+        z[:, :, 1] = dt[:, :, 1] * r[:, :, 0] + dt[:, :, 2] * r[:, :, 1]
+        return z
+
+    lanes = lambda a, b: np.einsum("gvcl,gvcl->gl", a, b)
+    t = np.zeros_like(rhs)
+    w = np.zeros_like(rhs)
+    r = np.zeros_like(rhs)
+    fwd(1, rhs, t, r)                                   # r = (Dt+L)^-1 b
+    x = np.zeros_like(rhs)
+    p = np.zeros_like(rhs)
+    z = apply_dt(r)
+    rz = lanes(r, z)
+    bb = lanes(r, r)
+    beta = np.zeros((G, W))
+    zs = np.ones((G, W))
+    active = bb > 0
+    iters = 0
+    while active.any() and iters < 2000:
+        back(0, z, p, t, beta, zs)                      # p <- zs z + beta p ; t = (Dt+U)^-1 p
+        dot = np.zeros((G, W))
+        fwd(0, p, t, w, dot)
+        alpha = np.where(active, rz / np.where(dot != 0, dot, 1), 0.0)
+        x += alpha[:, None, None, :] * p
+        r -= alpha[:, None, None, :] * (t + w)
+        z = apply_dt(r)
+        rz_new, rr = lanes(r, z), lanes(r, r)
+        conv = active & (rr <= (0.3 * tol) ** 2 * bb)
+        beta = np.where(active & ~conv, rz_new / np.where(rz != 0, rz, 1), 1.0)
+        zs = np.where(active & ~conv, 1.0, 0.0)
+        rz = np.where(active, rz_new, rz)
+        active = active & ~conv
+        iters += 1
+    assert not active.any()
+    xphys = np.zeros_like(rhs)
+    back(1, z, x, xphys)                                # x = (Dt+U)^-1 xhat
+    for k in range(n):
+        a = _frame_matrix(P, vals, k)
+        b = _frame_vector(P, rhs, k)
+        V = _frame_vector(P, xphys, k)
+        assert np.linalg.norm(a @ V - b) / np.linalg.norm(b) <= 1e-12
+        assert rel_l2(V, g["V_k"][k]) <= 1e-8
+    # padding lanes stay exactly zero
+    assert np.all(xphys[-1, :, :, n % W:] == 0.0) if n % W else True
 
 
 def test_bodies_tangent_and_detection_match_reference(golden):
