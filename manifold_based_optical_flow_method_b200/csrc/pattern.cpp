@@ -108,8 +108,10 @@ void block_multicolor(int64_t N, const double* xyz, const std::vector<int64_t>& 
     std::vector<int32_t> pid(N);
     for (int32_t k = 0; k < np; ++k)
         for (size_t q = leaves[k].first; q < leaves[k].second; ++q) pid[ids[q]] = k;
-    // greedy colouring of the patch adjacency graph in RCB (space-filling) order
-    std::vector<int32_t> color(np, -1);
+    // balanced greedy colouring of the patch adjacency graph in RCB (space-filling) order: among
+    // the colours no neighbour uses, take the one with the fewest patches so far (equal-sized
+    // colour classes keep every sweep launch large); open a new colour only when forced to
+    std::vector<int32_t> color(np, -1), class_size;
     std::vector<uint8_t> used;
     int32_t ncol = 0;
     for (int32_t k = 0; k < np; ++k) {
@@ -121,10 +123,12 @@ void block_multicolor(int64_t N, const double* xyz, const std::vector<int64_t>& 
                 if (c >= 0 && pid[adj[e]] != k) used[c] = 1;
             }
         }
-        int32_t c = 0;
-        while (c < ncol && used[c]) ++c;
-        color[k] = c;
-        if (c == ncol) ++ncol;
+        int32_t best = -1;
+        for (int32_t c = 0; c < ncol; ++c)
+            if (!used[c] && (best < 0 || class_size[c] < class_size[best])) best = c;
+        if (best < 0) { best = ncol++; class_size.push_back(0); }
+        color[k] = best;
+        class_size[best]++;
     }
     // the (single) short patch must be the very last tile: make its colour class the last one
     int32_t short_patch = -1;

@@ -34,6 +34,7 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kRowsPerWarp = MOF_TILE_ROWS / kWarps;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kPrefetchRows = 4;      // SSOR sweeps: matrix values are prefetched to L2 this many rows ahead
 
 __device__ __forceinline__ double* scal_ptr(double* scal, int64_t g, int which) {
     return scal + ((size_t)g * MOF_S_COUNT + which) * MOF_W;
@@ -300,7 +301,54 @@ __global__ void __launch_bounds__(256) pupdate_kernel(mof_batch_dev B, int64_t N
 // a patch are solved sequentially by the warp (mof_sweep_*_body); patches of one colour do not
 // touch each other, earlier colours are complete because they ran in earlier launches.
 // ---------------------------------------------------------------------------------
+// Pull the 4 x 256-byte lines of matrix block b of this group towards L2 (one address per lane
+// covers the line pair of a component).
+__device__ __forceinline__ void prefetch_block_l2(const double* __restrict__ vals_l, int32_t b) {
+    const double* p = vals_l + (size_t)b * 4 * MOF_W;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c * MOF_W));
+}
+
+// Off-diagonal part of one row of a sweep: acc -= sum_k A_k v[col_k] over blocks [bs, be).
+// All loads of up to four blocks are issued before the first use so that one memory round trip
+// serves the row (the matrix values are independent of the sweep's recurrence; only the gathered
+// v values may have been written by this thread a few rows earlier, hence plain loads for them).
+__device__ __forceinline__ void sweep_row_offdiag(const int32_t* __restrict__ col, const double* __restrict__ vals_l,
+                                                  const double* v_l, int32_t bs, int32_t be, double& a0, double& a1) {
+    for (int32_t base = bs; base < be; base += 4) {
+        const int cnt = be - base;                      // > 0; only the first four are handled per pass
+        int64_t j[4];
+        double a[4][4], v[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt) {
+                j[k] = col[base + k];
+                const double* ap = vals_l + (size_t)(base + k) * 4 * MOF_W;
+                a[k][0] = __ldcs(ap);
+                a[k][1] = __ldcs(ap + MOF_W);
+                a[k][2] = __ldcs(ap + 2 * MOF_W);
+                a[k][3] = __ldcs(ap + 3 * MOF_W);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt) {
+                v[k][0] = v_l[(size_t)(2 * j[k]) * MOF_W];
+                v[k][1] = v_l[(size_t)(2 * j[k] + 1) * MOF_W];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < cnt) {
+                a0 -= a[k][0] * v[k][0] + a[k][1] * v[k][1];
+                a1 -= a[k][2] * v[k][0] + a[k][3] * v[k][1];
+            }
+        }
+    }
+}
+
 // MODE 0: iteration (p <- zs z + beta p fused in, t = (Dt+U)^-1 p).  MODE 1: t = (Dt+U)^-1 pvec.
+// Same arithmetic as mof_sweep_back_body (mof_bodies.h), with the loads of a row batched.
 template <int MODE>
 __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                          const int32_t* __restrict__ diag, mof_batch_dev B, double* pvec,
@@ -318,13 +366,43 @@ __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restri
         beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
         zs = scal_ptr(B.scal, g, MOF_S_ZS)[lane];
     }
-    mof_sweep_back_body(rowptr, col, diag, B.vals + (size_t)g * nb * 4 * MOF_W + lane,
-                        B.minv + (size_t)g * N * 3 * MOF_W + lane, B.z + (size_t)g * N * 2 * MOF_W + lane,
-                        pvec + (size_t)g * N * 2 * MOF_W + lane, tout + (size_t)g * N * 2 * MOF_W + lane, r0, r1, beta, zs, MODE);
+    const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
+    const double* __restrict__ dt_l = B.minv + (size_t)g * N * 3 * MOF_W + lane;
+    const double* __restrict__ z_l = B.z + (size_t)g * N * 2 * MOF_W + lane;
+    double* p_l = pvec + (size_t)g * N * 2 * MOF_W + lane;
+    double* t_l = tout + (size_t)g * N * 2 * MOF_W + lane;
+    // row pointers of the patch: lane q holds rowptr[r0+q+1] and diag[r0+q] (two coalesced loads)
+    int32_t rp_lo = 0, rp_hi = 0, dg_lo = 0, dg_hi = 0;
+    if (r0 + lane < r1) { rp_lo = rowptr[r0 + lane + 1]; dg_lo = diag[r0 + lane]; }
+    if (r0 + 32 + lane < r1) { rp_hi = rowptr[r0 + 32 + lane + 1]; dg_hi = diag[r0 + 32 + lane]; }
+    for (int64_t i = r1 - 1; i >= r0; --i) {
+        const int q = (int)(i - r0);
+        const int32_t be = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
+        const int32_t bs = (q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32)) + 1;
+        const double d0 = dt_l[(size_t)i * 3 * MOF_W], d1 = dt_l[(size_t)i * 3 * MOF_W + MOF_W],
+                     d2 = dt_l[(size_t)i * 3 * MOF_W + 2 * MOF_W];
+        double a0 = p_l[(size_t)(2 * i) * MOF_W], a1 = p_l[(size_t)(2 * i + 1) * MOF_W];
+        if (MODE == 0) {
+            a0 = zs * z_l[(size_t)(2 * i) * MOF_W] + beta * a0;
+            a1 = zs * z_l[(size_t)(2 * i + 1) * MOF_W] + beta * a1;
+            p_l[(size_t)(2 * i) * MOF_W] = a0;
+            p_l[(size_t)(2 * i + 1) * MOF_W] = a1;
+        }
+        const double rdet = 1.0 / (d0 * d2 - d1 * d1);            // off the critical path: independent of the gather
+        if (q >= kPrefetchRows) {                                   // matrix values of a row a few steps ahead -> L2
+            const int qq = q - kPrefetchRows;
+            const int32_t pe = qq < 32 ? __shfl_sync(kFull, rp_lo, qq) : __shfl_sync(kFull, rp_hi, qq - 32);
+            const int32_t ps = (qq < 32 ? __shfl_sync(kFull, dg_lo, qq) : __shfl_sync(kFull, dg_hi, qq - 32)) + 1;
+            for (int32_t b = ps; b < pe; ++b) prefetch_block_l2(vals_l, b);
+        }
+        sweep_row_offdiag(col, vals_l, t_l, bs, be, a0, a1);
+        t_l[(size_t)(2 * i) * MOF_W] = (d2 * a0 - d1 * a1) * rdet;
+        t_l[(size_t)(2 * i + 1) * MOF_W] = (d0 * a1 - d1 * a0) * rdet;
+    }
 }
 
 // MODE 0: iteration (w = (Dt+L)^-1 (p - (2-omega) Dt t), p'(t+w) -> alpha in the last CTA of the
-// last colour).  MODE 1: wout = (Dt+L)^-1 pin.
+// last colour).  MODE 1: wout = (Dt+L)^-1 pin.  Same arithmetic as mof_sweep_fwd_body.
 template <int MODE>
 __global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                         const int32_t* __restrict__ diag, mof_batch_dev B, const double* pin,
@@ -340,10 +418,42 @@ __global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restric
     if (valid) {
         const int64_t r0 = (int64_t)tile * MOF_TILE_ROWS;
         const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
-        dot = mof_sweep_fwd_body(rowptr, col, diag, B.vals + (size_t)g * nb * 4 * MOF_W + lane,
-                                 B.minv + (size_t)g * N * 3 * MOF_W + lane, pin + (size_t)g * N * 2 * MOF_W + lane,
-                                 B.t + (size_t)g * N * 2 * MOF_W + lane, wout + (size_t)g * N * 2 * MOF_W + lane, r0, r1,
-                                 omega, MODE);
+        const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
+        const double* __restrict__ dt_l = B.minv + (size_t)g * N * 3 * MOF_W + lane;
+        const double* __restrict__ p_l = pin + (size_t)g * N * 2 * MOF_W + lane;
+        const double* __restrict__ t_l = B.t + (size_t)g * N * 2 * MOF_W + lane;
+        double* w_l = wout + (size_t)g * N * 2 * MOF_W + lane;
+        int32_t rp_lo = 0, rp_hi = 0, dg_lo = 0, dg_hi = 0;
+        if (r0 + lane < r1) { rp_lo = rowptr[r0 + lane]; dg_lo = diag[r0 + lane]; }
+        if (r0 + 32 + lane < r1) { rp_hi = rowptr[r0 + 32 + lane]; dg_hi = diag[r0 + 32 + lane]; }
+        const double kscale = 2.0 - omega;
+        for (int64_t i = r0; i < r1; ++i) {
+            const int q = (int)(i - r0);
+            const int32_t bs = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
+            const int32_t be = q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32);
+            const double d0 = dt_l[(size_t)i * 3 * MOF_W], d1 = dt_l[(size_t)i * 3 * MOF_W + MOF_W],
+                         d2 = dt_l[(size_t)i * 3 * MOF_W + 2 * MOF_W];
+            const double p0 = p_l[(size_t)(2 * i) * MOF_W], p1 = p_l[(size_t)(2 * i + 1) * MOF_W];
+            double a0 = p0, a1 = p1, t0 = 0.0, t1 = 0.0;
+            if (MODE == 0) {
+                t0 = t_l[(size_t)(2 * i) * MOF_W];
+                t1 = t_l[(size_t)(2 * i + 1) * MOF_W];
+                a0 -= kscale * (d0 * t0 + d1 * t1);
+                a1 -= kscale * (d1 * t0 + d2 * t1);
+            }
+            const double rdet = 1.0 / (d0 * d2 - d1 * d1);
+            if (q + kPrefetchRows < (int)(r1 - r0)) {
+                const int qq = q + kPrefetchRows;
+                const int32_t ps = qq < 32 ? __shfl_sync(kFull, rp_lo, qq) : __shfl_sync(kFull, rp_hi, qq - 32);
+                const int32_t pe = qq < 32 ? __shfl_sync(kFull, dg_lo, qq) : __shfl_sync(kFull, dg_hi, qq - 32);
+                for (int32_t b = ps; b < pe; ++b) prefetch_block_l2(vals_l, b);
+            }
+            sweep_row_offdiag(col, vals_l, w_l, bs, be, a0, a1);
+            const double o0 = (d2 * a0 - d1 * a1) * rdet, o1 = (d0 * a1 - d1 * a0) * rdet;
+            w_l[(size_t)(2 * i) * MOF_W] = o0;
+            w_l[(size_t)(2 * i + 1) * MOF_W] = o1;
+            if (MODE == 0) dot += p0 * (t0 + o0) + p1 * (t1 + o1);
+        }
     }
     if (MODE != 0) return;
     // one partial per patch; the CTA that completes the count over all colours reduces them

@@ -18,7 +18,8 @@ DEFAULT_CHECK_EVERY = 32
 DEFAULT_MAX_RESTARTS = 3
 DEFAULT_PRECOND = "ssor"     # "ssor" (block-multicolour SSOR, Eisenstat form) or "jacobi" (2x2 block Jacobi)
 DEFAULT_OMEGA = 1.4          # SSOR relaxation factor
-DEFAULT_BATCH_GROUPS = 16    # 16 x 32 = 512 frames per launch (~30 GB at 164k vertices)
+DEFAULT_BATCH_GROUPS = 32    # 32 x 32 = 1024 frames per launch (~66 GB at 164k vertices)
+DRAIN_STAGE_ROWS = 256       # rows per pinned staging buffer of the device->host pipeline
 
 
 @dataclasses.dataclass
@@ -121,8 +122,8 @@ class VelocitySolver:
         return self._batch
 
     def drain(self, width, rows=None):
-        """Cached HostDrain with staging buffers of (rows or one batch) x width doubles."""
-        rows = int(rows or self.batch_groups * GROUP)
+        """Cached HostDrain with pinned staging buffers of ``rows`` x width doubles."""
+        rows = int(rows or DRAIN_STAGE_ROWS)
         if self._drain is None or not self._drain.fits(rows, width):
             self._drain = HostDrain(self.torch, self.op.device, rows, width)
         return self._drain
@@ -191,7 +192,7 @@ class HostDrain:
     and a worker thread moves them into the caller's (pageable) numpy array.  The solver's
     host thread sits inside libmof_b200 (GIL released) meanwhile."""
 
-    def __init__(self, torch, device, max_rows, width, n_stages=2, copy_threads=4):
+    def __init__(self, torch, device, max_rows, width, n_stages=3, copy_threads=4):
         import queue
         import threading
         from concurrent.futures import ThreadPoolExecutor
@@ -225,7 +226,13 @@ class HostDrain:
 
     def submit(self, src_dev, dst_host):
         """Queue rows ``src_dev`` (device (r, width), produced on the current stream or on the
-        side stream) for delivery into ``dst_host`` (numpy (r, width))."""
+        side stream) for delivery into ``dst_host`` (numpy (r, width)); long blocks are cut into
+        staging-buffer-sized pieces."""
+        rows = int(src_dev.shape[0])
+        if rows > self.max_rows:
+            for a in range(0, rows, self.max_rows):
+                self.submit(src_dev[a:a + self.max_rows], dst_host[a:a + self.max_rows])
+            return
         torch = self.torch
         i = self.count % len(self.stages)
         self.count += 1
