@@ -331,7 +331,11 @@ def run_b200(args):
         others = {"sweep_back (all colours)": {"achieved": gbs(fl * per_frame["sweep_back"] + idx_bytes, prof.ms_spmv), "avg_ms": prof.ms_spmv / smp},
                   "sweep_fwd (all colours)": {"achieved": gbs(fl * per_frame["sweep_fwd"] + idx_bytes, prof.ms_pupdate), "avg_ms": prof.ms_pupdate / smp},
                   "update_kernel": {"achieved": gbs(fl * per_frame["update"], prof.ms_update), "avg_ms": prof.ms_update / smp}}
-        traffic_val = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "sweeps_traffic.json")) as fh:
+                traffic_val = json.load(fh)["dram_bytes_per_frame_iteration"] * fl / smp
+        except Exception:
+            traffic_val = None
     achieved = gbs(dom_bytes, dom_ms)
     roofline = {
         "kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
