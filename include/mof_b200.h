@@ -239,6 +239,20 @@ int mof_singularity_compact(int64_t n_vertices, int64_t n_faces, int64_t n_frame
                             const int64_t* foff, int32_t* vertex_idx, int32_t* face_idx,
                             double* lam_mu, double* P, int8_t* index, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * K6 ("next" row of SURVEY 8f): wave speed of S5_compute_wave_v.py.
+ * I: device (n_frames, N) row stride ld, REFERENCE vertex order (phases in (-pi,pi] or
+ * potentials); dt = 1/SF.  phase_mode 1: wave_velocity_phase (S5:79-123, wrapped time
+ * differences S5:60-77); 0: wave_velocity_amplitude (S5:14-58, np.gradient edge_order=2,
+ * needs n_frames >= 3).  Outputs (either may be NULL), reference vertex order:
+ * grad_point (n_frames,N,3) = compute_grad_M_I (S5:136-171); wave (n_frames,N) = time
+ * derivative / |projected gradient| (S5:121), signed and unscaled like the functions'
+ * return value (the script divides by 1000 and takes abs afterwards, S5:312-313).
+ * The derivative couples neighbouring frames: pass all frames of a trial in one call.
+ * ------------------------------------------------------------------------- */
+int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_frames, const double* I, int64_t ld, double dt,
+                   int phase_mode, double* grad_point, double* wave, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,101 @@
+"""Drop-in for the numerical functions of the reference's ``S5_compute_wave_v.py`` ("next" row 1
+of SURVEY.md section 8f): wave speed = |d/dt| / |surface gradient| of a phase (or amplitude) map.
+
+    wave_velocity_phase(surface, phases, dt, time_steps, e)          # reference :79-123
+    wave_velocity_amplitude(surface, potentials, dt, time_steps, e)  # reference :14-58
+    compute_grad_M_I(coordinates, triangles, potentials, surface, areas)   # reference :136-171
+    compute_temporal_gradient_phase(data, dt)                         # reference :60-77
+    angle_subtract(f1, f2, angleFlag=True)                            # reference :224-233
+
+``surface`` is anything with the pyvista members the reference uses (``points``, ``faces``,
+``compute_cell_sizes(...)['Area']``) -- a real ``pyvista.PolyData`` or ``synthetic.SurfaceMesh``.
+The per-vertex face lists come from the mesh pattern (ascending face index) instead of
+``surface.point_cell_ids``.  One fused CUDA kernel (csrc/wave.cu) does the per-face gradient, the
+area-weighted vertex average, the tangent projection, the basis coefficients, their norm, the
+(wrapped) time derivative and the division; no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .mesh import MeshOperator
+
+_ops = {}
+
+
+def _surface_arrays(surface):
+    coordinates = np.asarray(surface.points, dtype=np.float64)
+    triangles = np.asarray(surface.faces).reshape(-1, 4)[:, 1:]
+    areas = np.asarray(surface.compute_cell_sizes(length=False, volume=False)['Area'], dtype=np.float64)
+    return coordinates, triangles, areas
+
+
+def _operator(coordinates, triangles, areas, e=None):
+    """Mesh handle cached per (coordinates, triangles) buffers; normals only define e, which S5
+    receives from the caller, so the handle is built with dummy normals and e is uploaded."""
+    key = (coordinates.shape, triangles.shape, float(coordinates.sum()), int(np.asarray(triangles).sum()))
+    op = _ops.get(key)
+    if op is None:
+        _ops.clear()
+        normals = np.zeros_like(coordinates)
+        normals[:, 2] = 1.0
+        op = _ops[key] = MeshOperator(coordinates, normals, triangles, areas, reorder=1)
+    op.use_geometry(None, e, None, areas)
+    return op
+
+
+def _run(op, data, dt, phase_mode, want_grad, want_wave):
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    data = np.ascontiguousarray(np.asarray(data, dtype=np.float64))
+    T, N = data.shape
+    if N != op.n_vertices:
+        raise ValueError(f"data must have shape (T, {op.n_vertices}), got {data.shape}")
+    d = torch.from_numpy(data).to(op.device)
+    grad = torch.empty((T, N, 3), dtype=torch.float64, device=op.device) if want_grad else None
+    wave = torch.empty((T, N), dtype=torch.float64, device=op.device) if want_wave else None
+    ms = op.struct()
+    st = torch.cuda.current_stream(op.device).cuda_stream
+    _lib.check(lib.mof_wave_speed(ctypes.byref(ms), T, d.data_ptr(), N, float(dt), 1 if phase_mode else 0,
+                                  grad.data_ptr() if want_grad else None, wave.data_ptr() if want_wave else None, st))
+    return (grad.cpu().numpy() if want_grad else None), (wave.cpu().numpy() if want_wave else None)
+
+
+def compute_grad_M_I(coordinates, triangles, potentials, surface, areas):
+    """Reference :136-171 -> grad_point (time_steps, point_num, 3)."""
+    op = _operator(np.asarray(coordinates, dtype=np.float64), np.asarray(triangles), np.asarray(areas, dtype=np.float64))
+    return _run(op, potentials, 1.0, True, True, False)[0]
+
+
+def wave_velocity_phase(surface, phases, dt, time_steps, e):
+    """Reference :79-123 -> wave_velocity (time_steps, point_num), signed, rad/s per unit length."""
+    coordinates, triangles, areas = _surface_arrays(surface)
+    op = _operator(coordinates, triangles, areas, np.asarray(e, dtype=np.float64).reshape(-1, 2, 3))
+    return _run(op, np.asarray(phases)[:time_steps], dt, True, False, True)[1]
+
+
+def wave_velocity_amplitude(surface, potentials, dt, time_steps, e):
+    """Reference :14-58 (np.gradient(edge_order=2) time derivative)."""
+    coordinates, triangles, areas = _surface_arrays(surface)
+    op = _operator(coordinates, triangles, areas, np.asarray(e, dtype=np.float64).reshape(-1, 2, 3))
+    return _run(op, np.asarray(potentials)[:time_steps], dt, False, False, True)[1]
+
+
+def angle_subtract(f1, f2, angleFlag=True):
+    """Reference :224-233 (host helper; the kernel applies the same formula per element)."""
+    if angleFlag:
+        return np.mod(f1 - f2 + np.pi, 2 * np.pi) - np.pi
+    return f1 - f2
+
+
+def compute_temporal_gradient_phase(data, dt):
+    """Reference :60-77; computed by the kernel on a flat two-vertex mesh would be overkill, so
+    this thin helper evaluates the same three formulas with numpy for callers that want the
+    derivative alone (wave_velocity_phase fuses it into the kernel)."""
+    data = np.asarray(data, dtype=np.float64)
+    g = np.zeros_like(data)
+    g[0] = angle_subtract(data[1], data[0]) / dt
+    g[1:-1] = angle_subtract(data[2:], data[:-2]) / (2 * dt)
+    g[-1] = angle_subtract(data[-1], data[-2]) / dt
+    return g

@@ -207,3 +207,27 @@ def mesh_for_config(name):
     if name == "C4":
         return two_hemispheres(7)
     raise ValueError(f"unknown config {name!r}")
+
+
+class SurfaceMesh:
+    """Minimal stand-in for the pyvista PolyData members the reference scripts touch
+    (S3...:79-84, S5_compute_wave_v.py:18-21,162): ``points``, ``faces`` (flat [3,a,b,c,...]),
+    ``point_normals``, ``compute_cell_sizes(...)['Area']`` and ``point_cell_ids(i)``."""
+
+    def __init__(self, coordinates, triangles, normals=None, areas=None):
+        self.points = np.asarray(coordinates, dtype=np.float64)
+        tri = np.asarray(triangles, dtype=np.int64)
+        self.triangles = tri
+        self.faces = np.concatenate([np.full((len(tri), 1), 3, dtype=np.int64), tri], axis=1).ravel()
+        self.point_normals = vertex_normals(self.points, tri) if normals is None else np.asarray(normals)
+        self._areas = face_areas(self.points, tri) if areas is None else np.asarray(areas, dtype=np.float64)
+        order = np.argsort(tri.ravel(), kind="stable")
+        self._cells = order // 3
+        self._ptr = np.concatenate([[0], np.cumsum(np.bincount(tri.ravel(), minlength=len(self.points)))])
+
+    def compute_cell_sizes(self, length=False, volume=False):
+        return {"Area": self._areas}
+
+    def point_cell_ids(self, index):
+        """ids of the cells using point ``index``, ascending (VTK's order for a PolyData)."""
+        return [int(c) for c in self._cells[self._ptr[index]:self._ptr[index + 1]]]

@@ -304,3 +304,55 @@ def find_singularity_points_for_all_Vk(V_k_coord, coordinates, triangles, eps):
         vi, fi, lm, P, _ = find_singularity_points(coordinates, triangles, V_now, eps)
         out.append([coordinates[i] for i in vi] + [p for p in P])
     return out
+
+
+# ----------------------------------------------------------------------------
+# S5_compute_wave_v.py ("next" row 1)
+# ----------------------------------------------------------------------------
+def angle_subtract(f1, f2):
+    """S5_compute_wave_v.py:224-233."""
+    return np.mod(f1 - f2 + np.pi, 2 * np.pi) - np.pi
+
+
+def temporal_gradient_phase(data, dt):
+    """S5_compute_wave_v.py:60-77."""
+    data = np.asarray(data, dtype=np.float64)
+    g = np.zeros_like(data)
+    g[0] = angle_subtract(data[1], data[0]) / dt
+    g[1:-1] = angle_subtract(data[2:], data[:-2]) / (2 * dt)
+    g[-1] = angle_subtract(data[-1], data[-2]) / dt
+    return g
+
+
+def grad_M_I(coordinates, triangles, potentials, areas):
+    """S5_compute_wave_v.py:136-171 -> grad_point (T,N,3): area-weighted mean over the faces of a
+    vertex (ascending face index) of the per-face gradient sum_m I[T_m] grad_w[T][m]."""
+    t = np.asarray(triangles, dtype=np.int64)
+    pot = np.asarray(potentials, dtype=np.float64)
+    areas = np.asarray(areas, dtype=np.float64)
+    gw = gradient_w(coordinates, t)
+    T, N = pot.shape
+    gM = (pot[:, t[:, 0], None] * gw[None, :, 0] + pot[:, t[:, 1], None] * gw[None, :, 1]
+          + pot[:, t[:, 2], None] * gw[None, :, 2])                       # (T,F,3)  :154-158
+    gp = np.zeros((T, N, 3))
+    asum = np.zeros(N)
+    for f in range(len(t)):                                                # ascending faces = :161-166 order
+        for m in range(3):
+            gp[:, t[f, m]] += gM[:, f] * areas[f]
+            asum[t[f, m]] += areas[f]
+    return gp / asum[None, :, None]
+
+
+def wave_velocity(coordinates, triangles, areas, data, dt, e, phase=True):
+    """S5_compute_wave_v.py:79-123 (phase) / :14-58 (amplitude)."""
+    data = np.asarray(data, dtype=np.float64)
+    e = np.asarray(e, dtype=np.float64)
+    td = temporal_gradient_phase(data, dt) if phase else np.gradient(data, axis=0, edge_order=2) / dt
+    gp = grad_M_I(coordinates, triangles, data, areas)
+    e1, e2 = e[:, 0], e[:, 1]
+    n = np.cross(e1, e2)                                                   # :177
+    Vn = np.einsum("tnx,nx->tn", gp, n)[:, :, None] * n[None] / np.einsum("nx,nx->n", n, n)[None, :, None]
+    Vt = gp - Vn                                                           # :179
+    al = np.einsum("tnx,nx->tn", Vt, e1) / np.einsum("nx,nx->n", e1, e1)   # :189
+    be = np.einsum("tnx,nx->tn", Vt, e2) / np.einsum("nx,nx->n", e2, e2)   # :190
+    return td / np.sqrt(al ** 2 + be ** 2)                                 # :117,:121

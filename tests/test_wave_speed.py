@@ -1,0 +1,70 @@
+"""S5 wave-speed row ("next" row 1 of SURVEY 8f): oracle vs outputs of the unmodified
+S5_compute_wave_v.py (tests/golden/s5_*.npz, made by tests/golden/make_golden_s5.py) on CPU,
+and the CUDA kernel vs the same goldens / the oracle on the GPU box."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+from manifold_based_optical_flow_method_b200 import synthetic
+from oracle import mof_oracle
+
+CASES = ["s5_ico2", "s5_patch7"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_s5(case):
+    g = load_golden(case)
+    dt = float(g["dt"])
+    assert np.allclose(mof_oracle.temporal_gradient_phase(g["phases"], dt), g["temporal_gradient_phase"], rtol=1e-13, atol=1e-9)
+    gp = mof_oracle.grad_M_I(g["coordinates"], g["triangles"], g["phases"], g["areas"])
+    assert rel_l2(gp, g["grad_point"]) <= 1e-14
+    wp = mof_oracle.wave_velocity(g["coordinates"], g["triangles"], g["areas"], g["phases"], dt, g["e"], phase=True)
+    assert rel_l2(wp, g["wave_velocity_phase"]) <= 1e-12
+    wa = mof_oracle.wave_velocity(g["coordinates"], g["triangles"], g["areas"], g["potentials"], dt, g["e"], phase=False)
+    assert rel_l2(wa, g["wave_velocity_amplitude"]) <= 1e-12
+    # the wrapped derivative really wraps in this fixture
+    raw = np.abs(np.diff(g["phases"], axis=0)).max()
+    assert raw > np.pi
+
+
+def test_surface_mesh_stub_point_cells():
+    coords, tris, normals, areas = synthetic.icosphere(1)
+    s = synthetic.SurfaceMesh(coords, tris, normals, areas)
+    assert np.array_equal(s.faces.reshape(-1, 4)[:, 1:], tris)
+    for i in (0, 5, 41):
+        ids = s.point_cell_ids(i)
+        assert ids == sorted(ids) and all(i in tris[c] for c in ids)
+        assert len(ids) == int(np.sum(tris == i))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_wave_speed_matches_reference_s5(case):
+    from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5
+    g = load_golden(case)
+    dt = float(g["dt"])
+    surf = synthetic.SurfaceMesh(g["coordinates"], g["triangles"], g["normals"], g["areas"])
+    T = len(g["phases"])
+    wp = s5.wave_velocity_phase(surf, g["phases"], dt, T, g["e"])
+    assert wp.shape == g["wave_velocity_phase"].shape
+    assert rel_l2(wp, g["wave_velocity_phase"]) <= 1e-12
+    wa = s5.wave_velocity_amplitude(surf, g["potentials"], dt, T, g["e"])
+    assert rel_l2(wa, g["wave_velocity_amplitude"]) <= 1e-12
+    gp = s5.compute_grad_M_I(g["coordinates"], g["triangles"], g["phases"], surf, g["areas"])
+    assert rel_l2(gp, g["grad_point"]) <= 1e-13
+    assert np.allclose(s5.compute_temporal_gradient_phase(g["phases"], dt), g["temporal_gradient_phase"], rtol=1e-13, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_wave_speed_matches_oracle_medium():
+    """BASELINE.json configs[4]-style input at a size the oracle handles in seconds."""
+    from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5
+    coords, tris, normals, areas = synthetic.pial_like(4)
+    T, SF = 40, 512.0
+    t_k = synthetic.time_axis(T, SF)
+    phases = synthetic.wrapped_phase(coords, t_k, seed=4, omega=500.0)
+    e = mof_oracle.orthonormal_basis(normals)
+    surf = synthetic.SurfaceMesh(coords, tris, normals, areas)
+    w = s5.wave_velocity_phase(surf, phases, 1 / SF, T, e)
+    wo = mof_oracle.wave_velocity(coords, tris, areas, phases, 1 / SF, e, phase=True)
+    assert rel_l2(w, wo) <= 1e-12
