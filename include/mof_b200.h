@@ -116,8 +116,8 @@ typedef struct {
     double* dIt;             /* [G][N][32]       (I(t_k+1) - I(t_k)) / dt               */
     double* vals;            /* [G][nb][4][32]   a1 + lambda*a2 block values            */
     double* rhs;             /* [G][N][2][32]    f                                      */
-    double* minv;            /* [G][N][3][32]    block-Jacobi: inverse of the diagonal 2x2 blocks;
-                                                 SSOR: the diagonal blocks divided by omega (Dt)    */
+    double* minv;            /* [G][N][3][32]    block Jacobi: inverse of the diagonal 2x2 blocks;
+                                                 SSOR: S = D^-1/2, the symmetric scaling applied to vals / rhs */
     double* x;               /* [G][N][2][32]    solution (tangent coefficients)        */
     double* r;               /* [G][N][2][32]                                           */
     double* z;               /* [G][N][2][32]                                           */
@@ -168,9 +168,11 @@ int mof_geom_a2(const mof_mesh_dev* mesh, double* a2v, void* stream);
  * new value (:174-175); dt[k] = t_k[k+1]-t_k[k] (:125), device (n_frames,). */
 int mof_pack_frames(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const double* I_now,
                     const double* I_next, int64_t ld, const double* dt, void* stream);
-/* vals = a1(I) + lambda*a2, rhs = f, and the preconditioner data in `minv`:
- * omega = 0: inverse of the diagonal 2x2 blocks (block Jacobi); omega in (0,2): the diagonal
- * blocks divided by omega (SSOR). */
+/* omega = 0 (block Jacobi): vals = a1(I) + lambda*a2, rhs = f, minv = inverse of the diagonal
+ * 2x2 blocks.  omega in (0,2) (SSOR): the system is additionally scaled symmetrically with
+ * S = D^-1/2 (D = diagonal blocks): vals = S (a1 + lambda*a2) S (identity diagonal blocks),
+ * rhs = S f, minv = S; mof_pcg_solve_batch undoes the scaling (x = S xh) and judges convergence
+ * on the unscaled residual. */
 int mof_assemble_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double lambda_,
                        double omega, void* stream);
 

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) pack_kernel(int64_t N, int32_t n_frames, 
     }
 }
 
-__global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, double diag_scale) {
+__global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = blockIdx.y;
     const int64_t N = M.n_vertices, nb = M.n_blocks;
@@ -66,13 +66,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch
             if (b == bd) {
                 mof_assemble_block_body<true>(M, v, b, It_l, dIt_l, lambda_, a, f);
                 double mi[3];
-                if (diag_scale == 0.0) {
-                    mof_inv2_body(a, mi);                      // block-Jacobi: D^-1
-                } else {                                       // SSOR: Dt = D / omega
-                    mi[0] = a[0] * diag_scale;
-                    mi[1] = 0.5 * (a[1] + a[2]) * diag_scale;
-                    mi[2] = a[3] * diag_scale;
-                }
+                if (!ssor) mof_inv2_body(a, mi);               // block Jacobi: D^-1
+                else       mof_inv_sqrt2_body(a, mi);          // SSOR: S = D^-1/2 (scale_kernel applies it)
                 B.rhs[mof_ix_vec(N, g, v, 0) + lane] = f[0];
                 B.rhs[mof_ix_vec(N, g, v, 1) + lane] = f[1];
                 B.minv[mof_ix_minv(N, g, v, 0) + lane] = mi[0];
@@ -86,6 +81,35 @@ __global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch
             out[MOF_W] = a[1];
             out[2 * MOF_W] = a[2];
             out[3 * MOF_W] = a[3];
+        }
+    }
+}
+
+// SSOR path: symmetric diagonal scaling Ah = S A S, bh = S b with S = D^-1/2 (in B.minv), in place.
+// After it the diagonal blocks are the identity, so the sweeps and the vector kernel need no
+// per-vertex matrix data at all (3 x 24 N bytes less per iteration).
+__global__ void __launch_bounds__(256) scale_kernel(mof_mesh_dev M, mof_batch_dev B) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = blockIdx.y;
+    const int64_t N = M.n_vertices, nb = M.n_blocks;
+    const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int64_t v = row0 + rr;
+        if (v >= N) break;
+        double si[3], f0, f1;
+        for (int c = 0; c < 3; ++c) si[c] = B.minv[mof_ix_minv(N, g, v, c) + lane];
+        f0 = B.rhs[mof_ix_vec(N, g, v, 0) + lane];
+        f1 = B.rhs[mof_ix_vec(N, g, v, 1) + lane];
+        B.rhs[mof_ix_vec(N, g, v, 0) + lane] = si[0] * f0 + si[1] * f1;
+        B.rhs[mof_ix_vec(N, g, v, 1) + lane] = si[1] * f0 + si[2] * f1;
+        for (int32_t b = M.rowptr[v]; b < M.rowptr[v + 1]; ++b) {
+            const int64_t j = M.col[b];
+            double sj[3], a[4], o[4];
+            for (int c = 0; c < 3; ++c) sj[c] = B.minv[mof_ix_minv(N, g, j, c) + lane];
+            double* ap = B.vals + mof_ix_val(nb, g, b, 0) + lane;
+            for (int c = 0; c < 4; ++c) a[c] = ap[c * MOF_W];
+            mof_scale_block_body(si, sj, a, o);
+            for (int c = 0; c < 4; ++c) ap[c * MOF_W] = o[c];
         }
     }
 }
@@ -113,7 +137,11 @@ extern "C" int mof_assemble_batch(const mof_mesh_dev* mesh, const mof_batch_dev*
     MOF_REQUIRE(omega >= 0.0 && omega < 2.0, "omega must be 0 (block Jacobi) or in (0,2) (SSOR)");
     MOF_REQUIRE(batch->It && batch->dIt && batch->vals && batch->rhs && batch->minv, "batch buffers missing");
     dim3 grid((unsigned)mof_num_tiles(mesh->n_vertices), batch->n_groups);
-    assemble_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch, lambda_, omega > 0.0 ? 1.0 / omega : 0.0);
+    assemble_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch, lambda_, omega > 0.0);
     MOF_LAUNCH_CHECK("assemble_kernel");
+    if (omega > 0.0) {
+        scale_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch);
+        MOF_LAUNCH_CHECK("scale_kernel");
+    }
     return 0;
 }

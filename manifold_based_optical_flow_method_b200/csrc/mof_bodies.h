@@ -164,32 +164,42 @@ MOF_HD void mof_inv2_body(const double* a, double* m) {
 }
 
 // ---- SSOR sweeps (Eisenstat form of the SSOR-preconditioned CG) ------------------
-// A = L + D + U in the block-multicolour numbering (D = 2x2 diagonal blocks, U = L'),
-// Dt = D / omega.  The preconditioned operator is
-//     At v = t + (Dt+L)^-1 (v - (2-omega) Dt t),   t = (Dt+U)^-1 v,
+// The SSOR path first scales the system symmetrically with S = D^-1/2 (D = 2x2 diagonal blocks):
+// Ah = S A S has identity diagonal blocks, bh = S b, x = S xh.  SSOR is invariant under this
+// scaling (same iterates as SSOR on A), but the sweeps no longer need any diagonal data.
+// With Ah = L + I + U in the block-multicolour numbering and Dt = I / omega the preconditioned
+// operator is
+//     At v = t + (Dt+L)^-1 (v - ((2-omega)/omega) t),   t = (Dt+U)^-1 v,
 // i.e. one backward and one forward block-triangular solve, each reading half of the
 // off-diagonal blocks.  A sweep walks the rows of one patch (tile) sequentially for one
 // frame; patches of one colour are independent of each other.  Pointers carry the
-// (group, lane) offset: vertex v component c at [(2v+c)*W], block b entry c at [(4b+c)*W],
-// Dt of vertex v at [(3v+c)*W] (d00, d01, d11).
-MOF_HD void mof_solve2_body(double d0, double d1, double d2, double a0, double a1, double* o0, double* o1) {
-    const double det = d0 * d2 - d1 * d1;
-    *o0 = (d2 * a0 - d1 * a1) / det;
-    *o1 = (d0 * a1 - d1 * a0) / det;
+// (group, lane) offset: vertex v component c at [(2v+c)*W], block b entry c at [(4b+c)*W].
+
+// S = M^-1/2 of the SPD block M = [[a0,a1],[a2,a3]] (a1 ~ a2): sqrt(M) = (M + s I)/t with
+// s = sqrt(det M), t = sqrt(tr M + 2 s), hence M^-1/2 = [[c+s, -b],[-b, a+s]] / (s t).
+MOF_HD void mof_inv_sqrt2_body(const double* a, double* o) {
+    const double b = 0.5 * (a[1] + a[2]);
+    const double s = sqrt(a[0] * a[3] - b * b);
+    const double t = sqrt(a[0] + a[3] + 2.0 * s);
+    const double r = 1.0 / (s * t);
+    o[0] = (a[3] + s) * r;
+    o[1] = -b * r;
+    o[2] = (a[0] + s) * r;
 }
 
-// Backward sweep over rows r1-1 .. r0 of a patch: t_i = Dt_i^-1 (rhs_i - sum_{j>i} U_ij t_j).
-//   mode 0 (iteration): rhs_i = zs z_i + beta p_i and p_i <- rhs_i (the CG direction update fused
-//                       in; a frozen frame has zs = 0, beta = 1 and keeps its p)
+// Backward sweep over rows r1-1 .. r0 of a patch: t_i = omega (rhs_i - sum_{j>i} U_ij t_j).
+//   mode 0 (iteration): rhs_i = zsw r_i + beta p_i and p_i <- rhs_i: the CG direction update
+//                       p = z + beta p with z = Dt r = r / omega fused in (zsw = 1/omega; a frozen
+//                       frame has zsw = 0, beta = 1 and keeps its p)
 //   mode 1 (back-transform): rhs_i = p_i (p is the input vector and is left untouched)
 MOF_HD void mof_sweep_back_body(const int32_t* rowptr, const int32_t* col, const int32_t* diag,
-                                const double* vals_l, const double* dt_l, const double* z_l, double* p_l,
-                                double* t_l, int64_t r0, int64_t r1, double beta, double zs, int mode) {
+                                const double* vals_l, const double* r_l, double* p_l, double* t_l,
+                                int64_t r0, int64_t r1, double beta, double zsw, double omega, int mode) {
     for (int64_t i = r1 - 1; i >= r0; --i) {
         double a0, a1;
         if (mode == 0) {
-            a0 = zs * z_l[(2 * i) * MOF_W] + beta * p_l[(2 * i) * MOF_W];
-            a1 = zs * z_l[(2 * i + 1) * MOF_W] + beta * p_l[(2 * i + 1) * MOF_W];
+            a0 = zsw * r_l[(2 * i) * MOF_W] + beta * p_l[(2 * i) * MOF_W];
+            a1 = zsw * r_l[(2 * i + 1) * MOF_W] + beta * p_l[(2 * i + 1) * MOF_W];
             p_l[(2 * i) * MOF_W] = a0;
             p_l[(2 * i + 1) * MOF_W] = a1;
         } else {
@@ -203,31 +213,27 @@ MOF_HD void mof_sweep_back_body(const int32_t* rowptr, const int32_t* col, const
             a0 -= a[0] * t0 + a[MOF_W] * t1;
             a1 -= a[2 * MOF_W] * t0 + a[3 * MOF_W] * t1;
         }
-        const double* d = dt_l + (size_t)i * 3 * MOF_W;
-        double o0, o1;
-        mof_solve2_body(d[0], d[MOF_W], d[2 * MOF_W], a0, a1, &o0, &o1);
-        t_l[(2 * i) * MOF_W] = o0;
-        t_l[(2 * i + 1) * MOF_W] = o1;
+        t_l[(2 * i) * MOF_W] = omega * a0;
+        t_l[(2 * i + 1) * MOF_W] = omega * a1;
     }
 }
 
-// Forward sweep over rows r0 .. r1-1: w_i = Dt_i^-1 (v_i - sum_{j<i} L_ij w_j).
-//   mode 0 (iteration): v_i = p_i - (2-omega) Dt_i t_i ; returns sum_i p_i . (t_i + w_i)
+// Forward sweep over rows r0 .. r1-1: w_i = omega (v_i - sum_{j<i} L_ij w_j).
+//   mode 0 (iteration): v_i = p_i - ((2-omega)/omega) t_i ; returns sum_i p_i . (t_i + w_i)
 //   mode 1 (transform a rhs): v_i = p_i ; returns 0
 MOF_HD double mof_sweep_fwd_body(const int32_t* rowptr, const int32_t* col, const int32_t* diag,
-                                 const double* vals_l, const double* dt_l, const double* p_l, const double* t_l,
-                                 double* w_l, int64_t r0, int64_t r1, double omega, int mode) {
+                                 const double* vals_l, const double* p_l, const double* t_l, double* w_l,
+                                 int64_t r0, int64_t r1, double omega, int mode) {
     double dot = 0.0;
+    const double ks = (2.0 - omega) / omega;
     for (int64_t i = r0; i < r1; ++i) {
-        const double* d = dt_l + (size_t)i * 3 * MOF_W;
-        const double d0 = d[0], d1 = d[MOF_W], d2 = d[2 * MOF_W];
         const double p0 = p_l[(2 * i) * MOF_W], p1 = p_l[(2 * i + 1) * MOF_W];
         double a0 = p0, a1 = p1, t0 = 0.0, t1 = 0.0;
         if (mode == 0) {
             t0 = t_l[(2 * i) * MOF_W];
             t1 = t_l[(2 * i + 1) * MOF_W];
-            a0 -= (2.0 - omega) * (d0 * t0 + d1 * t1);
-            a1 -= (2.0 - omega) * (d1 * t0 + d2 * t1);
+            a0 -= ks * t0;
+            a1 -= ks * t1;
         }
         for (int32_t b = rowptr[i]; b < diag[i]; ++b) {
             const int64_t j = col[b];
@@ -236,13 +242,23 @@ MOF_HD double mof_sweep_fwd_body(const int32_t* rowptr, const int32_t* col, cons
             a0 -= a[0] * w0 + a[MOF_W] * w1;
             a1 -= a[2 * MOF_W] * w0 + a[3 * MOF_W] * w1;
         }
-        double o0, o1;
-        mof_solve2_body(d0, d1, d2, a0, a1, &o0, &o1);
+        const double o0 = omega * a0, o1 = omega * a1;
         w_l[(2 * i) * MOF_W] = o0;
         w_l[(2 * i + 1) * MOF_W] = o1;
         if (mode == 0) dot += p0 * (t0 + o0) + p1 * (t1 + o1);
     }
     return dot;
+}
+
+// Symmetric scaling of one off-diagonal/diagonal block: Ah = S_i A S_j (S symmetric, 3 values each)
+MOF_HD void mof_scale_block_body(const double* si, const double* sj, const double* a, double* o) {
+    // T = S_i A
+    const double t00 = si[0] * a[0] + si[1] * a[2], t01 = si[0] * a[1] + si[1] * a[3];
+    const double t10 = si[1] * a[0] + si[2] * a[2], t11 = si[1] * a[1] + si[2] * a[3];
+    o[0] = t00 * sj[0] + t01 * sj[1];
+    o[1] = t00 * sj[1] + t01 * sj[2];
+    o[2] = t10 * sj[0] + t11 * sj[1];
+    o[3] = t10 * sj[1] + t11 * sj[2];
 }
 
 // ---- K4 ----------------------------------------------------------------------

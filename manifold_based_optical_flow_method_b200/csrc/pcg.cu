@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(const int32_t* __restrict__ r
 // true-residual check (init_kernel, MODE_VERIFY) asks for more iterations.
 // ---------------------------------------------------------------------------------
 template <bool SSOR>
-__global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N, int ntiles) {
+__global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N, int ntiles, double inv_omega) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     if (group_done_ptr(B.state, G)[g]) return;
@@ -216,25 +216,28 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
         const int64_t v = row0 + q;
         if (v >= N) break;
         const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
-        const size_t im = mof_ix_minv(N, g, v, 0) + lane;
         const double p0 = B.p[i0], p1 = B.p[i1];
         double a0 = __ldcs(B.ap + i0), a1 = __ldcs(B.ap + i1);
         if (SSOR) { a0 += __ldcs(B.t + i0); a1 += __ldcs(B.t + i1); }
         double x0 = B.x[i0], x1 = B.x[i1];
         double r0 = B.r[i0], r1 = B.r[i1];
-        const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
         x0 = fma(alpha, p0, x0);
         x1 = fma(alpha, p1, x1);
         r0 = fma(-alpha, a0, r0);
         r1 = fma(-alpha, a1, r1);
-        const double z0 = m0 * r0 + m1 * r1;
-        const double z1 = m1 * r0 + m2 * r1;
         B.x[i0] = x0; B.x[i1] = x1;
         B.r[i0] = r0; B.r[i1] = r1;
-        B.z[i0] = z0; B.z[i1] = z1;
-        rz = fma(r0, z0, rz); rz = fma(r1, z1, rz);
+        if (!SSOR) {                                   // z = D^-1 r ; SSOR: z = r / omega is never stored
+            const size_t im = mof_ix_minv(N, g, v, 0) + lane;
+            const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
+            const double z0 = m0 * r0 + m1 * r1;
+            const double z1 = m1 * r0 + m2 * r1;
+            B.z[i0] = z0; B.z[i1] = z1;
+            rz = fma(r0, z0, rz); rz = fma(r1, z1, rz);
+        }
         rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
     }
+    if (SSOR) rz = rr * inv_omega;                     // r'z with z = r / omega (linear, so per-lane partials add up)
     double val[2] = {rz, rr}, tot[2];
     if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
         return;
@@ -352,7 +355,8 @@ __device__ __forceinline__ void sweep_row_offdiag(const int32_t* __restrict__ co
 template <int MODE>
 __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                          const int32_t* __restrict__ diag, mof_batch_dev B, double* pvec,
-                                                         double* tout, int64_t N, int64_t nb, int tile0, int tile1) {
+                                                         double* tout, int64_t N, int64_t nb, int tile0, int tile1,
+                                                         double omega) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     if (MODE == 0 && group_done_ptr(B.state, G)[g]) return;
@@ -361,14 +365,13 @@ __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restri
     if (tile >= tile1) return;
     const int64_t r0 = (int64_t)tile * MOF_TILE_ROWS;
     const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
-    double beta = 0.0, zs = 1.0;
+    double beta = 0.0, zsw = 0.0;
     if (MODE == 0) {
         beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
-        zs = scal_ptr(B.scal, g, MOF_S_ZS)[lane];
+        zsw = scal_ptr(B.scal, g, MOF_S_ZS)[lane] / omega;         // z = Dt r = r / omega
     }
     const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
-    const double* __restrict__ dt_l = B.minv + (size_t)g * N * 3 * MOF_W + lane;
-    const double* __restrict__ z_l = B.z + (size_t)g * N * 2 * MOF_W + lane;
+    const double* __restrict__ r_l = B.r + (size_t)g * N * 2 * MOF_W + lane;
     double* p_l = pvec + (size_t)g * N * 2 * MOF_W + lane;
     double* t_l = tout + (size_t)g * N * 2 * MOF_W + lane;
     // row pointers of the patch: lane q holds rowptr[r0+q+1] and diag[r0+q] (two coalesced loads)
@@ -379,16 +382,13 @@ __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restri
         const int q = (int)(i - r0);
         const int32_t be = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
         const int32_t bs = (q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32)) + 1;
-        const double d0 = dt_l[(size_t)i * 3 * MOF_W], d1 = dt_l[(size_t)i * 3 * MOF_W + MOF_W],
-                     d2 = dt_l[(size_t)i * 3 * MOF_W + 2 * MOF_W];
         double a0 = p_l[(size_t)(2 * i) * MOF_W], a1 = p_l[(size_t)(2 * i + 1) * MOF_W];
         if (MODE == 0) {
-            a0 = zs * z_l[(size_t)(2 * i) * MOF_W] + beta * a0;
-            a1 = zs * z_l[(size_t)(2 * i + 1) * MOF_W] + beta * a1;
+            a0 = zsw * r_l[(size_t)(2 * i) * MOF_W] + beta * a0;
+            a1 = zsw * r_l[(size_t)(2 * i + 1) * MOF_W] + beta * a1;
             p_l[(size_t)(2 * i) * MOF_W] = a0;
             p_l[(size_t)(2 * i + 1) * MOF_W] = a1;
         }
-        const double rdet = 1.0 / (d0 * d2 - d1 * d1);            // off the critical path: independent of the gather
         if (q >= kPrefetchRows) {                                   // matrix values of a row a few steps ahead -> L2
             const int qq = q - kPrefetchRows;
             const int32_t pe = qq < 32 ? __shfl_sync(kFull, rp_lo, qq) : __shfl_sync(kFull, rp_hi, qq - 32);
@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restri
             for (int32_t b = ps; b < pe; ++b) prefetch_block_l2(vals_l, b);
         }
         sweep_row_offdiag(col, vals_l, t_l, bs, be, a0, a1);
-        t_l[(size_t)(2 * i) * MOF_W] = (d2 * a0 - d1 * a1) * rdet;
-        t_l[(size_t)(2 * i + 1) * MOF_W] = (d0 * a1 - d1 * a0) * rdet;
+        t_l[(size_t)(2 * i) * MOF_W] = omega * a0;
+        t_l[(size_t)(2 * i + 1) * MOF_W] = omega * a1;
     }
 }
 
@@ -419,29 +419,25 @@ __global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restric
         const int64_t r0 = (int64_t)tile * MOF_TILE_ROWS;
         const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
         const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
-        const double* __restrict__ dt_l = B.minv + (size_t)g * N * 3 * MOF_W + lane;
         const double* __restrict__ p_l = pin + (size_t)g * N * 2 * MOF_W + lane;
         const double* __restrict__ t_l = B.t + (size_t)g * N * 2 * MOF_W + lane;
         double* w_l = wout + (size_t)g * N * 2 * MOF_W + lane;
         int32_t rp_lo = 0, rp_hi = 0, dg_lo = 0, dg_hi = 0;
         if (r0 + lane < r1) { rp_lo = rowptr[r0 + lane]; dg_lo = diag[r0 + lane]; }
         if (r0 + 32 + lane < r1) { rp_hi = rowptr[r0 + 32 + lane]; dg_hi = diag[r0 + 32 + lane]; }
-        const double kscale = 2.0 - omega;
+        const double kscale = (2.0 - omega) / omega;
         for (int64_t i = r0; i < r1; ++i) {
             const int q = (int)(i - r0);
             const int32_t bs = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
             const int32_t be = q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32);
-            const double d0 = dt_l[(size_t)i * 3 * MOF_W], d1 = dt_l[(size_t)i * 3 * MOF_W + MOF_W],
-                         d2 = dt_l[(size_t)i * 3 * MOF_W + 2 * MOF_W];
             const double p0 = p_l[(size_t)(2 * i) * MOF_W], p1 = p_l[(size_t)(2 * i + 1) * MOF_W];
             double a0 = p0, a1 = p1, t0 = 0.0, t1 = 0.0;
             if (MODE == 0) {
                 t0 = t_l[(size_t)(2 * i) * MOF_W];
                 t1 = t_l[(size_t)(2 * i + 1) * MOF_W];
-                a0 -= kscale * (d0 * t0 + d1 * t1);
-                a1 -= kscale * (d1 * t0 + d2 * t1);
+                a0 -= kscale * t0;
+                a1 -= kscale * t1;
             }
-            const double rdet = 1.0 / (d0 * d2 - d1 * d1);
             if (q + kPrefetchRows < (int)(r1 - r0)) {
                 const int qq = q + kPrefetchRows;
                 const int32_t ps = qq < 32 ? __shfl_sync(kFull, rp_lo, qq) : __shfl_sync(kFull, rp_hi, qq - 32);
@@ -449,7 +445,7 @@ __global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restric
                 for (int32_t b = ps; b < pe; ++b) prefetch_block_l2(vals_l, b);
             }
             sweep_row_offdiag(col, vals_l, w_l, bs, be, a0, a1);
-            const double o0 = (d2 * a0 - d1 * a1) * rdet, o1 = (d0 * a1 - d1 * a0) * rdet;
+            const double o0 = omega * a0, o1 = omega * a1;
             w_l[(size_t)(2 * i) * MOF_W] = o0;
             w_l[(size_t)(2 * i + 1) * MOF_W] = o1;
             if (MODE == 0) dot += p0 * (t0 + o0) + p1 * (t1 + o1);
@@ -477,17 +473,18 @@ __global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------------
-// Start / verification kernel.
+// Start / verification kernel.  ssor != 0: the batch holds the scaled system (vals = S A S,
+// rhs = S b, minv = S); norms of the ORIGINAL residual / rhs are obtained by applying S^-1.
 //   MODE_START_JACOBI : x = 0, r = rhs, z = D^-1 r, p = 0 ; ||b||^2 ; per-frame bookkeeping
-//   MODE_NORM         : ||rhs||^2 -> BBT (true rhs norm for the SSOR path)
-//   MODE_START_SSOR   : r (= (Dt+L)^-1 rhs, already in B.r) ; x = 0, z = Dt r, p = 0 ; bookkeeping
-//   MODE_VERIFY       : true residual ||rhs - ap||^2 with ap = A x ; frames that were frozen on
-//                       the recurrence residual but miss tol get a tighter threshold and resume
+//   MODE_NORM         : ||S^-1 rhs||^2 = ||b||^2 -> BBT (SSOR path)
+//   MODE_START_SSOR   : r (= (Dt+L)^-1 rhs, already in B.r) ; x = 0, p = 0 ; bookkeeping
+//   MODE_VERIFY       : true residual ||b - A x||^2 from ap = A x (scaled space for SSOR) ; frames
+//                       frozen on the recurrence residual that miss tol get a tighter threshold and resume
 // ---------------------------------------------------------------------------------
 enum { MODE_START_JACOBI = 0, MODE_NORM = 1, MODE_START_SSOR = 2, MODE_VERIFY = 3 };
 
 __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, int ntiles, int mode, double tol2,
-                                                   int last_round) {
+                                                   int last_round, int ssor, double inv_omega) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -498,23 +495,32 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
         const int64_t v = row0 + q;
         if (v >= N) break;
         const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
+        const size_t im = mof_ix_minv(N, g, v, 0) + lane;
         double r0, r1;
         if (mode == MODE_START_SSOR) { r0 = B.r[i0]; r1 = B.r[i1]; }
         else                         { r0 = B.rhs[i0]; r1 = B.rhs[i1]; }
         if (mode == MODE_VERIFY) { r0 -= B.ap[i0]; r1 -= B.ap[i1]; }
-        if (mode == MODE_START_JACOBI || mode == MODE_START_SSOR) {
-            const size_t im = mof_ix_minv(N, g, v, 0) + lane;
+        if (ssor && (mode == MODE_VERIFY || mode == MODE_NORM)) {      // back to the unscaled system: S^-1 r
+            const double s0 = B.minv[im], s1 = B.minv[im + MOF_W], s2 = B.minv[im + 2 * MOF_W];
+            const double rdet = 1.0 / (s0 * s2 - s1 * s1);
+            const double u0 = (s2 * r0 - s1 * r1) * rdet, u1 = (s0 * r1 - s1 * r0) * rdet;
+            r0 = u0; r1 = u1;
+        }
+        if (mode == MODE_START_JACOBI) {
             const double m0 = B.minv[im], m1 = B.minv[im + MOF_W], m2 = B.minv[im + 2 * MOF_W];
             const double z0 = m0 * r0 + m1 * r1;
             const double z1 = m1 * r0 + m2 * r1;
-            B.x[i0] = 0.0; B.x[i1] = 0.0;
-            B.p[i0] = 0.0; B.p[i1] = 0.0;
-            if (mode == MODE_START_JACOBI) { B.r[i0] = r0; B.r[i1] = r1; }
+            B.r[i0] = r0; B.r[i1] = r1;
             B.z[i0] = z0; B.z[i1] = z1;
             rz = fma(r0, z0, rz); rz = fma(r1, z1, rz);
         }
+        if (mode == MODE_START_JACOBI || mode == MODE_START_SSOR) {
+            B.x[i0] = 0.0; B.x[i1] = 0.0;
+            B.p[i0] = 0.0; B.p[i1] = 0.0;
+        }
         rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
     }
+    if (mode == MODE_START_SSOR) rz = rr * inv_omega;                   // z = r / omega
     double val[2] = {rz, rr}, tot[2];
     if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
         return;
@@ -574,6 +580,23 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
             *done = 0;
             atomicAdd(groups_active_ptr(B.state, G), 1);
         }
+    }
+}
+
+// SSOR path, end of the solve: x = S xs with xs (solution of the scaled system) in B.t
+__global__ void __launch_bounds__(256) unscale_kernel(mof_batch_dev B, int64_t N) {
+    const int64_t g = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int64_t v = row0 + q;
+        if (v >= N) break;
+        const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
+        const size_t im = mof_ix_minv(N, g, v, 0) + lane;
+        const double s0 = B.minv[im], s1 = B.minv[im + MOF_W], s2 = B.minv[im + 2 * MOF_W];
+        const double t0 = B.t[i0], t1 = B.t[i1];
+        B.x[i0] = s0 * t0 + s1 * t1;
+        B.x[i1] = s1 * t0 + s2 * t1;
     }
 }
 
@@ -665,6 +688,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     const int G = B.n_groups;
     const int ntiles = (int)mof_num_tiles(N);
     const double tol2 = tol * tol;
+    const double inv_omega = ssor ? 1.0 / omega : 0.0;
     dim3 grid(ntiles, G);
     int32_t* d_active_groups = B.state + (size_t)G * MOF_I_COUNT * MOF_W + 2 * (size_t)G;
     int64_t launches = 0;
@@ -674,8 +698,8 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
             const int t0 = mesh->color_tile_ptr[c], t1 = mesh->color_tile_ptr[c + 1];
             if (t1 <= t0) continue;
             dim3 gs(mof_cdiv(t1 - t0, kWarps), G);
-            if (mode == 0) sweep_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1);
-            else           sweep_back_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1);
+            if (mode == 0) sweep_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1, omega);
+            else           sweep_back_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1, omega);
             ++launches;
         }
     };
@@ -693,12 +717,12 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     // group_done, tickets, groups_active, lanes_active <- 0
     MOF_CUDA_TRY(cudaMemsetAsync(B.state + (size_t)G * MOF_I_COUNT * MOF_W, 0, (2 * (size_t)G + 2) * sizeof(int32_t), st));
     if (!ssor) {
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_JACOBI, tol2, 0);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_JACOBI, tol2, 0, 0, 0.0);
         launches += 1;
     } else {
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_NORM, tol2, 0);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_NORM, tol2, 0, 1, inv_omega);
         sweep_fwd(1, B.rhs, B.r);                                   // r = (Dt+L)^-1 b
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_SSOR, tol2, 0);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_SSOR, tol2, 0, 1, inv_omega);
         launches += 2;
     }
     MOF_LAUNCH_CHECK("pcg start kernels");
@@ -730,14 +754,14 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                     spmv_kernel<true><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, B.p, B.ap, N, nb, ntiles,
                                                            B.partial, B.scal, B.state, G);
                     if (sample) cudaEventRecord(ev[2], st);
-                    update_kernel<false><<<grid, 256, 0, st>>>(B, N, ntiles);
+                    update_kernel<false><<<grid, 256, 0, st>>>(B, N, ntiles, 0.0);
                     launches += 3;
                 } else {
                     sweep_back(0, B.p, B.t);                        // p <- zs z + beta p ; t = (Dt+U)^-1 p
                     if (sample) cudaEventRecord(ev[1], st);
                     sweep_fwd(0, B.p, B.ap);                        // w ; alpha
                     if (sample) cudaEventRecord(ev[2], st);
-                    update_kernel<true><<<grid, 256, 0, st>>>(B, N, ntiles);
+                    update_kernel<true><<<grid, 256, 0, st>>>(B, N, ntiles, inv_omega);
                     launches += 1;
                 }
                 if (sample) cudaEventRecord(ev[3], st);
@@ -761,11 +785,11 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
             }
         }
         // confirm on the true residual b - A x; frames that miss tol resume with a tighter threshold
-        if (ssor) sweep_back(1, B.x, B.t);                           // x = (Dt+U)^-1 xhat
+        if (ssor) sweep_back(1, B.x, B.t);                           // xs = (Dt+U)^-1 xhat (scaled system)
         spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, xphys, B.ap, N, nb, ntiles, nullptr,
                                                 nullptr, nullptr, G);
         const int last_round = (rounds >= max_restarts || it >= max_iter) ? 1 : 0;
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_VERIFY, tol2, last_round);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_VERIFY, tol2, last_round, ssor ? 1 : 0, inv_omega);
         launches += 2;
         MOF_LAUNCH_CHECK("verification kernels");
         MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -773,8 +797,11 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         if (h_active <= 0 || last_round) break;
         ++rounds;
     }
-    if (ssor)   // hand the physical solution back in batch->x (mof_unpack_solution reads it)
-        MOF_CUDA_TRY(cudaMemcpyAsync(B.x, B.t, (size_t)G * N * 2 * MOF_W * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (ssor) {  // hand the solution of the original system back in batch->x (mof_unpack_solution reads it)
+        unscale_kernel<<<grid, 256, 0, st>>>(B, N);
+        MOF_LAUNCH_CHECK("unscale_kernel");
+        launches += 1;
+    }
     if (prof) prof->launches_total += launches;
 
     // per-frame report

@@ -93,7 +93,12 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
         receives = root is None or r == root
         if receives:
             V_host = np.empty((sum(counts), width), dtype=np.float64)
-        drain = cof._solver(op).drain(width)
+        solver = cof._solver(op)
+        drain = solver.drain(width)
+        # several batches per shard so that gather + drain of batch k hide behind the solve of k+1
+        groups = -(-n_loc // 32)
+        saved_groups = solver.batch_groups
+        solver.batch_groups = max(4, min(saved_groups, -(-groups // 4)))
 
         def on_batch(k0, k1, Vd):
             def collect():
@@ -120,6 +125,7 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
         rep = np.zeros((0, 3))
     rep_dev = torch.from_numpy(rep).to(op.device)
     if pipelined:
+        solver.batch_groups = saved_groups
         drain.finish()
         torch.cuda.current_stream(op.device).wait_stream(drain.stream)
         rep_all = gather_rows(rep_dev, counts, root=0 if gather == "root" else None)

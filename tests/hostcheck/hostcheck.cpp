@@ -53,13 +53,8 @@ void hc_assemble(const mof_mesh_dev* M, int32_t G, const double* It, const doubl
                     if (b == M->diag[v]) {
                         mof_assemble_block_body<true>(*M, v, b, It_l, dIt_l, lambda_, a, f);
                         double mi[3];
-                        if (omega == 0.0) {
-                            mof_inv2_body(a, mi);
-                        } else {
-                            mi[0] = a[0] * (1.0 / omega);
-                            mi[1] = 0.5 * (a[1] + a[2]) * (1.0 / omega);
-                            mi[2] = a[3] * (1.0 / omega);
-                        }
+                        if (omega == 0.0) mof_inv2_body(a, mi);
+                        else              mof_inv_sqrt2_body(a, mi);
                         for (int c = 0; c < 2; ++c) rhs[mof_ix_vec(N, g, v, c) + l] = f[c];
                         for (int c = 0; c < 3; ++c) minv[mof_ix_minv(N, g, v, c) + l] = mi[c];
                     } else {
@@ -67,6 +62,22 @@ void hc_assemble(const mof_mesh_dev* M, int32_t G, const double* It, const doubl
                     }
                     for (int c = 0; c < 4; ++c) vals[mof_ix_val(nb, g, b, c) + l] = a[c];
                 }
+            if (omega == 0.0) continue;
+            // scale_kernel: Ah = S A S, bh = S b
+            for (int64_t v = 0; v < N; ++v) {
+                double si[3];
+                for (int c = 0; c < 3; ++c) si[c] = minv[mof_ix_minv(N, g, v, c) + l];
+                double f0 = rhs[mof_ix_vec(N, g, v, 0) + l], f1 = rhs[mof_ix_vec(N, g, v, 1) + l];
+                rhs[mof_ix_vec(N, g, v, 0) + l] = si[0] * f0 + si[1] * f1;
+                rhs[mof_ix_vec(N, g, v, 1) + l] = si[1] * f0 + si[2] * f1;
+                for (int32_t b = M->rowptr[v]; b < M->rowptr[v + 1]; ++b) {
+                    double sj[3], a[4], o[4];
+                    for (int c = 0; c < 3; ++c) sj[c] = minv[mof_ix_minv(N, g, M->col[b], c) + l];
+                    for (int c = 0; c < 4; ++c) a[c] = vals[mof_ix_val(nb, g, b, c) + l];
+                    mof_scale_block_body(si, sj, a, o);
+                    for (int c = 0; c < 4; ++c) vals[mof_ix_val(nb, g, b, c) + l] = o[c];
+                }
+            }
         }
 }
 
@@ -88,32 +99,31 @@ void hc_spmv(const mof_mesh_dev* M, int32_t G, const double* vals, const double*
 }
 
 // SSOR sweeps over tiles [tile0, tile1) of one colour, all groups and lanes (sweep_*_kernel)
-void hc_sweep_back(const mof_mesh_dev* M, int32_t G, const double* vals, const double* dt, const double* z, double* p,
-                   double* t, int32_t tile0, int32_t tile1, const double* beta, const double* zs, int32_t mode) {
+void hc_sweep_back(const mof_mesh_dev* M, int32_t G, const double* vals, const double* r, double* p, double* t,
+                   int32_t tile0, int32_t tile1, const double* beta, const double* zs, double omega, int32_t mode) {
     const int64_t N = M->n_vertices, nb = M->n_blocks;
     for (int64_t g = 0; g < G; ++g)
         for (int l = 0; l < MOF_W; ++l)
             for (int32_t tile = tile0; tile < tile1; ++tile) {
                 int64_t r0 = (int64_t)tile * MOF_TILE_ROWS, r1 = r0 + MOF_TILE_ROWS < N ? r0 + MOF_TILE_ROWS : N;
                 mof_sweep_back_body(M->rowptr, M->col, M->diag, vals + (size_t)g * nb * 4 * MOF_W + l,
-                                    dt + (size_t)g * N * 3 * MOF_W + l, z + (size_t)g * N * 2 * MOF_W + l,
-                                    p + (size_t)g * N * 2 * MOF_W + l, t + (size_t)g * N * 2 * MOF_W + l, r0, r1,
-                                    beta ? beta[g * MOF_W + l] : 0.0, zs ? zs[g * MOF_W + l] : 1.0, mode);
+                                    r + (size_t)g * N * 2 * MOF_W + l, p + (size_t)g * N * 2 * MOF_W + l,
+                                    t + (size_t)g * N * 2 * MOF_W + l, r0, r1, beta ? beta[g * MOF_W + l] : 0.0,
+                                    (zs ? zs[g * MOF_W + l] : 1.0) / omega, omega, mode);
             }
 }
 
 // dot[g][lane] += p'(t+w) over the tiles (mode 0)
-void hc_sweep_fwd(const mof_mesh_dev* M, int32_t G, const double* vals, const double* dt, const double* pin,
-                  const double* t, double* w, int32_t tile0, int32_t tile1, double omega, int32_t mode, double* dot) {
+void hc_sweep_fwd(const mof_mesh_dev* M, int32_t G, const double* vals, const double* pin, const double* t, double* w,
+                  int32_t tile0, int32_t tile1, double omega, int32_t mode, double* dot) {
     const int64_t N = M->n_vertices, nb = M->n_blocks;
     for (int64_t g = 0; g < G; ++g)
         for (int l = 0; l < MOF_W; ++l)
             for (int32_t tile = tile0; tile < tile1; ++tile) {
                 int64_t r0 = (int64_t)tile * MOF_TILE_ROWS, r1 = r0 + MOF_TILE_ROWS < N ? r0 + MOF_TILE_ROWS : N;
                 double d = mof_sweep_fwd_body(M->rowptr, M->col, M->diag, vals + (size_t)g * nb * 4 * MOF_W + l,
-                                              dt + (size_t)g * N * 3 * MOF_W + l, pin + (size_t)g * N * 2 * MOF_W + l,
-                                              t + (size_t)g * N * 2 * MOF_W + l, w + (size_t)g * N * 2 * MOF_W + l, r0, r1,
-                                              omega, mode);
+                                              pin + (size_t)g * N * 2 * MOF_W + l, t + (size_t)g * N * 2 * MOF_W + l,
+                                              w + (size_t)g * N * 2 * MOF_W + l, r0, r1, omega, mode);
                 if (dot) dot[g * MOF_W + l] += d;
             }
 }

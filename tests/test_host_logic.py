@@ -234,53 +234,57 @@ def test_bodies_ssor_eisenstat_pcg_matches_reference(case):
     rows, cols = P.block_rows(), P.col.astype(np.int64)
     cross = tile_of[rows] != tile_of[cols]
     assert np.all(color_of_tile[tile_of[rows[cross]]] != color_of_tile[tile_of[cols[cross]]])
-    vals, rhs, dt = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]), omega)
+    vals0, rhs0, _ = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]), 0.0)       # unscaled system (block-Jacobi layout)
+    vals, rhs, S = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]), omega)       # S A S, S b, S = D^-1/2
     n = len(g["V_k"])
     G = vals.shape[0]
+    # the scaling really is D^-1/2: scaled diagonal blocks are the identity
+    dblk = vals[:, P.diag]                                                       # (G, N, 4, W)
+    assert np.allclose(dblk[:, :, 0, :n % W or W], 1.0, atol=1e-13) and np.allclose(dblk[:, :, 1, :n % W or W], 0.0, atol=1e-13)
     ms = hm.struct()
     ptr = [int(x) for x in P.color_tile_ptr]
     C = P.n_colors
     ref = ctypes.byref(ms)
 
-    def back(mode, z, p, t, beta=None, zs=None):
+    def back(mode, r, p, t, beta=None, zs=None):
         for c in range(C - 1, -1, -1):
-            hc.hc_sweep_back(ref, G, vals.ctypes.data, dt.ctypes.data, z.ctypes.data, p.ctypes.data, t.ctypes.data, ptr[c], ptr[c + 1],
-                             beta.ctypes.data if beta is not None else None, zs.ctypes.data if zs is not None else None, mode)
+            hc.hc_sweep_back(ref, G, vals.ctypes.data, r.ctypes.data, p.ctypes.data, t.ctypes.data, ptr[c], ptr[c + 1],
+                             beta.ctypes.data if beta is not None else None, zs.ctypes.data if zs is not None else None, omega, mode)
 
     def fwd(mode, pin, t, w, dot=None):
         for c in range(C):
-            hc.hc_sweep_fwd(ref, G, vals.ctypes.data, dt.ctypes.data, pin.ctypes.data, t.ctypes.data, w.ctypes.data, ptr[c], ptr[c + 1],
+            hc.hc_sweep_fwd(ref, G, vals.ctypes.data, pin.ctypes.data, t.ctypes.data, w.ctypes.data, ptr[c], ptr[c + 1],
                             omega, mode, dot.ctypes.data if dot is not None else None)
 
-    def apply_dt(r):
-        z = np.empty_like(r)
-        z[:, :, 0] = dt[:, :, 0] * r[:, :, 0] + dt[:, :, 1] * r[:, :, 1]
-        z[:, :, 1] = dt[:, :, 1] * r[:, :, 0] + dt[:, :, 2] * r[:, :, 1]
-        return z
+    def apply_S(v):
+        o = np.empty_like(v)
+        o[:, :, 0] = S[:, :, 0] * v[:, :, 0] + S[:, :, 1] * v[:, :, 1]
+        o[:, :, 1] = S[:, :, 1] * v[:, :, 0] + S[:, :, 2] * v[:, :, 1]
+        return o
 
     lanes = lambda a, b: np.einsum("gvcl,gvcl->gl", a, b)
     t = np.zeros_like(rhs)
     w = np.zeros_like(rhs)
     r = np.zeros_like(rhs)
-    fwd(1, rhs, t, r)                                   # r = (Dt+L)^-1 b
+    fwd(1, rhs, t, r)                                   # r = (Dt+L)^-1 S b
     x = np.zeros_like(rhs)
     p = np.zeros_like(rhs)
-    z = apply_dt(r)
-    rz = lanes(r, z)
-    bb = lanes(r, r)
+    rr = lanes(r, r)
+    rz = rr / omega                                     # z = Dt r = r / omega
+    bb = rr.copy()
     beta = np.zeros((G, W))
     zs = np.ones((G, W))
     active = bb > 0
     iters = 0
     while active.any() and iters < 2000:
-        back(0, z, p, t, beta, zs)                      # p <- zs z + beta p ; t = (Dt+U)^-1 p
+        back(0, r, p, t, beta, zs)                      # p <- zs r/omega + beta p ; t = (Dt+U)^-1 p
         dot = np.zeros((G, W))
         fwd(0, p, t, w, dot)
         alpha = np.where(active, rz / np.where(dot != 0, dot, 1), 0.0)
         x += alpha[:, None, None, :] * p
         r -= alpha[:, None, None, :] * (t + w)
-        z = apply_dt(r)
-        rz_new, rr = lanes(r, z), lanes(r, r)
+        rr = lanes(r, r)
+        rz_new = rr / omega
         conv = active & (rr <= (0.3 * tol) ** 2 * bb)
         beta = np.where(active & ~conv, rz_new / np.where(rz != 0, rz, 1), 1.0)
         zs = np.where(active & ~conv, 1.0, 0.0)
@@ -288,11 +292,12 @@ def test_bodies_ssor_eisenstat_pcg_matches_reference(case):
         active = active & ~conv
         iters += 1
     assert not active.any()
-    xphys = np.zeros_like(rhs)
-    back(1, z, x, xphys)                                # x = (Dt+U)^-1 xhat
+    xs = np.zeros_like(rhs)
+    back(1, r, x, xs)                                   # xs = (Dt+U)^-1 xhat : solution of the scaled system
+    xphys = apply_S(xs)                                 # x = S xs
     for k in range(n):
-        a = _frame_matrix(P, vals, k)
-        b = _frame_vector(P, rhs, k)
+        a = _frame_matrix(P, vals0, k)
+        b = _frame_vector(P, rhs0, k)
         V = _frame_vector(P, xphys, k)
         assert np.linalg.norm(a @ V - b) / np.linalg.norm(b) <= 1e-12
         assert rel_l2(V, g["V_k"][k]) <= 1e-8
