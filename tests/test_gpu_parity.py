@@ -402,3 +402,40 @@ def test_full_size_properties(mods):
         assert np.allclose(lm, lmo, rtol=0, atol=1e-10)
         assert np.array_equal(idx, mof_oracle.face_poincare_index(coords, tris, Vx[k], fio))
     torch.cuda.empty_cache()
+
+
+def test_full_size_phase_config4(mods):
+    """BASELINE.json configs[3]: ~320k-vertex two-component mesh with wrapped-phase input (values in
+    (-pi, pi], ill conditioned: cond ~1e6) -> velocity solve + singularity detection."""
+    cof, fsp = mods
+    if cof.settings["precond"] == "jacobi":
+        pytest.skip("run once, with the default preconditioner")
+    coords, tris, normals, areas = synthetic.two_hemispheres(7)
+    N = len(coords)
+    assert N == 327684
+    T = 4
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.wrapped_phase(coords, t_k, seed=0)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    info = cof.last_solve_info
+    assert info.converged and np.all(info.relres <= RES_TOL)
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    assert abs(a2.tocsr() - a2o).max() <= 1e-13 * abs(a2o).max()
+    # residual of every frame against the oracle-assembled system
+    for k in range(T - 1):
+        a1, f = mof_oracle.assemble_frame(gwo, eo, into, tris, areas, t_k[k + 1] - t_k[k], I[k], I[k + 1])
+        A = mof_oracle.system_matrix(a1, a2o, 0.01)
+        assert np.linalg.norm(A @ V_k[k] - f) / np.linalg.norm(f) <= 1e-11
+    # the reference algorithm's direct solve (SuperLU) for one frame: the parity gate itself
+    from scipy.sparse.linalg import spsolve
+    Vo = spsolve(A, f)
+    worst = rel_l2(V_k[T - 2], Vo)
+    assert worst <= V_TOL, worst
+    # detection: exact index lists against the oracle on the same field
+    Vx = fsp.process_V_k(V_k[:1], e)
+    s = fsp.detect_singularities(Vx, coords, tris, 1e-4)
+    vio, fio, lmo, Po, vmaxo = mof_oracle.find_singularity_points(coords, tris, Vx[0], 1e-4)
+    vi, fi, lm, P, idx = s.frame(0)
+    assert np.array_equal(vi, vio) and np.array_equal(fi, fio) and s.v_length_max[0] == vmaxo
+    assert len(fi) > 100      # wrapped phases create many critical points
