@@ -20,6 +20,7 @@ DEFAULT_PRECOND = "ssor"     # "ssor" (block-multicolour SSOR, Eisenstat form) o
 DEFAULT_OMEGA = 1.4          # SSOR relaxation factor
 DEFAULT_BATCH_GROUPS = 32    # 32 x 32 = 1024 frames per launch (~66 GB at 164k vertices)
 DRAIN_STAGE_ROWS = 256       # rows per pinned staging buffer of the device->host pipeline
+DEFAULT_STREAMS = 2          # concurrent solve streams: one stream's launch tails are filled by the other's kernels
 
 
 @dataclasses.dataclass
@@ -92,7 +93,8 @@ class VelocitySolver:
     """Solves batches of frames on one GPU.  Buffers are allocated once and reused."""
 
     def __init__(self, op, batch_groups=None, tol=DEFAULT_TOL, max_iter=DEFAULT_MAX_ITER,
-                 check_every=DEFAULT_CHECK_EVERY, max_restarts=DEFAULT_MAX_RESTARTS, precond=None, omega=DEFAULT_OMEGA):
+                 check_every=DEFAULT_CHECK_EVERY, max_restarts=DEFAULT_MAX_RESTARTS, precond=None, omega=DEFAULT_OMEGA,
+                 n_streams=DEFAULT_STREAMS):
         self.torch = _lib.require_cuda()
         self.lib = _lib.load()
         self.op = op
@@ -110,7 +112,10 @@ class VelocitySolver:
             per_group = FrameBatch.bytes_per_group(op.n_vertices, op.n_blocks)
             batch_groups = max(1, min(DEFAULT_BATCH_GROUPS, int(0.6 * free) // max(per_group, 1)))
         self.batch_groups = int(batch_groups)
+        self.n_streams = max(1, int(n_streams))
         self._batch = None
+        self._lanes = None           # per-stream (FrameBatch, torch Stream, PcgProfile) of the concurrent path
+        self._pool = None
         self._drain = None
         self.profile = None          # set to _lib.PcgProfile() to accumulate sampled kernel timings
         self.aux_launches = 0        # pack / assemble / unpack launches issued so far
@@ -120,6 +125,67 @@ class VelocitySolver:
             self._batch = None
             self._batch = FrameBatch(self.op, n_groups, with_t=self.precond == "ssor")
         return self._batch
+
+    def _solve_concurrent(self, ranges, lanes, groups_per_batch, I_dev, I2_dev, dt_dev, lambda_, V_dev, on_batch):
+        """Batches are dealt round-robin to ``lanes`` host threads, each with its own CUDA stream and
+        FrameBatch.  Every PCG iteration is a chain of short dependent launches (one per patch
+        colour); with two independent chains in flight the SMs idling in one chain's launch tail run
+        the other chain's CTAs, and one chain's convergence poll never drains the GPU."""
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        torch, op = self.torch, self.op
+        if self._lanes is None or len(self._lanes) < lanes or self._lanes[0][0].n_groups < groups_per_batch:
+            self._lanes = None
+            self._lanes = [(FrameBatch(op, groups_per_batch, with_t=self.precond == "ssor"),
+                            torch.cuda.Stream(device=op.device)) for _ in range(lanes)]
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=self.n_streams)
+        main = torch.cuda.current_stream(op.device)
+        infos = [None] * len(ranges)
+        turn = threading.Condition()
+        next_q = [0]                 # callbacks run in batch order on every rank (they may issue collectives)
+        profiles = [_lib.PcgProfile() if self.profile is not None else None for _ in range(lanes)]
+
+        failed = [False]
+
+        def work(lane):
+            batch, stream = self._lanes[lane]
+            try:
+                with torch.cuda.device(op.device), torch.cuda.stream(stream):
+                    stream.wait_stream(main)
+                    for q in range(lane, len(ranges), lanes):
+                        k0, k1 = ranges[q]
+                        infos[q] = self.solve_batch(I_dev[k0:k1], I2_dev[k0 + 1:k1 + 1], dt_dev[k0:k1], lambda_,
+                                                    V_dev[k0:k1], batch=batch, profile=profiles[lane])
+                        with turn:
+                            turn.wait_for(lambda: next_q[0] == q or failed[0])
+                            if failed[0]:
+                                return stream
+                            if on_batch is not None:
+                                on_batch(k0, k1, V_dev[k0:k1])
+                            next_q[0] = q + 1
+                            turn.notify_all()
+            except BaseException:
+                with turn:
+                    failed[0] = True
+                    turn.notify_all()
+                raise
+            return stream
+
+        futures = [self._pool.submit(work, lane) for lane in range(lanes)]
+        errors = []
+        for f in futures:
+            try:
+                main.wait_stream(f.result())
+            except Exception as exc:            # every worker is joined before re-raising
+                errors.append(exc)
+        if errors:
+            raise errors[0]
+        if self.profile is not None:
+            for p in profiles:
+                for name, _ in _lib.PcgProfile._fields_:
+                    setattr(self.profile, name, getattr(self.profile, name) + getattr(p, name))
+        return infos
 
     def drain(self, width, rows=None):
         """Cached HostDrain with pinned staging buffers of ``rows`` x width doubles."""
@@ -140,12 +206,15 @@ class VelocitySolver:
         _lib.check(lib.mof_assemble_batch(ctypes.byref(ms), ctypes.byref(bs), float(lambda_), self.omega, st))
         return ms, bs
 
-    def solve_batch(self, I_now, I_next, dt, lambda_, V_out):
+    def solve_batch(self, I_now, I_next, dt, lambda_, V_out, batch=None, profile=None):
         """One batch: frames = rows of I_now.  V_out: device (n_frames, 2N) view.  -> SolveInfo"""
         torch, lib, op = self.torch, self.lib, self.op
         n_frames = int(I_now.shape[0])
         G = (n_frames + GROUP - 1) // GROUP
-        batch = self.batch(G)
+        if batch is None:
+            batch = self.batch(G)
+        if profile is None:
+            profile = self.profile
         st = torch.cuda.current_stream(op.device).cuda_stream
         ms, bs = self.assemble(batch, I_now, I_next, dt, lambda_, n_frames)
         iters = np.zeros(G * GROUP, np.int32)
@@ -154,9 +223,9 @@ class VelocitySolver:
         _lib.check(lib.mof_pcg_solve_batch(ctypes.byref(ms), ctypes.byref(bs), float(self.tol), self.omega, int(self.max_iter),
                                            int(self.check_every), int(self.max_restarts), iters.ctypes.data,
                                            relres.ctypes.data, status.ctypes.data,
-                                           ctypes.byref(self.profile) if self.profile is not None else None, st),
+                                           ctypes.byref(profile) if profile is not None else None, st),
                    allow_positive=True)
-        self.aux_launches += 3
+        self.aux_launches += 3 + (1 if self.precond == "ssor" else 0)
         assert V_out.stride(1) == 1
         _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
         return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames])
@@ -171,13 +240,19 @@ class VelocitySolver:
         n = int(dt_dev.shape[0])
         if V_dev is None:
             V_dev = torch.empty((n, 2 * op.n_vertices), dtype=torch.float64, device=op.device)
-        infos = []
-        step = self.batch_groups * GROUP
-        for k0 in range(0, n, step):
-            k1 = min(n, k0 + step)
-            infos.append(self.solve_batch(I_dev[k0:k1], I2_dev[k0 + 1:k1 + 1], dt_dev[k0:k1], lambda_, V_dev[k0:k1]))
-            if on_batch is not None:
-                on_batch(k0, k1, V_dev[k0:k1])
+        groups = -(-n // GROUP)
+        lanes = min(self.n_streams, max(1, groups // 2))          # concurrency only pays with >= 2 groups per stream
+        per = max(1, min(self.batch_groups // lanes, -(-groups // lanes))) if lanes > 1 else self.batch_groups
+        step = per * GROUP
+        ranges = [(k0, min(n, k0 + step)) for k0 in range(0, n, step)]
+        if lanes == 1 or len(ranges) == 1:
+            infos = []
+            for k0, k1 in ranges:
+                infos.append(self.solve_batch(I_dev[k0:k1], I2_dev[k0 + 1:k1 + 1], dt_dev[k0:k1], lambda_, V_dev[k0:k1]))
+                if on_batch is not None:
+                    on_batch(k0, k1, V_dev[k0:k1])
+        else:
+            infos = self._solve_concurrent(ranges, lanes, step // GROUP, I_dev, I2_dev, dt_dev, lambda_, V_dev, on_batch)
         if infos:
             info = SolveInfo(np.concatenate([i.iterations for i in infos]), np.concatenate([i.relres for i in infos]),
                              np.concatenate([i.status for i in infos]))
