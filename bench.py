@@ -351,7 +351,7 @@ def run_b200(args):
 
     # ---- SpMV micro-measurement (BASELINE.json names "SpMV HBM GB/s"): the solver's SpMV kernel on
     # the last assembled batch, K launches back to back
-    batch = solver._batch
+    batch = solver._batch if solver._batch is not None else solver._lanes[0][0]
     ms_, bs_ = op.struct(), batch.struct()
     stream = torch.cuda.current_stream().cuda_stream
     sp0, sp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

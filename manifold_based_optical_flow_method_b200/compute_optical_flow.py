@@ -40,7 +40,8 @@ settings = {
     "max_iter": DEFAULT_MAX_ITER,
     "precond": DEFAULT_PRECOND,    # "ssor": block-multicolour SSOR (Eisenstat form); "jacobi": 2x2 block Jacobi
     "omega": DEFAULT_OMEGA,        # SSOR relaxation factor
-    "batch_groups": None,          # None = sized from free device memory (<= 8 groups of 32 frames)
+    "batch_groups": None,          # None = sized from free device memory (<= 32 groups of 32 frames)
+    "streams": None,               # None = solver default (2 concurrent solve streams)
     "allow_unconverged": False,
     "device": None,                # None = current CUDA device
 }
@@ -73,9 +74,13 @@ def _solver(op):
     precond = settings["precond"] if op.pattern.n_colors > 0 else "jacobi"
     omega = float(settings["omega"])
     s = _solvers.get(key)
-    if s is None or s.op is not op or s.precond != precond or (precond == "ssor" and s.omega != omega):
+    streams = settings["streams"]
+    if s is None or s.op is not op or s.precond != precond or (precond == "ssor" and s.omega != omega) \
+            or (settings["batch_groups"] is not None and s.batch_groups != settings["batch_groups"]) \
+            or (streams is not None and s.n_streams != streams):
         _solvers.clear()           # one mesh at a time keeps device memory bounded
-        s = _solvers[key] = VelocitySolver(op, batch_groups=settings["batch_groups"], precond=precond, omega=omega)
+        kw = {} if streams is None else {"n_streams": streams}
+        s = _solvers[key] = VelocitySolver(op, batch_groups=settings["batch_groups"], precond=precond, omega=omega, **kw)
     s.tol, s.max_iter = settings["tol"], settings["max_iter"]
     return s
 

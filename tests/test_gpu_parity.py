@@ -275,6 +275,33 @@ def test_ragged_frame_counts(n_frames, mods):
         assert rel_l2(V_k[k], Vo) <= V_TOL
 
 
+def test_concurrent_streams_match_single_stream(mods):
+    """Batches dealt to two concurrent solve streams give bit-identical fields to the single-stream
+    path (every frame's arithmetic is private to its lane; reductions are deterministic)."""
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(3)
+    T = 200                           # 199 frames = 7 groups -> 2 streams x batches of 2 groups
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=6)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    out = {}
+    try:
+        for streams in (1, 2):
+            cof.settings["streams"] = streams
+            cof.settings["batch_groups"] = 4
+            V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+            assert cof.last_solve_info.converged and len(cof.last_solve_info.iterations) == T - 1
+            out[streams] = np.asarray(V_k)
+    finally:
+        cof.settings["streams"] = None
+        cof.settings["batch_groups"] = None
+    assert np.array_equal(out[1], out[2])
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    for k in (0, 100, 198):
+        Vo = mof_oracle.worker(k, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[k], I[k + 1])
+        assert rel_l2(out[2][k], Vo) <= V_TOL
+
+
 def test_empty_time_axis(mods):
     cof, _ = mods
     coords, tris, normals, areas = synthetic.icosphere(1)
