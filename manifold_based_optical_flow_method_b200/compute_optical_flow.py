@@ -41,7 +41,7 @@ settings = {
     "precond": DEFAULT_PRECOND,    # "ssor": block-multicolour SSOR (Eisenstat form); "jacobi": 2x2 block Jacobi
     "omega": DEFAULT_OMEGA,        # SSOR relaxation factor
     "batch_groups": None,          # None = sized from free device memory (<= 32 groups of 32 frames)
-    "streams": None,               # None = solver default (2 concurrent solve streams)
+    "streams": None,               # None = solver default (1; 2 = batches on two concurrent streams)
     "allow_unconverged": False,
     "device": None,                # None = current CUDA device
 }

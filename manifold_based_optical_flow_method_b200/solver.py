@@ -20,7 +20,7 @@ DEFAULT_PRECOND = "ssor"     # "ssor" (block-multicolour SSOR, Eisenstat form) o
 DEFAULT_OMEGA = 1.4          # SSOR relaxation factor
 DEFAULT_BATCH_GROUPS = 32    # 32 x 32 = 1024 frames per launch (~66 GB at 164k vertices)
 DRAIN_STAGE_ROWS = 256       # rows per pinned staging buffer of the device->host pipeline
-DEFAULT_STREAMS = 2          # concurrent solve streams: one stream's launch tails are filled by the other's kernels
+DEFAULT_STREAMS = 1          # concurrent solve streams (2 fills launch tails: +2 % measured, but blurs per-kernel timing)
 
 
 @dataclasses.dataclass
