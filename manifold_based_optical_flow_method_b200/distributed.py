@@ -95,10 +95,11 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
             V_host = np.empty((sum(counts), width), dtype=np.float64)
         solver = cof._solver(op)
         drain = solver.drain(width)
-        # several batches per shard so that gather + drain of batch k hide behind the solve of k+1
+        # two batches per shard: gather + drain of the first hide behind the solve of the second
+        # (smaller batches would hide more of the drain but cost more in solve efficiency)
         groups = -(-n_loc // 32)
         saved_groups = solver.batch_groups
-        solver.batch_groups = max(4, min(saved_groups, -(-groups // 4)))
+        solver.batch_groups = max(8, min(saved_groups, -(-groups // 2)))
 
         def on_batch(k0, k1, Vd):
             def collect():
