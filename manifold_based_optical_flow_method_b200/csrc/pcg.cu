@@ -1,13 +1,14 @@
-// K2/K3 -- batched fp64 conjugate gradients with 2x2 block-Jacobi preconditioning.
+// K2/K3 -- batched fp64 preconditioned conjugate gradients, two preconditioners, one driver.
 // Replaces scipy.sparse.linalg.spsolve (SuperLU) in worker,
 // utils/compute_optical_flow.py:147, for a whole batch of frames at once.
 //
 // Layout and mapping.  The matrix of every frame shares one block pattern (rowptr/col over
 // the renumbered vertex adjacency).  Values and vectors are frame-minor,
-// [group][slot][32 frames]: a warp works on one block row, lane = frame, so each value /
+// [group][slot][32 frames]: a warp works on block rows, lane = frame, so each value /
 // vector access of a warp is one 256-byte line and the column index is read once for 32
-// frames.  A CTA (8 warps) owns a tile of MOF_TILE_ROWS consecutive rows; grid = (tiles,
-// groups).
+// frames.  Vector kernels and the SpMV: a CTA (8 warps) owns a tile of MOF_TILE_ROWS
+// consecutive rows, grid = (tiles, groups).  SSOR sweeps: a warp owns one patch (= tile) of
+// the launch's colour and walks its rows in sequence, 8 patches per CTA.
 //
 // Reductions.  Dot products are private to a lane (a frame) while a warp walks its rows;
 // the 8 warps of a CTA are combined through shared memory in warp order, the per-tile
@@ -16,15 +17,19 @@
 // bit-reproducible and independent of how frames are batched or sharded over GPUs.
 // That last CTA also does the scalar step (alpha, beta, convergence test per frame).
 //
-// Per iteration: spmv_kernel (ap = A p, p'Ap, alpha), update_kernel (x += alpha p,
-// r -= alpha ap, z = Minv r, r'z, r'r, beta, convergence), pupdate_kernel (p = z + beta p).
-// Converged frames get alpha = beta = 0 (frozen); a group whose frames are all done makes
-// its CTAs return at once.
-//
-// HBM bytes per frame-iteration at N vertices, nb blocks:
-//   spmv   : 32 nb (values) + 16 N (p, gathered through L2) + 16 N (ap)   [+ 4 nb/32 indices]
-//   update : read p, ap, x, r (64 N) + minv (24 N), write x, r, z (48 N)
-//   pupdate: read z, p (32 N), write p (16 N)
+// omega = 0, block Jacobi (the north-star design), per iteration:
+//   pupdate_kernel (p = zs z + beta p), spmv_kernel (ap = A p, p'Ap, alpha),
+//   update_kernel<false> (x += alpha p, r -= alpha ap, z = D^-1 r, r'z, r'r, beta, convergence).
+//   HBM bytes per frame-iteration: spmv 32 nb + 32 N, update 136 N, pupdate 48 N  (72.1 MB at ico7)
+// omega in (0,2), block-multicolour SSOR in Eisenstat's form on the D^-1/2-scaled system
+// (identity diagonal blocks, see mof_bodies.h), per iteration:
+//   sweep_back_kernel<0> per colour, last colour first (p = zs r/omega + beta p fused; t = (Dt+U)^-1 p),
+//   sweep_fwd_kernel<0> per colour (w = (Dt+L)^-1 (p - ((2-omega)/omega) t); p'(t+w); alpha),
+//   update_kernel<true> (x += alpha p, r -= alpha (t+w), r'r, beta, convergence).
+//   HBM bytes per frame-iteration: sweeps 2 x 16 (nb-N) + 112 N, update 112 N  (68.1 MB at ico7),
+//   ~3.1x fewer iterations than block Jacobi.
+// A frame that meets its threshold is frozen with (alpha, beta, zs) = (0, 1, 0) and can resume
+// exactly; a group whose frames are all frozen makes its CTAs return at once.
 #include <math.h>
 
 #include "mof_common.cuh"
