@@ -317,51 +317,71 @@ __device__ __forceinline__ void prefetch_block_l2(const double* __restrict__ val
     for (int c = 0; c < 4; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c * MOF_W));
 }
 
-// Off-diagonal part of one row of a sweep: acc -= sum_k A_k v[col_k] over blocks [bs, be).
-// All loads of up to four blocks are issued before the first use so that one memory round trip
-// serves the row (the matrix values are independent of the sweep's recurrence; only the gathered
-// v values may have been written by this thread a few rows earlier, hence plain loads for them).
-__device__ __forceinline__ void sweep_row_offdiag(const int32_t* __restrict__ col, const double* __restrict__ vals_l,
-                                                  const double* v_l, int32_t bs, int32_t be, double& a0, double& a1) {
-    for (int32_t base = bs; base < be; base += 4) {
-        const int cnt = be - base;                      // > 0; only the first four are handled per pass
-        int64_t j[4];
-        double a[4][4], v[4][2];
+// What a sweep knows about a row one step before it is processed: its block range, the first
+// four column indices and the row's entries of the two streamed vectors.  Loading these one row
+// ahead takes the DRAM latency of the streamed vectors and the index latency off the per-row
+// critical path (ncu: 32 % of the stall samples sat on the first use of r/p, 8 % on the indices).
+struct RowPre {
+    int32_t bs, be;
+    int32_t c[4];
+    double s[4];
+};
+
+// Off-diagonal part of one row of a sweep: acc -= sum_k A_k v[col_k] over blocks [bs, be), in two
+// steps so that the caller can put independent work (the next row's loads, L2 prefetches) between
+// issuing the loads and consuming them.  All loads of up to four blocks are issued before the
+// first use: one memory round trip serves the row (the matrix values are independent of the
+// sweep's recurrence; only the gathered v values may have been written by this thread a few rows
+// earlier, hence plain loads for them).
+struct RowBatch {
+    double a[4][4], v[4][2];
+};
+
+__device__ __forceinline__ void sweep_row_issue(const double* __restrict__ vals_l, const double* v_l, const RowPre& R,
+                                                RowBatch& Bt) {
+    const int cnt = R.be - R.bs;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < cnt) {
-                j[k] = col[base + k];
-                const double* ap = vals_l + (size_t)(base + k) * 4 * MOF_W;
-                a[k][0] = __ldcs(ap);
-                a[k][1] = __ldcs(ap + MOF_W);
-                a[k][2] = __ldcs(ap + 2 * MOF_W);
-                a[k][3] = __ldcs(ap + 3 * MOF_W);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < cnt) {
-                v[k][0] = v_l[(size_t)(2 * j[k]) * MOF_W];
-                v[k][1] = v_l[(size_t)(2 * j[k] + 1) * MOF_W];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < cnt) {
-                a0 -= a[k][0] * v[k][0] + a[k][1] * v[k][1];
-                a1 -= a[k][2] * v[k][0] + a[k][3] * v[k][1];
-            }
+    for (int k = 0; k < 4; ++k) {
+        if (k < cnt) {
+            const double* ap = vals_l + (size_t)(R.bs + k) * 4 * MOF_W;
+            Bt.a[k][0] = __ldcs(ap);
+            Bt.a[k][1] = __ldcs(ap + MOF_W);
+            Bt.a[k][2] = __ldcs(ap + 2 * MOF_W);
+            Bt.a[k][3] = __ldcs(ap + 3 * MOF_W);
+            Bt.v[k][0] = v_l[(size_t)(2 * (int64_t)R.c[k]) * MOF_W];
+            Bt.v[k][1] = v_l[(size_t)(2 * (int64_t)R.c[k] + 1) * MOF_W];
         }
     }
 }
 
+__device__ __forceinline__ void sweep_row_consume(const int32_t* __restrict__ col, const double* __restrict__ vals_l,
+                                                  const double* v_l, const RowPre& R, const RowBatch& Bt, double& a0,
+                                                  double& a1) {
+    const int cnt = R.be - R.bs;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < cnt) {
+            a0 -= Bt.a[k][0] * Bt.v[k][0] + Bt.a[k][1] * Bt.v[k][1];
+            a1 -= Bt.a[k][2] * Bt.v[k][0] + Bt.a[k][3] * Bt.v[k][1];
+        }
+    }
+    for (int32_t b = R.bs + 4; b < R.be; ++b) {            // rows with more than four blocks in this half (rare)
+        const int64_t j = col[b];
+        const double* ap = vals_l + (size_t)b * 4 * MOF_W;
+        const double v0 = v_l[(size_t)(2 * j) * MOF_W], v1 = v_l[(size_t)(2 * j + 1) * MOF_W];
+        a0 -= __ldcs(ap) * v0 + __ldcs(ap + MOF_W) * v1;
+        a1 -= __ldcs(ap + 2 * MOF_W) * v0 + __ldcs(ap + 3 * MOF_W) * v1;
+    }
+}
+
 // MODE 0: iteration (p <- zs z + beta p fused in, t = (Dt+U)^-1 p).  MODE 1: t = (Dt+U)^-1 pvec.
-// Same arithmetic as mof_sweep_back_body (mof_bodies.h), with the loads of a row batched.
+// Same arithmetic as mof_sweep_back_body (mof_bodies.h), with the loads of a row batched and the
+// next row's streamed data fetched one row ahead.
 template <int MODE>
-__global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                         const int32_t* __restrict__ diag, mof_batch_dev B, double* pvec,
-                                                         double* tout, int64_t N, int64_t nb, int tile0, int tile1,
-                                                         double omega) {
+__global__ void __launch_bounds__(256, 2) sweep_back_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                            const int32_t* __restrict__ diag, mof_batch_dev B, double* pvec,
+                                                            double* tout, int64_t N, int64_t nb, int tile0, int tile1,
+                                                            double omega) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     if (MODE == 0 && group_done_ptr(B.state, G)[g]) return;
@@ -370,6 +390,7 @@ __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restri
     if (tile >= tile1) return;
     const int64_t r0 = (int64_t)tile * MOF_TILE_ROWS;
     const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
+    const int nrows = (int)(r1 - r0);
     double beta = 0.0, zsw = 0.0;
     if (MODE == 0) {
         beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
@@ -383,36 +404,54 @@ __global__ void __launch_bounds__(256) sweep_back_kernel(const int32_t* __restri
     int32_t rp_lo = 0, rp_hi = 0, dg_lo = 0, dg_hi = 0;
     if (r0 + lane < r1) { rp_lo = rowptr[r0 + lane + 1]; dg_lo = diag[r0 + lane]; }
     if (r0 + 32 + lane < r1) { rp_hi = rowptr[r0 + 32 + lane + 1]; dg_hi = diag[r0 + 32 + lane]; }
-    for (int64_t i = r1 - 1; i >= r0; --i) {
-        const int q = (int)(i - r0);
-        const int32_t be = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
-        const int32_t bs = (q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32)) + 1;
-        double a0 = p_l[(size_t)(2 * i) * MOF_W], a1 = p_l[(size_t)(2 * i + 1) * MOF_W];
+    auto load_row = [&](int q, RowPre& R) {
+        R.be = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
+        R.bs = (q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32)) + 1;
+        const size_t i = (size_t)(r0 + q);
+        R.s[0] = p_l[(2 * i) * MOF_W];
+        R.s[1] = p_l[(2 * i + 1) * MOF_W];
         if (MODE == 0) {
-            a0 = zsw * r_l[(size_t)(2 * i) * MOF_W] + beta * a0;
-            a1 = zsw * r_l[(size_t)(2 * i + 1) * MOF_W] + beta * a1;
-            p_l[(size_t)(2 * i) * MOF_W] = a0;
-            p_l[(size_t)(2 * i + 1) * MOF_W] = a1;
+            R.s[2] = r_l[(2 * i) * MOF_W];
+            R.s[3] = r_l[(2 * i + 1) * MOF_W];
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (R.bs + k < R.be) R.c[k] = col[R.bs + k];
+    };
+    RowPre cur, nxt;
+    load_row(nrows - 1, cur);
+    for (int q = nrows - 1; q >= 0; --q) {
+        const size_t i = (size_t)(r0 + q);
+        RowBatch bt;
+        sweep_row_issue(vals_l, t_l, cur, bt);                      // this row's matrix values and gathered t
+        if (q > 0) load_row(q - 1, nxt);
         if (q >= kPrefetchRows) {                                   // matrix values of a row a few steps ahead -> L2
             const int qq = q - kPrefetchRows;
             const int32_t pe = qq < 32 ? __shfl_sync(kFull, rp_lo, qq) : __shfl_sync(kFull, rp_hi, qq - 32);
             const int32_t ps = (qq < 32 ? __shfl_sync(kFull, dg_lo, qq) : __shfl_sync(kFull, dg_hi, qq - 32)) + 1;
             for (int32_t b = ps; b < pe; ++b) prefetch_block_l2(vals_l, b);
         }
-        sweep_row_offdiag(col, vals_l, t_l, bs, be, a0, a1);
-        t_l[(size_t)(2 * i) * MOF_W] = omega * a0;
-        t_l[(size_t)(2 * i + 1) * MOF_W] = omega * a1;
+        double a0 = cur.s[0], a1 = cur.s[1];
+        if (MODE == 0) {
+            a0 = zsw * cur.s[2] + beta * a0;
+            a1 = zsw * cur.s[3] + beta * a1;
+            p_l[(2 * i) * MOF_W] = a0;
+            p_l[(2 * i + 1) * MOF_W] = a1;
+        }
+        sweep_row_consume(col, vals_l, t_l, cur, bt, a0, a1);
+        t_l[(2 * i) * MOF_W] = omega * a0;
+        t_l[(2 * i + 1) * MOF_W] = omega * a1;
+        cur = nxt;
     }
 }
 
-// MODE 0: iteration (w = (Dt+L)^-1 (p - (2-omega) Dt t), p'(t+w) -> alpha in the last CTA of the
+// MODE 0: iteration (w = (Dt+L)^-1 (p - ((2-omega)/omega) t), p'(t+w) -> alpha in the last CTA of the
 // last colour).  MODE 1: wout = (Dt+L)^-1 pin.  Same arithmetic as mof_sweep_fwd_body.
 template <int MODE>
-__global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                        const int32_t* __restrict__ diag, mof_batch_dev B, const double* pin,
-                                                        double* wout, int64_t N, int64_t nb, int tile0, int tile1,
-                                                        int ntiles, double omega) {
+__global__ void __launch_bounds__(256, 2) sweep_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                           const int32_t* __restrict__ diag, mof_batch_dev B, const double* pin,
+                                                           double* wout, int64_t N, int64_t nb, int tile0, int tile1,
+                                                           int ntiles, double omega) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     if (MODE == 0 && group_done_ptr(B.state, G)[g]) return;
@@ -423,6 +462,7 @@ __global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restric
     if (valid) {
         const int64_t r0 = (int64_t)tile * MOF_TILE_ROWS;
         const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
+        const int nrows = (int)(r1 - r0);
         const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
         const double* __restrict__ p_l = pin + (size_t)g * N * 2 * MOF_W + lane;
         const double* __restrict__ t_l = B.t + (size_t)g * N * 2 * MOF_W + lane;
@@ -431,29 +471,47 @@ __global__ void __launch_bounds__(256) sweep_fwd_kernel(const int32_t* __restric
         if (r0 + lane < r1) { rp_lo = rowptr[r0 + lane]; dg_lo = diag[r0 + lane]; }
         if (r0 + 32 + lane < r1) { rp_hi = rowptr[r0 + 32 + lane]; dg_hi = diag[r0 + 32 + lane]; }
         const double kscale = (2.0 - omega) / omega;
-        for (int64_t i = r0; i < r1; ++i) {
-            const int q = (int)(i - r0);
-            const int32_t bs = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
-            const int32_t be = q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32);
-            const double p0 = p_l[(size_t)(2 * i) * MOF_W], p1 = p_l[(size_t)(2 * i + 1) * MOF_W];
-            double a0 = p0, a1 = p1, t0 = 0.0, t1 = 0.0;
+        auto load_row = [&](int q, RowPre& R) {
+            R.bs = q < 32 ? __shfl_sync(kFull, rp_lo, q) : __shfl_sync(kFull, rp_hi, q - 32);
+            R.be = q < 32 ? __shfl_sync(kFull, dg_lo, q) : __shfl_sync(kFull, dg_hi, q - 32);
+            const size_t i = (size_t)(r0 + q);
+            R.s[0] = p_l[(2 * i) * MOF_W];
+            R.s[1] = p_l[(2 * i + 1) * MOF_W];
             if (MODE == 0) {
-                t0 = t_l[(size_t)(2 * i) * MOF_W];
-                t1 = t_l[(size_t)(2 * i + 1) * MOF_W];
-                a0 -= kscale * t0;
-                a1 -= kscale * t1;
+                R.s[2] = t_l[(2 * i) * MOF_W];
+                R.s[3] = t_l[(2 * i + 1) * MOF_W];
             }
-            if (q + kPrefetchRows < (int)(r1 - r0)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (R.bs + k < R.be) R.c[k] = col[R.bs + k];
+        };
+        RowPre cur, nxt;
+        load_row(0, cur);
+        for (int q = 0; q < nrows; ++q) {
+            const size_t i = (size_t)(r0 + q);
+            RowBatch bt;
+            sweep_row_issue(vals_l, w_l, cur, bt);                  // this row's matrix values and gathered w
+            if (q + 1 < nrows) load_row(q + 1, nxt);
+            if (q + kPrefetchRows < nrows) {
                 const int qq = q + kPrefetchRows;
                 const int32_t ps = qq < 32 ? __shfl_sync(kFull, rp_lo, qq) : __shfl_sync(kFull, rp_hi, qq - 32);
                 const int32_t pe = qq < 32 ? __shfl_sync(kFull, dg_lo, qq) : __shfl_sync(kFull, dg_hi, qq - 32);
                 for (int32_t b = ps; b < pe; ++b) prefetch_block_l2(vals_l, b);
             }
-            sweep_row_offdiag(col, vals_l, w_l, bs, be, a0, a1);
+            const double p0 = cur.s[0], p1 = cur.s[1];
+            double a0 = p0, a1 = p1, t0 = 0.0, t1 = 0.0;
+            if (MODE == 0) {
+                t0 = cur.s[2];
+                t1 = cur.s[3];
+                a0 -= kscale * t0;
+                a1 -= kscale * t1;
+            }
+            sweep_row_consume(col, vals_l, w_l, cur, bt, a0, a1);
             const double o0 = omega * a0, o1 = omega * a1;
-            w_l[(size_t)(2 * i) * MOF_W] = o0;
-            w_l[(size_t)(2 * i + 1) * MOF_W] = o1;
+            w_l[(2 * i) * MOF_W] = o0;
+            w_l[(2 * i + 1) * MOF_W] = o1;
             if (MODE == 0) dot += p0 * (t0 + o0) + p1 * (t1 + o1);
+            cur = nxt;
         }
     }
     if (MODE != 0) return;
