@@ -255,6 +255,17 @@ int mof_singularity_compact(int64_t n_vertices, int64_t n_faces, int64_t n_frame
 int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_frames, const double* I, int64_t ld, double dt,
                    int phase_mode, double* grad_point, double* wave, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * On-disk formats either side of the path ("next" row 4 of SURVEY 8f), host only, multi-threaded.
+ * The pandas CSV dialect of load_potentials (pd.read_csv(..., header='infer', index_col=0),
+ * compute_optical_flow.py:203-207) and reshape_and_save_data (pd.DataFrame(a).to_csv(path),
+ * :314-320): header ",0,1,...", rows "r,v0,v1,...", doubles printed like Python's repr (shortest
+ * round trip), NaN as an empty field.  n_threads <= 0: all hardware threads.
+ * ------------------------------------------------------------------------- */
+int mof_csv_write(const char* path, const double* data, int64_t rows, int64_t cols, int n_threads);
+int mof_csv_dims(const char* path, int64_t* rows, int64_t* cols);    /* data rows, value columns */
+int mof_csv_read(const char* path, double* data, int64_t rows, int64_t cols, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

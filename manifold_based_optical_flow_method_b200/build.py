@@ -13,12 +13,12 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(CSRC, "libmof_b200.so")
 
-SOURCES = ["error.cpp", "pattern.cpp", "geom.cu", "assemble.cu", "pcg.cu", "detect.cu", "wave.cu"]
+SOURCES = ["error.cpp", "pattern.cpp", "csvio.cpp", "geom.cu", "assemble.cu", "pcg.cu", "detect.cu", "wave.cu"]
 HEADERS = ["mof_error.h", "mof_bodies.h", "mof_common.cuh", os.path.join(INCLUDE, "mof_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "--cudart", "static",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-pthread", "-shared", "--cudart", "static",
 ]
 
 

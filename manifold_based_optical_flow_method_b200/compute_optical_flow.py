@@ -179,18 +179,27 @@ def worker(k, a2, grad_w, e, integral_wi_wj, triangles, t_k, areas, lambda_, I_k
 
 
 def reshape_and_save_data(data, file_path):
-    """Reference :314-320 (same CSV layout: pandas DataFrame.to_csv of data.reshape(n, -1))."""
-    import pandas as pd
+    """Reference :314-320: pd.DataFrame(data.reshape(n, -1)).to_csv(file_path).  Same bytes on disk
+    (header ",0,1,...", Python-repr floats), written by the multi-threaded C++ writer of
+    libmof_b200 (csrc/csvio.cpp): a (999, 327684) field file is 6.5 GB of text."""
+    import ctypes
     if isinstance(data, list):
         data = np.array(data)
-    reshaped_data = data.reshape(data.shape[0], -1)
-    pd.DataFrame(reshaped_data).to_csv(file_path)
+    reshaped = np.ascontiguousarray(np.asarray(data).reshape(np.asarray(data).shape[0], -1), dtype=np.float64)
+    _lib.check(_lib.load().mof_csv_write(str(file_path).encode(), reshaped.ctypes.data, reshaped.shape[0],
+                                         reshaped.shape[1], 0))
 
 
 def load_potentials(csv_path):
-    """Reference :203-207."""
-    import pandas as pd
-    return pd.read_csv(csv_path, sep=',', header='infer', index_col=0).values
+    """Reference :203-207: pd.read_csv(csv_path, sep=',', header='infer', index_col=0).values, read by
+    the multi-threaded C++ parser (correctly rounded doubles = pandas float_precision='round_trip')."""
+    import ctypes
+    lib = _lib.load()
+    rows, cols = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(lib.mof_csv_dims(str(csv_path).encode(), ctypes.byref(rows), ctypes.byref(cols)))
+    out = np.empty((rows.value, cols.value), dtype=np.float64)
+    _lib.check(lib.mof_csv_read(str(csv_path).encode(), out.ctypes.data, rows.value, cols.value, 0))
+    return out
 
 
 __all__ = ["compute_geometrical_quantities", "compute_velocity_field", "worker", "reshape_and_save_data",
