@@ -16,7 +16,7 @@ boundary, as produced by S1_reconstruct_surface.py:85-98).
 import numpy as np
 
 __all__ = [
-    "icosphere", "pial_like", "two_hemispheres", "open_patch",
+    "icosphere", "pial_like", "two_hemispheres", "open_patch", "fan_mesh",
     "vertex_normals", "face_areas", "travelling_wave", "wrapped_phase",
     "time_axis", "mesh_for_config",
 ]
@@ -153,6 +153,30 @@ def open_patch(n=12, seed=0, size=10.0):
                 tris += [[a, b, c], [a, c, d]]
             else:
                 tris += [[a, b, d], [b, c, d]]
+    return _finish(v, np.array(tris, dtype=np.int64))
+
+
+def fan_mesh(n_rim=40, n_rings=3, seed=0):
+    """Open cap with one vertex of valence ``n_rim`` (> 32: a block row longer than a warp) surrounded
+    by ``n_rings`` rings of ``n_rim`` vertices each; gently curved and jittered."""
+    rng = np.random.default_rng(seed)
+    pts = [[0.0, 0.0, 0.0]]
+    for r in range(1, n_rings + 1):
+        ang = 2 * np.pi * (np.arange(n_rim) + 0.5 * (r % 2)) / n_rim
+        rad = r * (1.0 + 0.05 * rng.uniform(-1, 1, n_rim))
+        pts += [[rad[k] * np.cos(ang[k]), rad[k] * np.sin(ang[k]), -0.05 * rad[k] ** 2] for k in range(n_rim)]
+    v = np.array(pts)
+    ring = lambda r, k: 1 + (r - 1) * n_rim + (k % n_rim)
+    tris = [[0, ring(1, k), ring(1, k + 1)] for k in range(n_rim)]
+    for r in range(1, n_rings):
+        for k in range(n_rim):
+            a, b = ring(r, k), ring(r, k + 1)
+            if r % 2 == 1:
+                c, d = ring(r + 1, k), ring(r + 1, k + 1)
+                tris += [[a, c, b], [b, c, d]]
+            else:
+                c, d = ring(r + 1, k - 1), ring(r + 1, k)
+                tris += [[a, c, d], [a, d, b]]
     return _finish(v, np.array(tris, dtype=np.int64))
 
 

@@ -217,7 +217,7 @@ def test_singular_vertices_and_face_skip(mods):
 # ---------------------------------------------------------------------------------
 # oracle on seeded inputs (sizes the oracle finishes in seconds)
 # ---------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["C1_wave", "patch_wave", "two_phase"])
+@pytest.mark.parametrize("case", ["C1_wave", "patch_wave", "two_phase", "fan_wave"])
 def test_velocity_field_matches_oracle(case, mods):
     cof, fsp = mods
     if case == "C1_wave":          # BASELINE.json configs[0] mesh (ico5, 10,242 vertices)
@@ -226,6 +226,9 @@ def test_velocity_field_matches_oracle(case, mods):
     elif case == "patch_wave":     # open surface with boundary, irregular valence
         coords, tris, normals, areas = synthetic.open_patch(40, seed=2)
         T, SF, kind = 36, 256.0, "wave"      # 35 frames: one full group + 3 ragged lanes
+    elif case == "fan_wave":       # a vertex of valence 40: block rows longer than a warp / than a load batch
+        coords, tris, normals, areas = synthetic.fan_mesh(40, 3)
+        T, SF, kind = 5, 512.0, "wave"
     else:                          # two components + wrapped-phase input (config 4 style)
         coords, tris, normals, areas = synthetic.two_hemispheres(4, radius=80.0)
         T, SF, kind = 4, 512.0, "phase"
