@@ -268,7 +268,7 @@ class HostDrain:
     and a worker thread moves them into the caller's (pageable) numpy array.  The solver's
     host thread sits inside libmof_b200 (GIL released) meanwhile."""
 
-    def __init__(self, torch, device, max_rows, width, n_stages=3, copy_threads=4):
+    def __init__(self, torch, device, max_rows, width, n_stages=4, copy_threads=None):
         import queue
         import threading
         from concurrent.futures import ThreadPoolExecutor
@@ -280,6 +280,9 @@ class HostDrain:
             f.set()
         self.stream = torch.cuda.Stream(device=device)
         self.queue = queue.Queue()
+        if copy_threads is None:          # staging -> destination memcpy is the slow half of the drain
+            import os
+            copy_threads = max(4, min(12, (os.cpu_count() or 8) - 2))
         self.pool = ThreadPoolExecutor(copy_threads)
         self.copy_threads = copy_threads
         self.count = 0
