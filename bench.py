@@ -372,6 +372,31 @@ def run_b200(args):
                         "note": "mof_spmv_batch (block-CSR, frame-minor) on the assembled batch; in-solver use: "
                                 + ("every iteration" if solver.precond == "jacobi" else "true-residual verification")}
 
+    # ---- detection (K4 + K5), reported separately from the solve: tangent -> xyz, vmax,
+    # singular vertices / faces with ordered compaction, on the fields of the last step
+    detection = None
+    try:
+        from manifold_based_optical_flow_method_b200 import find_singularity_point as fsp
+        nd = min(n, 256)
+        e_dev = torch.from_numpy(np.ascontiguousarray(e)).to(dev)
+        coords_dev = torch.from_numpy(np.ascontiguousarray(coords)).to(dev)
+        tri_dev = torch.from_numpy(np.ascontiguousarray(tris, dtype=np.int32)).to(dev)
+        for rep in range(2):                       # first pass warms up
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            Vxyz, speed, vmax = fsp.tangent_to_xyz_device(V_dev[:nd], e_dev)
+            sing = fsp.detect_singularities_device(coords_dev, tri_dev, Vxyz, 1e-4, vmax)
+            d1.record()
+            torch.cuda.synchronize()
+        det_ms = d0.elapsed_time(d1)
+        detection = {"frames_per_s": nd / (det_ms * 1e-3), "frames": nd, "ms": det_ms,
+                     "critical_points_per_frame": float(len(sing.face_idx) + len(sing.vertex_idx)) / nd,
+                     "note": "process_V_k + speed + vmax (K4) and find_singularity_points (K5) on device-resident fields, "
+                             "including the host read of the per-frame counts"}
+        del Vxyz, speed, vmax, sing
+    except Exception as exc:                        # detection timing is auxiliary: never fail the bench line on it
+        detection = {"error": repr(exc)}
+
     # ---- end-to-end leg: host buffers in, host buffers out, through the reference-shaped API
     e2e = None
     if not args.no_e2e:
@@ -411,6 +436,7 @@ def run_b200(args):
                        "l2": "no flush: the per-step working set (1.17 GB of matrix values per 32-frame group) is >> 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), one process per GPU"},
             "clocks": clock_report, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "detection": detection,
             "solver": {"converged": converged, "iterations_mean": float(np.mean(info.iterations)),
                        "iterations_max": int(np.max(info.iterations)), "relres_max": float(np.max(info.relres)),
                        "geometry_seconds": geom_s, "setup_seconds": time.time() - t0},
