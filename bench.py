@@ -322,11 +322,11 @@ def run_b200(args):
         traffic_val = traffic["dram_bytes_per_frame_launch"] * fl / smp if traffic else None
     else:
         # (system scaled to identity diagonal blocks: no per-vertex matrix data in the iteration)
-        # backward sweeps: U blocks 16 (nb-N) + read r, p + write p, t (64 N)
+        # backward sweeps: U blocks 16 (nb-N) + read r, p, x + write p, t, x (96 N)
         # forward  sweeps: L blocks 16 (nb-N) + read p, t + write w (48 N)
-        # update         : read p, w, t, x, r (80 N), write x, r (32 N)
-        per_frame = {"sweep_back": 16.0 * (nb - N) + 64.0 * N, "sweep_fwd": 16.0 * (nb - N) + 48.0 * N,
-                     "update": 112.0 * N}
+        # update         : read w, t, r (48 N), write r (16 N)
+        per_frame = {"sweep_back": 16.0 * (nb - N) + 96.0 * N, "sweep_fwd": 16.0 * (nb - N) + 48.0 * N,
+                     "update": 64.0 * N}
         dom_name = "sweep_back_kernel<0> + sweep_fwd_kernel<0> (Eisenstat SSOR operator, all colours of one iteration)"
         dom_bytes = fl * (per_frame["sweep_back"] + per_frame["sweep_fwd"]) + 2 * idx_bytes
         dom_ms = prof.ms_spmv + prof.ms_pupdate

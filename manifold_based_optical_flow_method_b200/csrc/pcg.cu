@@ -23,10 +23,11 @@
 //   HBM bytes per frame-iteration: spmv 32 nb + 32 N, update 136 N, pupdate 48 N  (72.1 MB at ico7)
 // omega in (0,2), block-multicolour SSOR in Eisenstat's form on the D^-1/2-scaled system
 // (identity diagonal blocks, see mof_bodies.h), per iteration:
-//   sweep_back_kernel<0> per colour, last colour first (p = zs r/omega + beta p fused; t = (Dt+U)^-1 p),
+//   sweep_back_kernel<0> per colour, last colour first (x += alpha p of the previous step and
+//                        p = zs r/omega + beta p fused; t = (Dt+U)^-1 p),
 //   sweep_fwd_kernel<0> per colour (w = (Dt+L)^-1 (p - ((2-omega)/omega) t); p'(t+w); alpha),
-//   update_kernel<true> (x += alpha p, r -= alpha (t+w), r'r, beta, convergence).
-//   HBM bytes per frame-iteration: sweeps 2 x 16 (nb-N) + 112 N, update 112 N  (68.1 MB at ico7),
+//   update_kernel<true> (r -= alpha (t+w), r'r, beta, convergence).
+//   HBM bytes per frame-iteration: sweeps 2 x 16 (nb-N) + 144 N, update 64 N  (65.5 MB at ico7),
 //   ~3.1x fewer iterations than block Jacobi.
 // A frame that meets its threshold is frozen with (alpha, beta, zs) = (0, 1, 0) and can resume
 // exactly; a group whose frames are all frozen makes its CTAs return at once.
@@ -221,16 +222,15 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
         const int64_t v = row0 + q;
         if (v >= N) break;
         const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
-        const double p0 = B.p[i0], p1 = B.p[i1];
         double a0 = __ldcs(B.ap + i0), a1 = __ldcs(B.ap + i1);
         if (SSOR) { a0 += __ldcs(B.t + i0); a1 += __ldcs(B.t + i1); }
-        double x0 = B.x[i0], x1 = B.x[i1];
         double r0 = B.r[i0], r1 = B.r[i1];
-        x0 = fma(alpha, p0, x0);
-        x1 = fma(alpha, p1, x1);
+        if (!SSOR) {                                   // SSOR: x += alpha p is folded into the next backward sweep
+            B.x[i0] = fma(alpha, B.p[i0], B.x[i0]);
+            B.x[i1] = fma(alpha, B.p[i1], B.x[i1]);
+        }
         r0 = fma(-alpha, a0, r0);
         r1 = fma(-alpha, a1, r1);
-        B.x[i0] = x0; B.x[i1] = x1;
         B.r[i0] = r0; B.r[i1] = r1;
         if (!SSOR) {                                   // z = D^-1 r ; SSOR: z = r / omega is never stored
             const size_t im = mof_ix_minv(N, g, v, 0) + lane;
@@ -324,7 +324,7 @@ __device__ __forceinline__ void prefetch_block_l2(const double* __restrict__ val
 struct RowPre {
     int32_t bs, be;
     int32_t c[4];
-    double s[4];
+    double s[6];
 };
 
 // Off-diagonal part of one row of a sweep: acc -= sum_k A_k v[col_k] over blocks [bs, be), in two
@@ -374,12 +374,13 @@ __device__ __forceinline__ void sweep_row_consume(const int32_t* __restrict__ co
     }
 }
 
-// MODE 0: iteration (p <- zs z + beta p fused in, t = (Dt+U)^-1 p).  MODE 1: t = (Dt+U)^-1 pvec.
+// MODE 0: iteration (x += alpha p_old and p <- zs r/omega + beta p_old fused in, t = (Dt+U)^-1 p).
+// MODE 1: back-transform t = (Dt+U)^-1 (x + alpha p), i.e. of the iterate including its pending step.
 // Same arithmetic as mof_sweep_back_body (mof_bodies.h), with the loads of a row batched and the
 // next row's streamed data fetched one row ahead.
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) sweep_back_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                            const int32_t* __restrict__ diag, mof_batch_dev B, double* pvec,
+                                                            const int32_t* __restrict__ diag, mof_batch_dev B,
                                                             double* tout, int64_t N, int64_t nb, int tile0, int tile1,
                                                             double omega) {
     const int64_t g = blockIdx.y;
@@ -392,13 +393,18 @@ __global__ void __launch_bounds__(256, 2) sweep_back_kernel(const int32_t* __res
     const int64_t r1 = min(N, r0 + (int64_t)MOF_TILE_ROWS);
     const int nrows = (int)(r1 - r0);
     double beta = 0.0, zsw = 0.0;
+    // x += alpha p of the PREVIOUS iteration is applied here, where p is read anyway (the vector
+    // kernel then never touches x or p): alpha is the step the last forward sweep computed; it is 0
+    // once a frozen frame's last step has been applied
+    const double alpha = scal_ptr(B.scal, g, MOF_S_ALPHA)[lane];
     if (MODE == 0) {
         beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
         zsw = scal_ptr(B.scal, g, MOF_S_ZS)[lane] / omega;         // z = Dt r = r / omega
     }
     const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
     const double* __restrict__ r_l = B.r + (size_t)g * N * 2 * MOF_W + lane;
-    double* p_l = pvec + (size_t)g * N * 2 * MOF_W + lane;
+    double* p_l = B.p + (size_t)g * N * 2 * MOF_W + lane;
+    double* x_l = B.x + (size_t)g * N * 2 * MOF_W + lane;
     double* t_l = tout + (size_t)g * N * 2 * MOF_W + lane;
     // row pointers of the patch: lane q holds rowptr[r0+q+1] and diag[r0+q] (two coalesced loads)
     int32_t rp_lo = 0, rp_hi = 0, dg_lo = 0, dg_hi = 0;
@@ -414,6 +420,8 @@ __global__ void __launch_bounds__(256, 2) sweep_back_kernel(const int32_t* __res
             R.s[2] = r_l[(2 * i) * MOF_W];
             R.s[3] = r_l[(2 * i + 1) * MOF_W];
         }
+        R.s[4] = x_l[(2 * i) * MOF_W];
+        R.s[5] = x_l[(2 * i + 1) * MOF_W];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (R.bs + k < R.be) R.c[k] = col[R.bs + k];
@@ -431,12 +439,19 @@ __global__ void __launch_bounds__(256, 2) sweep_back_kernel(const int32_t* __res
             const int32_t ps = (qq < 32 ? __shfl_sync(kFull, dg_lo, qq) : __shfl_sync(kFull, dg_hi, qq - 32)) + 1;
             for (int32_t b = ps; b < pe; ++b) prefetch_block_l2(vals_l, b);
         }
-        double a0 = cur.s[0], a1 = cur.s[1];
+        // pending step of the previous iteration: x += alpha p_old
+        const double x0 = fma(alpha, cur.s[0], cur.s[4]), x1 = fma(alpha, cur.s[1], cur.s[5]);
+        double a0, a1;
         if (MODE == 0) {
-            a0 = zsw * cur.s[2] + beta * a0;
-            a1 = zsw * cur.s[3] + beta * a1;
+            x_l[(2 * i) * MOF_W] = x0;
+            x_l[(2 * i + 1) * MOF_W] = x1;
+            a0 = zsw * cur.s[2] + beta * cur.s[0];
+            a1 = zsw * cur.s[3] + beta * cur.s[1];
             p_l[(2 * i) * MOF_W] = a0;
             p_l[(2 * i + 1) * MOF_W] = a1;
+        } else {                                                    // back-transform of the complete iterate
+            a0 = x0;
+            a1 = x1;
         }
         sweep_row_consume(col, vals_l, t_l, cur, bt, a0, a1);
         t_l[(2 * i) * MOF_W] = omega * a0;
@@ -756,13 +771,13 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     int32_t* d_active_groups = B.state + (size_t)G * MOF_I_COUNT * MOF_W + 2 * (size_t)G;
     int64_t launches = 0;
 
-    auto sweep_back = [&](int mode, double* pvec, double* tout) {
+    auto sweep_back = [&](int mode, double* tout) {
         for (int c = C - 1; c >= 0; --c) {
             const int t0 = mesh->color_tile_ptr[c], t1 = mesh->color_tile_ptr[c + 1];
             if (t1 <= t0) continue;
             dim3 gs(mof_cdiv(t1 - t0, kWarps), G);
-            if (mode == 0) sweep_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1, omega);
-            else           sweep_back_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pvec, tout, N, nb, t0, t1, omega);
+            if (mode == 0) sweep_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, t0, t1, omega);
+            else           sweep_back_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, t0, t1, omega);
             ++launches;
         }
     };
@@ -820,7 +835,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                     update_kernel<false><<<grid, 256, 0, st>>>(B, N, ntiles, 0.0);
                     launches += 3;
                 } else {
-                    sweep_back(0, B.p, B.t);                        // p <- zs z + beta p ; t = (Dt+U)^-1 p
+                    sweep_back(0, B.t);                             // x += alpha p ; p <- zs r/omega + beta p ; t = (Dt+U)^-1 p
                     if (sample) cudaEventRecord(ev[1], st);
                     sweep_fwd(0, B.p, B.ap);                        // w ; alpha
                     if (sample) cudaEventRecord(ev[2], st);
@@ -848,7 +863,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
             }
         }
         // confirm on the true residual b - A x; frames that miss tol resume with a tighter threshold
-        if (ssor) sweep_back(1, B.x, B.t);                           // xs = (Dt+U)^-1 xhat (scaled system)
+        if (ssor) sweep_back(1, B.t);                                // xs = (Dt+U)^-1 (xhat + pending alpha p)
         spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, xphys, B.ap, N, nb, ntiles, nullptr,
                                                 nullptr, nullptr, G);
         const int last_round = (rounds >= max_restarts || it >= max_iter) ? 1 : 0;
