@@ -242,6 +242,25 @@ int mof_singularity_compact(int64_t n_vertices, int64_t n_faces, int64_t n_frame
                             double* lam_mu, double* P, int8_t* index, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * K5b ("next" row 2 of SURVEY 8f): Jacobian classification of the detected critical points
+ * (compute_jacobian_matrix_for_vertex / _for_interior, classify_critical_point,
+ * find_singularity_point.py:355-498) for the output of mof_singularity_compact.
+ * e (N,2,3) REFERENCE vertex order; ring_ptr/ring_idx: ascending 1-ring neighbour lists
+ * (pyvista point_neighbors, fsp:375); face_nbr (F,3): face across edge AB / BC / CA of each face,
+ * -1 on the boundary ("the other triangle on the nearest edge", fsp:432-438); voff/foff
+ * (n_frames+1) offsets of each frame inside the point lists.  Outputs per point: the 2x2
+ * matrix the reference accumulates (row-major) and its class 0 Node, 1 Focus, 2 Saddle,
+ * 3 Indeterminate.
+ * ------------------------------------------------------------------------- */
+int mof_classify_singularities(int64_t n_vertices, int64_t n_faces, int64_t n_frames, const double* coords,
+                               const int32_t* tri, const double* Vxyz, const double* vmax, const double* e,
+                               const int32_t* ring_ptr, const int32_t* ring_idx, const int32_t* face_nbr,
+                               const int64_t* voff, const int64_t* foff, int64_t n_vertex_points,
+                               int64_t n_face_points, const int32_t* vertex_idx, const int32_t* face_idx,
+                               const double* P, double* jac_v, int8_t* cls_v, double* jac_f, int8_t* cls_f,
+                               void* stream);
+
+/* ------------------------------------------------------------------------- *
  * K6 ("next" row of SURVEY 8f): wave speed of S5_compute_wave_v.py.
  * I: device (n_frames, N) row stride ld, REFERENCE vertex order (phases in (-pi,pi] or
  * potentials); dt = 1/SF.  phase_mode 1: wave_velocity_phase (S5:79-123, wrapped time

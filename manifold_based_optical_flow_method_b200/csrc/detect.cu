@@ -175,7 +175,103 @@ __global__ void __launch_bounds__(MOF_DETECT_CHUNK) fcompact_kernel(int64_t N, i
     if (index) index[o] = (int8_t)sign;
 }
 
+// ---- Jacobian classification of the detected critical points (fsp:355-498, 561-605) ----------
+// One thread per point (tens of points per frame).  Vertices use the 1-ring as near points and the
+// vertex's own tangent basis; interior points use the vertices of their face plus those of the face
+// across the nearest edge, in ascending vertex order, and a basis built from the face normal.
+__device__ __forceinline__ int64_t frame_of(const int64_t* __restrict__ off, int64_t n_frames, int64_t q) {
+    int64_t lo = 0, hi = n_frames;                 // off[lo] <= q < off[hi]
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void classify_vertex_kernel(int64_t N, int64_t n_frames, const double* __restrict__ coords,
+                                       const double* __restrict__ Vxyz, const double* __restrict__ vmax,
+                                       const double* __restrict__ e, const int32_t* __restrict__ ring_ptr,
+                                       const int32_t* __restrict__ ring_idx, const int64_t* __restrict__ voff,
+                                       const int32_t* __restrict__ vertex_idx, double* __restrict__ jac,
+                                       int8_t* __restrict__ cls) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= voff[n_frames]) return;
+    const int64_t k = frame_of(voff, n_frames, q);
+    const int64_t i = vertex_idx[q];
+    const double* Vk = Vxyz + (size_t)k * N * 3;
+    double J[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int32_t r = ring_ptr[i]; r < ring_ptr[i + 1]; ++r) {
+        const int64_t nb = ring_idx[r];
+        mof_jacobian_term_body(coords + 3 * i, coords + 3 * nb, Vk + 3 * nb, vmax[k], e + 6 * i, e + 6 * i + 3, J);
+    }
+    for (int c = 0; c < 4; ++c) jac[4 * q + c] = J[c];
+    cls[q] = (int8_t)mof_classify_body(J);
+}
+
+__global__ void classify_face_kernel(int64_t N, int64_t n_frames, const double* __restrict__ coords,
+                                     const int32_t* __restrict__ tri, const double* __restrict__ Vxyz,
+                                     const double* __restrict__ vmax, const int32_t* __restrict__ face_nbr,
+                                     const int64_t* __restrict__ foff, const int32_t* __restrict__ face_idx,
+                                     const double* __restrict__ P, double* __restrict__ jac, int8_t* __restrict__ cls) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= foff[n_frames]) return;
+    const int64_t k = frame_of(foff, n_frames, q);
+    const int64_t t = face_idx[q];
+    const int64_t a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+    const double *A = coords + 3 * a, *B = coords + 3 * b, *C = coords + 3 * c;
+    const double ab[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, ac[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+    double n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+    const double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    n[0] /= nl; n[1] /= nl; n[2] /= nl;                                           // calculate_normal, fsp:285-289
+    double eb[6];
+    mof_basis_body(n, eb);                                                        // compute_orthonormal_basis, fsp:304-314
+    const double* Pq = P + 3 * q;
+    const int edge = mof_nearest_edge_body(A, B, C, Pq);
+    const int64_t other = face_nbr[3 * t + edge];
+    int64_t near[6] = {a, b, c, -1, -1, -1};
+    int cnt = 3;
+    if (other >= 0)
+        for (int m = 0; m < 3; ++m) {
+            const int64_t v = tri[3 * other + m];
+            bool dup = false;
+            for (int z = 0; z < cnt; ++z) dup |= near[z] == v;
+            if (!dup) near[cnt++] = v;
+        }
+    for (int x = 1; x < cnt; ++x)                                                  // ascending vertex order
+        for (int y = x; y > 0 && near[y - 1] > near[y]; --y) { int64_t w = near[y]; near[y] = near[y - 1]; near[y - 1] = w; }
+    const double* Vk = Vxyz + (size_t)k * N * 3;
+    double J[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int z = 0; z < cnt; ++z)
+        mof_jacobian_term_body(Pq, coords + 3 * near[z], Vk + 3 * near[z], vmax[k], eb, eb + 3, J);
+    for (int m = 0; m < 4; ++m) jac[4 * q + m] = J[m];
+    cls[q] = (int8_t)mof_classify_body(J);
+}
+
 }  // namespace
+
+extern "C" int mof_classify_singularities(int64_t N, int64_t F, int64_t n_frames, const double* coords, const int32_t* tri,
+                                          const double* Vxyz, const double* vmax, const double* e,
+                                          const int32_t* ring_ptr, const int32_t* ring_idx, const int32_t* face_nbr,
+                                          const int64_t* voff, const int64_t* foff, int64_t n_vertex_points,
+                                          int64_t n_face_points, const int32_t* vertex_idx, const int32_t* face_idx,
+                                          const double* P, double* jac_v, int8_t* cls_v, double* jac_f, int8_t* cls_f,
+                                          void* stream) {
+    MOF_REQUIRE(N > 0 && F >= 0 && n_frames > 0 && coords && tri && Vxyz && vmax && e && voff && foff, "bad arguments");
+    cudaStream_t st = mof_stream(stream);
+    if (n_vertex_points > 0) {
+        MOF_REQUIRE(ring_ptr && ring_idx && vertex_idx && jac_v && cls_v, "vertex arguments missing");
+        classify_vertex_kernel<<<mof_cdiv(n_vertex_points, 128), 128, 0, st>>>(N, n_frames, coords, Vxyz, vmax, e, ring_ptr,
+                                                                             ring_idx, voff, vertex_idx, jac_v, cls_v);
+        MOF_LAUNCH_CHECK("classify_vertex_kernel");
+    }
+    if (n_face_points > 0) {
+        MOF_REQUIRE(face_nbr && face_idx && P && jac_f && cls_f, "face arguments missing");
+        classify_face_kernel<<<mof_cdiv(n_face_points, 128), 128, 0, st>>>(N, n_frames, coords, tri, Vxyz, vmax, face_nbr, foff,
+                                                                         face_idx, P, jac_f, cls_f);
+        MOF_LAUNCH_CHECK("classify_face_kernel");
+    }
+    return 0;
+}
 
 extern "C" int mof_tangent_to_xyz(int64_t N, int64_t n_frames, const double* V, int64_t ldV, const double* e,
                                   double* Vxyz, double* speed, double* vmax, void* stream) {

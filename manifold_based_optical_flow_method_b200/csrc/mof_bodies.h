@@ -318,4 +318,55 @@ MOF_HD bool mof_face_zero_body(const double* A, const double* B, const double* C
     return (l + m <= 1) && (l >= 0) && (m >= 0);               // fsp:130 (false for NaN)
 }
 
+// ---- Jacobian classification (fsp:355-498) -----------------------------------------------
+// One near point's contribution to the 2x2 "Jacobian" the reference accumulates (fsp:383-399 /
+// :442-458): the neighbour's velocity / vmax projected on the plane (e1, e2) and expressed in that
+// basis (u, v), divided by the neighbour's offset from `origin` along e1 and e2.  Divisions by a
+// zero offset give inf / nan exactly like the reference.
+MOF_HD void mof_jacobian_term_body(const double* origin, const double* X, const double* V, double vmax, const double* e1,
+                                   const double* e2, double* J) {
+    const double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    const double s[3] = {V[0] / vmax, V[1] / vmax, V[2] / vmax};
+    const double sn = s[0] * n[0] + s[1] * n[1] + s[2] * n[2];
+    const double p[3] = {s[0] - sn * n[0] / nn, s[1] - sn * n[1] / nn, s[2] - sn * n[2] / nn};     // fsp:206-210
+    const double u = (p[0] * e1[0] + p[1] * e1[1] + p[2] * e1[2]) / (e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    const double v = (p[0] * e2[0] + p[1] * e2[1] + p[2] * e2[2]) / (e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+    const double b[3] = {X[0] - origin[0], X[1] - origin[1], X[2] - origin[2]};                   // fsp:231
+    const double bn = b[0] * n[0] + b[1] * n[1] + b[2] * n[2];
+    const double q[3] = {b[0] - bn * n[0] / nn, b[1] - bn * n[1] / nn, b[2] - bn * n[2] / nn};     // fsp:235
+    const double d1 = q[0] * e1[0] + q[1] * e1[1] + q[2] * e1[2];                                 // fsp:238-239
+    const double d2 = q[0] * e2[0] + q[1] * e2[1] + q[2] * e2[2];
+    J[0] += u / d1; J[1] += u / d2; J[2] += v / d1; J[3] += v / d2;                               // fsp:396-399
+}
+
+// classify_critical_point, fsp:463-498: 0 Node, 1 Focus, 2 Saddle, 3 Indeterminate
+MOF_HD int mof_classify_body(const double* J) {
+    const double trace = J[0] + J[3];
+    const double det = J[0] * J[3] - J[1] * J[2];
+    if (det > 0) return trace * trace > 4 * det ? 0 : 1;
+    if (det < 0) return 2;
+    return 3;
+}
+
+// find_nearest_edge_and_vertices, fsp:318-351, with its flat argmin over the three 3-vectors
+// |cross(P - X, v)| / |v|: flat index 0 -> edge AB (0), 1 -> BC (1), anything else -> CA (2).
+MOF_HD int mof_nearest_edge_body(const double* A, const double* B, const double* C, const double* P) {
+    const double* X[3] = {A, B, C};
+    const double* Y[3] = {B, C, A};
+    double best = 0.0;
+    int arg = -1;
+    for (int k = 0; k < 3; ++k) {
+        const double v[3] = {Y[k][0] - X[k][0], Y[k][1] - X[k][1], Y[k][2] - X[k][2]};
+        const double w[3] = {P[0] - X[k][0], P[1] - X[k][1], P[2] - X[k][2]};
+        const double c[3] = {w[1] * v[2] - w[2] * v[1], w[2] * v[0] - w[0] * v[2], w[0] * v[1] - w[1] * v[0]};
+        const double len = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        for (int m = 0; m < 3; ++m) {
+            const double d = fabs(c[m] / len);
+            if (arg < 0 || d < best) { best = d; arg = 3 * k + m; }      // first minimum, like np.argmin
+        }
+    }
+    return arg == 0 ? 0 : (arg == 1 ? 1 : 2);
+}
+
 #endif  // MOF_BODIES_H

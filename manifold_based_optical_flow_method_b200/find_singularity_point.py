@@ -5,6 +5,8 @@
         -> (singularity_vertices, singularity_interiors, v_length_max)      # reference :140-189
     find_singularity_points_for_all_Vk(V_k_coord, coordinates, triangles, eps)
         -> list (per frame) of point coordinates                            # reference :530-558
+    find_singularity_points_and_classify_for_all_Vk(V_k_coord, coordinates, triangles, eps, surface, e)
+        -> (points per frame, "Node" / "Focus" / "Saddle" / "Indeterminate" per point)   # reference :561-605
 
 plus the batched form the kernels natively produce, ``detect_singularities`` (all frames in
 one call, flat index arrays + per-face Poincare index).
@@ -197,5 +199,120 @@ def find_singularity_points_for_all_Vk(V_k_coord, coordinates, triangles, eps):
     return out
 
 
+CLASS_NAMES = ("Node", "Focus", "Saddle", "Indeterminate")      # classify_critical_point, reference :463-498
+
+
+@dataclasses.dataclass
+class Classified:
+    """Critical points of a batch of frames with the reference's 2x2 "Jacobian" and class; within a
+    frame the order is the reference's: singular vertices first, then interior points."""
+    singularities: "Singularities"
+    offsets: np.ndarray           # (n+1,) start of each frame in the arrays below
+    points: np.ndarray            # (m,3)
+    jacobians: np.ndarray         # (m,2,2)
+    codes: np.ndarray             # (m,) index into CLASS_NAMES
+
+
+def mesh_adjacency(triangles, n_vertices):
+    """1-ring neighbour lists (CSR, ascending; pyvista point_neighbors, reference :375) and the face
+    across each edge AB / BC / CA of every face (-1 on the boundary; the smallest other face if an
+    edge is shared by more than two), as int32 arrays."""
+    t = np.ascontiguousarray(np.asarray(triangles), dtype=np.int64)
+    F = len(t)
+    pairs = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]], t[:, [1, 0]], t[:, [2, 1]], t[:, [0, 2]]])
+    pairs = np.unique(pairs, axis=0)
+    ring_ptr = np.concatenate([[0], np.cumsum(np.bincount(pairs[:, 0], minlength=n_vertices))]).astype(np.int32)
+    ring_idx = pairs[:, 1].astype(np.int32)
+    a = np.concatenate([t[:, 0], t[:, 1], t[:, 2]])
+    b = np.concatenate([t[:, 1], t[:, 2], t[:, 0]])
+    key = np.minimum(a, b) * n_vertices + np.maximum(a, b)
+    face = np.tile(np.arange(F), 3)
+    slot = np.repeat(np.arange(3), F)
+    order = np.lexsort((face, key))
+    ks, fs = key[order], face[order]
+    nbr = -np.ones((F, 3), dtype=np.int32)
+    start = np.concatenate([[True], ks[1:] != ks[:-1]])
+    group_first = np.maximum.accumulate(np.where(start, np.arange(len(ks)), 0))
+    group_size = np.diff(np.concatenate([np.nonzero(start)[0], [len(ks)]]))
+    size_of = np.repeat(group_size, group_size)
+    first_face = fs[group_first]
+    second_face = np.where(size_of > 1, fs[np.minimum(group_first + 1, len(ks) - 1)], -1)
+    other = np.where(fs == first_face, second_face, first_face)       # smallest other face of the edge
+    other = np.where(size_of > 1, other, -1)
+    nbr[fs, slot[order]] = other
+    return ring_ptr, ring_idx, nbr
+
+
+def classify_singularities(V_k_coord, coordinates, triangles, eps, e):
+    """Detection (K5) + Jacobian classification (K5b) for all frames -> Classified."""
+    torch, dev = _torch_dev()
+    lib = _lib.load()
+    coords = np.ascontiguousarray(np.asarray(coordinates, dtype=np.float64))
+    tri = np.ascontiguousarray(np.asarray(triangles), dtype=np.int32)
+    V = np.asarray(V_k_coord, dtype=np.float64)
+    if V.ndim == 2:
+        V = V[None]
+    V = np.ascontiguousarray(V[:, :, :3])
+    N, F = len(coords), len(tri)
+    e_np = np.ascontiguousarray(np.asarray(e, dtype=np.float64)).reshape(-1, 2, 3)
+    ring_ptr, ring_idx, nbr = mesh_adjacency(tri, N)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    coords_d, tri_d, e_d = up(coords), up(tri), up(e_np)
+    rp_d, ri_d, nb_d = up(ring_ptr), up(ring_idx), up(nbr)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    parts, jv, cv, jf, cf = [], [], [], [], []
+    for k0 in range(0, V.shape[0], FRAMES_PER_CALL):
+        Vd = up(V[k0:k0 + FRAMES_PER_CALL])
+        n = int(Vd.shape[0])
+        vmax = torch.empty((n,), dtype=torch.float64, device=dev)
+        _lib.check(lib.mof_vmax(N, n, Vd.data_ptr(), vmax.data_ptr(), st))
+        s = detect_singularities_device(coords_d, tri_d, Vd, eps, vmax)
+        nv, nf = len(s.vertex_idx), len(s.face_idx)
+        jac_v = torch.empty((max(nv, 1), 4), dtype=torch.float64, device=dev)
+        cls_v = torch.empty((max(nv, 1),), dtype=torch.int8, device=dev)
+        jac_f = torch.empty((max(nf, 1), 4), dtype=torch.float64, device=dev)
+        cls_f = torch.empty((max(nf, 1),), dtype=torch.int8, device=dev)
+        voff, foff = up(s.vertex_offsets.astype(np.int64)), up(s.face_offsets.astype(np.int64))
+        vi = up(s.vertex_idx) if nv else cls_v
+        fi = up(s.face_idx) if nf else cls_f
+        Pd = up(s.P) if nf else jac_f
+        _lib.check(lib.mof_classify_singularities(
+            N, F, n, coords_d.data_ptr(), tri_d.data_ptr(), Vd.data_ptr(), vmax.data_ptr(), e_d.data_ptr(),
+            rp_d.data_ptr(), ri_d.data_ptr(), nb_d.data_ptr(), voff.data_ptr(), foff.data_ptr(), nv, nf,
+            vi.data_ptr(), fi.data_ptr(), Pd.data_ptr(), jac_v.data_ptr(), cls_v.data_ptr(), jac_f.data_ptr(),
+            cls_f.data_ptr(), st))
+        parts.append(s)
+        jv.append(jac_v[:nv].cpu().numpy()); cv.append(cls_v[:nv].cpu().numpy())
+        jf.append(jac_f[:nf].cpu().numpy()); cf.append(cls_f[:nf].cpu().numpy())
+    s = _concat(parts)
+    jv, cv, jf, cf = np.concatenate(jv), np.concatenate(cv), np.concatenate(jf), np.concatenate(cf)
+    pts, jac, codes, offsets = [], [], [], [0]
+    for k in range(len(s.v_length_max)):
+        v = slice(s.vertex_offsets[k], s.vertex_offsets[k + 1])
+        f = slice(s.face_offsets[k], s.face_offsets[k + 1])
+        pts += [coords[s.vertex_idx[v]], s.P[f]]
+        jac += [jv[v], jf[f]]
+        codes += [cv[v], cf[f]]
+        offsets.append(offsets[-1] + (v.stop - v.start) + (f.stop - f.start))
+    return Classified(s, np.asarray(offsets, dtype=np.int64), np.concatenate(pts).reshape(-1, 3),
+                      np.concatenate(jac).reshape(-1, 2, 2), np.concatenate(codes).astype(np.int64))
+
+
+def find_singularity_points_and_classify_for_all_Vk(V_k_coord, coordinates, triangles, eps, surface, e):
+    """Reference :561-605.  ``surface`` is accepted for signature compatibility; the adjacency the
+    reference takes from it (point_neighbors, find_cells_intersecting_line) is derived from
+    ``triangles``.  -> (singularity_points, classification): per frame a list of coordinates and a
+    list of "Node" / "Focus" / "Saddle" / "Indeterminate"."""
+    c = classify_singularities(V_k_coord, coordinates, triangles, eps, e)
+    pts, cls = [], []
+    for k in range(len(c.offsets) - 1):
+        sl = slice(c.offsets[k], c.offsets[k + 1])
+        pts.append([p.copy() for p in c.points[sl]])
+        cls.append([CLASS_NAMES[q] for q in c.codes[sl]])
+    return pts, cls
+
+
 __all__ = ["process_V_k", "speed_magnitude", "find_singularity_points", "find_singularity_points_for_all_Vk",
-           "detect_singularities", "detect_singularities_device", "tangent_to_xyz_device", "Singularities"]
+           "detect_singularities", "detect_singularities_device", "tangent_to_xyz_device", "Singularities",
+           "find_singularity_points_and_classify_for_all_Vk", "classify_singularities", "mesh_adjacency", "Classified",
+           "CLASS_NAMES"]

@@ -255,3 +255,21 @@ class SurfaceMesh:
     def point_cell_ids(self, index):
         """ids of the cells using point ``index``, ascending (VTK's order for a PolyData)."""
         return [int(c) for c in self._cells[self._ptr[index]:self._ptr[index + 1]]]
+
+    def point_neighbors(self, index):
+        """1-ring of point ``index`` (pyvista: points sharing a cell with it), ascending."""
+        out = set()
+        for c in self.point_cell_ids(index):
+            out.update(int(v) for v in self.triangles[c])
+        out.discard(int(index))
+        return sorted(out)
+
+    def find_cells_intersecting_line(self, pointa, pointb, tolerance=0.0):
+        """Stand-in for the VTK cell locator as utils/find_singularity_point.py:435 uses it: the
+        segment is always a mesh edge there, and the caller wants "the other triangle on that
+        edge", so the cells containing BOTH end points are returned (ascending).  (The real
+        locator may also return cells that merely touch an end point; which of them
+        ``set(...).pop()`` then picks is not defined by the reference.)"""
+        a = int(np.argmin(np.linalg.norm(self.points - np.asarray(pointa), axis=1)))
+        b = int(np.argmin(np.linalg.norm(self.points - np.asarray(pointb), axis=1)))
+        return sorted(set(self.point_cell_ids(a)) & set(self.point_cell_ids(b)))

@@ -356,3 +356,115 @@ def wave_velocity(coordinates, triangles, areas, data, dt, e, phase=True):
     al = np.einsum("tnx,nx->tn", Vt, e1) / np.einsum("nx,nx->n", e1, e1)   # :189
     be = np.einsum("tnx,nx->tn", Vt, e2) / np.einsum("nx,nx->n", e2, e2)   # :190
     return td / np.sqrt(al ** 2 + be ** 2)                                 # :117,:121
+
+
+# ----------------------------------------------------------------------------
+# Jacobian classification of critical points (utils/find_singularity_point.py:355-498,561-605;
+# "next" row 2 of SURVEY 8f).  pyvista is replaced by explicit adjacency: point_neighbors = the
+# 1-ring (ascending), and "the other triangle on the nearest edge" for find_cells_intersecting_line
+# followed by set.pop() (fsp:434-437), which the reference does not define more precisely.
+# ----------------------------------------------------------------------------
+CLASS_NAMES = ("Node", "Focus", "Saddle", "Indeterminate")
+
+
+def one_ring(triangles, N):
+    """ascending 1-ring neighbour lists as CSR (ptr, idx)"""
+    t = np.asarray(triangles, dtype=np.int64)
+    pairs = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]], t[:, [1, 0]], t[:, [2, 1]], t[:, [0, 2]]])
+    pairs = np.unique(pairs, axis=0)
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(pairs[:, 0], minlength=N))])
+    return ptr, pairs[:, 1].copy()
+
+
+def face_neighbors(triangles):
+    """(F,3): face across edge k of each face (edge 0 = AB, 1 = BC, 2 = CA), -1 on the boundary;
+    if more than two faces share an edge the smallest other face index is taken."""
+    t = np.asarray(triangles, dtype=np.int64)
+    F = len(t)
+    edges = {}
+    for f in range(F):
+        for k in range(3):
+            key = tuple(sorted((int(t[f, k]), int(t[f, (k + 1) % 3]))))
+            edges.setdefault(key, []).append(f)
+    out = -np.ones((F, 3), dtype=np.int64)
+    for f in range(F):
+        for k in range(3):
+            key = tuple(sorted((int(t[f, k]), int(t[f, (k + 1) % 3]))))
+            others = [g for g in edges[key] if g != f]
+            if others:
+                out[f, k] = min(others)
+    return out
+
+
+def _jacobian_sum(origin, near, coordinates, V_now, vmax, e1, e2):
+    """fsp:383-399 / :442-458: J += [[u/d1, u/d2], [v/d1, v/d2]] over the near points."""
+    J = np.zeros((2, 2))
+    n = np.cross(e1, e2)
+    for nb in near:
+        Vn = V_now[nb] / vmax
+        Vp = Vn - np.dot(Vn, n) * n / np.dot(n, n)                       # project_vector_to_plane, fsp:206-210
+        u = np.dot(Vp, e1) / np.dot(e1, e1)                              # express_vector_on_basis, fsp:266-267
+        v = np.dot(Vp, e2) / np.dot(e2, e2)
+        Br = coordinates[nb] - origin                                    # position_diff_on_basis_with_origin, fsp:231-239
+        pr = Br - np.dot(Br, n) * n / np.dot(n, n)
+        d1, d2 = np.dot(pr, e1), np.dot(pr, e2)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            J += np.array([[u / d1, u / d2], [v / d1, v / d2]])
+    return J
+
+
+def jacobian_for_vertex(index, coordinates, V_now, vmax, e, ring_ptr, ring_idx):
+    """compute_jacobian_matrix_for_vertex, fsp:355-402."""
+    near = ring_idx[ring_ptr[index]:ring_ptr[index + 1]]
+    return _jacobian_sum(coordinates[index], near, coordinates, V_now, vmax, e[index][0], e[index][1])
+
+
+def nearest_edge_index(A, B, C, P):
+    """find_nearest_edge_and_vertices, fsp:318-351, including its flat argmin over the three
+    3-vectors |cross(P - X, v)| / |v| (index 0 -> AB, 1 -> BC, anything else -> CA)."""
+    v1, v2, v3 = B - A, C - B, A - C
+    d = np.array([np.abs(np.cross(P - A, v1) / np.linalg.norm(v1)), np.abs(np.cross(P - B, v2) / np.linalg.norm(v2)),
+                  np.abs(np.cross(P - C, v3) / np.linalg.norm(v3))])
+    k = int(np.argmin(d))
+    return 0 if k == 0 else (1 if k == 1 else 2)
+
+
+def jacobian_for_interior(face, P, coordinates, triangles, V_now, vmax, fnbr):
+    """compute_jacobian_matrix_for_interior, fsp:405-460."""
+    tri = np.asarray(triangles[face], dtype=np.int64)
+    A, B, C = coordinates[tri[0]], coordinates[tri[1]], coordinates[tri[2]]
+    normal = np.cross(B - A, C - A)
+    normal = normal / np.linalg.norm(normal)                              # calculate_normal, fsp:285-289
+    e1, e2 = orthonormal_basis(normal[None])[0]                           # compute_orthonormal_basis, fsp:304-314
+    k = nearest_edge_index(A, B, C, P)
+    other = fnbr[face, k]
+    near = set(int(v) for v in tri)
+    if other >= 0:
+        near |= set(int(v) for v in triangles[other])
+    return _jacobian_sum(P, sorted(near), coordinates, V_now, vmax, e1, e2)
+
+
+def classify(J):
+    """classify_critical_point, fsp:463-498 -> index into CLASS_NAMES."""
+    trace = J[0, 0] + J[1, 1]
+    det = J[0, 0] * J[1, 1] - J[0, 1] * J[1, 0]
+    if det > 0:
+        return 0 if trace ** 2 > 4 * det else 1
+    if det < 0:
+        return 2
+    return 3
+
+
+def classify_singularities(coordinates, triangles, V_now, eps, e):
+    """One frame of find_singularity_points_and_classify_for_all_Vk, fsp:582-603
+    -> (points (n,3), class codes (n,), jacobians (n,2,2)); vertices first, then interiors."""
+    coordinates = np.asarray(coordinates, dtype=np.float64)
+    V_now = np.asarray(V_now, dtype=np.float64)
+    vi, fi, lm, P, vmax = find_singularity_points(coordinates, triangles, V_now, eps)
+    ptr, idx = one_ring(triangles, len(coordinates))
+    fnbr = face_neighbors(triangles)
+    Js = [jacobian_for_vertex(int(i), coordinates, V_now, vmax, e, ptr, idx) for i in vi]
+    Js += [jacobian_for_interior(int(f), P[q], coordinates, triangles, V_now, vmax, fnbr) for q, f in enumerate(fi)]
+    pts = [coordinates[i] for i in vi] + [p for p in P]
+    return (np.asarray(pts).reshape(-1, 3), np.asarray([classify(J) for J in Js], dtype=np.int64),
+            np.asarray(Js).reshape(-1, 2, 2))
