@@ -323,21 +323,31 @@ MOF_HD bool mof_face_zero_body(const double* A, const double* B, const double* C
 // :442-458): the neighbour's velocity / vmax projected on the plane (e1, e2) and expressed in that
 // basis (u, v), divided by the neighbour's offset from `origin` along e1 and e2.  Divisions by a
 // zero offset give inf / nan exactly like the reference.
+MOF_HD double mof_dot3_plain(const double* a, const double* b) {       // separate multiplies and adds, like numpy
+    return MOF_ADD(MOF_ADD(MOF_MUL(a[0], b[0]), MOF_MUL(a[1], b[1])), MOF_MUL(a[2], b[2]));
+}
+
 MOF_HD void mof_jacobian_term_body(const double* origin, const double* X, const double* V, double vmax, const double* e1,
                                    const double* e2, double* J) {
-    const double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-    const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    // no FMA contraction anywhere here: on symmetric meshes an offset along e1 / e2 can be exactly 0
+    // in the reference's arithmetic, and the resulting inf / nan decide the class
+    const double n[3] = {MOF_ADD(MOF_MUL(e1[1], e2[2]), -MOF_MUL(e1[2], e2[1])), MOF_ADD(MOF_MUL(e1[2], e2[0]), -MOF_MUL(e1[0], e2[2])),
+                         MOF_ADD(MOF_MUL(e1[0], e2[1]), -MOF_MUL(e1[1], e2[0]))};
+    const double nn = mof_dot3_plain(n, n);
     const double s[3] = {V[0] / vmax, V[1] / vmax, V[2] / vmax};
-    const double sn = s[0] * n[0] + s[1] * n[1] + s[2] * n[2];
-    const double p[3] = {s[0] - sn * n[0] / nn, s[1] - sn * n[1] / nn, s[2] - sn * n[2] / nn};     // fsp:206-210
-    const double u = (p[0] * e1[0] + p[1] * e1[1] + p[2] * e1[2]) / (e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
-    const double v = (p[0] * e2[0] + p[1] * e2[1] + p[2] * e2[2]) / (e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
-    const double b[3] = {X[0] - origin[0], X[1] - origin[1], X[2] - origin[2]};                   // fsp:231
-    const double bn = b[0] * n[0] + b[1] * n[1] + b[2] * n[2];
-    const double q[3] = {b[0] - bn * n[0] / nn, b[1] - bn * n[1] / nn, b[2] - bn * n[2] / nn};     // fsp:235
-    const double d1 = q[0] * e1[0] + q[1] * e1[1] + q[2] * e1[2];                                 // fsp:238-239
-    const double d2 = q[0] * e2[0] + q[1] * e2[1] + q[2] * e2[2];
-    J[0] += u / d1; J[1] += u / d2; J[2] += v / d1; J[3] += v / d2;                               // fsp:396-399
+    const double sn = mof_dot3_plain(s, n);
+    const double p[3] = {MOF_ADD(s[0], -(MOF_MUL(sn, n[0]) / nn)), MOF_ADD(s[1], -(MOF_MUL(sn, n[1]) / nn)),
+                         MOF_ADD(s[2], -(MOF_MUL(sn, n[2]) / nn))};                                   // fsp:206-210
+    const double u = mof_dot3_plain(p, e1) / mof_dot3_plain(e1, e1);                                     // fsp:266-267
+    const double v = mof_dot3_plain(p, e2) / mof_dot3_plain(e2, e2);
+    const double b[3] = {MOF_ADD(X[0], -origin[0]), MOF_ADD(X[1], -origin[1]), MOF_ADD(X[2], -origin[2])};   // fsp:231
+    const double bn = mof_dot3_plain(b, n);
+    const double q[3] = {MOF_ADD(b[0], -(MOF_MUL(bn, n[0]) / nn)), MOF_ADD(b[1], -(MOF_MUL(bn, n[1]) / nn)),
+                         MOF_ADD(b[2], -(MOF_MUL(bn, n[2]) / nn))};                                   // fsp:235
+    const double d1 = mof_dot3_plain(q, e1);                                                             // fsp:238-239
+    const double d2 = mof_dot3_plain(q, e2);
+    J[0] = MOF_ADD(J[0], u / d1); J[1] = MOF_ADD(J[1], u / d2);                                          // fsp:396-399
+    J[2] = MOF_ADD(J[2], v / d1); J[3] = MOF_ADD(J[3], v / d2);
 }
 
 // classify_critical_point, fsp:463-498: 0 Node, 1 Focus, 2 Saddle, 3 Indeterminate
