@@ -261,6 +261,25 @@ int mof_classify_singularities(int64_t n_vertices, int64_t n_faces, int64_t n_fr
                                void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * K7 ("next" row 3 of SURVEY 8f): multi-ring winding numbers of singular points
+ * (calculate_winding_numbers, S7_winding_line.py:120-165; angle_between_vectors / winding_number
+ * :59-87; polar ordering :93-102).  For each of the n_points points (points (n,3);
+ * frame_of_point (n,) selects the velocity field Vxyz[frame] of shape (N,3)): the closest mesh
+ * vertex (S7:130), then for ring level 0 .. max_level-1 around it (breadth-first topological
+ * rings over ring_ptr / ring_idx, pyvista point_neighbors_levels, S7:131) the winding number of
+ * the velocity field along the ring ordered by polar angle in the vertex's tangent basis
+ * e (N,2,3).  counts = number of consecutive rings accepted by the reference's rule (first ring
+ * within 0.01 of +1 or -1 fixes the type, later rings within 0.001 of it); types = +1 / -1 / 0;
+ * winding (n, max_level), optional: the winding numbers evaluated, NaN after the stop;
+ * status: 0 ok, 2 a ring held more than 1024 vertices (count stops there).  Where the mesh runs
+ * out of rings the count stops (the reference raises IndexError).  All REFERENCE vertex order.
+ * ------------------------------------------------------------------------- */
+int mof_winding_numbers(int64_t n_vertices, int64_t n_frames, const double* coords, const double* Vxyz,
+                        const double* e, const int32_t* ring_ptr, const int32_t* ring_idx, int64_t n_points,
+                        const double* points, const int32_t* frame_of_point, int max_level, int32_t* closest,
+                        int32_t* counts, int8_t* types, double* winding, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * K6 ("next" row of SURVEY 8f): wave speed of S5_compute_wave_v.py.
  * I: device (n_frames, N) row stride ld, REFERENCE vertex order (phases in (-pi,pi] or
  * potentials); dt = 1/SF.  phase_mode 1: wave_velocity_phase (S5:79-123, wrapped time

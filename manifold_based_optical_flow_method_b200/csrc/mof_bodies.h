@@ -379,4 +379,56 @@ MOF_HD int mof_nearest_edge_body(const double* A, const double* B, const double*
     return arg == 0 ? 0 : (arg == 1 ? 1 : 2);
 }
 
+// ---- multi-ring winding numbers (S7_winding_line.py:59-165) ----
+// One ring vertex X with velocity V seen from the centre vertex O in its tangent basis (e1, e2):
+// polar-angle sort key (S7:36-45, :97) and the tangent components of V (S7:26-33, :48-57).
+MOF_HD void mof_winding_element_body(const double* O, const double* X, const double* V, const double* e1, const double* e2,
+                                     double* key, double* vx, double* vy) {
+    const double n[3] = {MOF_ADD(MOF_MUL(e1[1], e2[2]), -MOF_MUL(e1[2], e2[1])), MOF_ADD(MOF_MUL(e1[2], e2[0]), -MOF_MUL(e1[0], e2[2])),
+                         MOF_ADD(MOF_MUL(e1[0], e2[1]), -MOF_MUL(e1[1], e2[0]))};
+    const double nn = mof_dot3_plain(n, n);
+    const double b[3] = {MOF_ADD(X[0], -O[0]), MOF_ADD(X[1], -O[1]), MOF_ADD(X[2], -O[2])};
+    const double bn = mof_dot3_plain(b, n);
+    const double q[3] = {MOF_ADD(b[0], -(MOF_MUL(bn, n[0]) / nn)), MOF_ADD(b[1], -(MOF_MUL(bn, n[1]) / nn)),
+                         MOF_ADD(b[2], -(MOF_MUL(bn, n[2]) / nn))};
+    *key = atan2(mof_dot3_plain(q, e2), mof_dot3_plain(q, e1));
+    const double vn = mof_dot3_plain(V, n);
+    const double t[3] = {MOF_ADD(V[0], -(MOF_MUL(vn, n[0]) / nn)), MOF_ADD(V[1], -(MOF_MUL(vn, n[1]) / nn)),
+                         MOF_ADD(V[2], -(MOF_MUL(vn, n[2]) / nn))};
+    *vx = mof_dot3_plain(t, e1) / mof_dot3_plain(e1, e1);
+    *vy = mof_dot3_plain(t, e2) / mof_dot3_plain(e2, e2);
+}
+
+// angle_between_vectors, S7:59-74: signed angle from a to b, counter-clockwise positive; NaN for a zero vector.
+MOF_HD double mof_signed_angle_body(double ax, double ay, double bx, double by) {
+    const double la = sqrt(MOF_ADD(MOF_MUL(ax, ax), MOF_MUL(ay, ay)));
+    const double lb = sqrt(MOF_ADD(MOF_MUL(bx, bx), MOF_MUL(by, by)));
+    const double ux = ax / la, uy = ay / la, wx = bx / lb, wy = by / lb;
+    double d = MOF_ADD(MOF_MUL(ux, wx), MOF_MUL(uy, wy));
+    if (d > 1.0) d = 1.0;
+    else if (d < -1.0) d = -1.0;
+    double ang = acos(d);
+    if (MOF_ADD(MOF_MUL(ux, wy), -MOF_MUL(uy, wx)) < 0.0) ang = -ang;
+    return ang;
+}
+
+// The acceptance rule of S7:150-163 for the winding number w of ring `level`; *flag is the type
+// fixed by the first ring (+1 / -1, 0 = neither).  Returns true when the ring counts.
+MOF_HD bool mof_winding_accept_body(int level, double w, int* flag) {
+    if (level == 0) {
+        if (w >= -1.01 && w <= -0.99) { *flag = -1; return true; }
+        if (w >= 0.99 && w <= 1.01) { *flag = 1; return true; }
+        return false;
+    }
+    if (*flag == 1) return w >= 0.999 && w <= 1.001;
+    if (*flag == -1) return w >= -1.001 && w <= -0.999;
+    return false;
+}
+
+// distance of S7:130's find_closest_point (Euclidean, like np.linalg.norm of the difference)
+MOF_HD double mof_dist3_body(const double* a, const double* b) {
+    const double d[3] = {MOF_ADD(a[0], -b[0]), MOF_ADD(a[1], -b[1]), MOF_ADD(a[2], -b[2])};
+    return sqrt(mof_dot3_plain(d, d));
+}
+
 #endif  // MOF_BODIES_H

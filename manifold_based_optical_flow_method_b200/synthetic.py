@@ -264,6 +264,25 @@ class SurfaceMesh:
         out.discard(int(index))
         return sorted(out)
 
+    def find_closest_point(self, point):
+        """index of the vertex closest to ``point`` (lowest index on ties)"""
+        return int(np.argmin(np.linalg.norm(self.points - np.asarray(point, dtype=np.float64), axis=1)))
+
+    def point_neighbors_levels(self, ind, n_levels=1):
+        """pyvista's generator of topological rings: level 1 = 1-ring, level k = vertices first
+        reached after k edges; yields exactly ``n_levels`` lists (empty once the mesh is exhausted)."""
+        neighbors = set(self.point_neighbors(ind))
+        yield sorted(neighbors)
+        visited = set(neighbors)
+        visited.add(int(ind))
+        for _ in range(n_levels - 1):
+            new = set()
+            for n in neighbors:
+                new.update(self.point_neighbors(n))
+            neighbors = new - visited
+            yield sorted(neighbors)
+            visited |= neighbors
+
     def find_cells_intersecting_line(self, pointa, pointb, tolerance=0.0):
         """Stand-in for the VTK cell locator as utils/find_singularity_point.py:435 uses it: the
         segment is always a mesh edge there, and the caller wants "the other triangle on that

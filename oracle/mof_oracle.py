@@ -23,6 +23,8 @@ vectorised over faces/vertices (the literal reference needs ~380 us per face in
 pure Python, i.e. ~165 s per frame at 164k vertices) but keeps the reference's
 operation order inside each scalar expression.
 """
+import math
+
 import numpy as np
 import scipy.sparse as sp
 from scipy.sparse.linalg import spsolve
@@ -468,3 +470,108 @@ def classify_singularities(coordinates, triangles, V_now, eps, e):
     pts = [coordinates[i] for i in vi] + [p for p in P]
     return (np.asarray(pts).reshape(-1, 3), np.asarray([classify(J) for J in Js], dtype=np.int64),
             np.asarray(Js).reshape(-1, 2, 2))
+
+
+# ----------------------------------------------------------------------------
+# Multi-ring winding numbers of a singular point (S7_winding_line.py:59-165; "next" row 3 of
+# SURVEY 8f).  pyvista is replaced by explicit adjacency: find_closest_point = the nearest vertex
+# (lowest index on ties), point_neighbors_levels = breadth-first topological rings.
+# ----------------------------------------------------------------------------
+def closest_vertex(coordinates, point):
+    """surf.find_closest_point, S7:130."""
+    d = np.linalg.norm(np.asarray(coordinates, dtype=np.float64) - np.asarray(point, dtype=np.float64), axis=1)
+    return int(np.argmin(d))
+
+
+def ring_levels(ring_ptr, ring_idx, index, max_level):
+    """surf.point_neighbors_levels(index, max_level), S7:131: ring k+1 = unvisited neighbours of ring k
+    (ascending); stops at the first empty ring."""
+    seen = {int(index)}
+    cur = [int(index)]
+    out = []
+    for _ in range(max_level):
+        nxt = set()
+        for v in cur:
+            nxt.update(int(w) for w in ring_idx[ring_ptr[v]:ring_ptr[v + 1]])
+        nxt -= seen
+        if not nxt:
+            break
+        cur = sorted(nxt)
+        seen |= nxt
+        out.append(cur)
+    return out
+
+
+def signed_angle(v1, v2):
+    """angle_between_vectors, S7:59-74 (2-vectors; counter-clockwise positive)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a = np.asarray(v1, dtype=np.float64) / np.sqrt(v1[0] * v1[0] + v1[1] * v1[1])
+        b = np.asarray(v2, dtype=np.float64) / np.sqrt(v2[0] * v2[0] + v2[1] * v2[1])
+        d = a[0] * b[0] + a[1] * b[1]
+        if d > 1:
+            d = 1.0
+        elif d < -1:
+            d = -1.0
+        ang = np.arccos(d)
+    if a[0] * b[1] - a[1] * b[0] < 0:
+        ang = -ang
+    return ang
+
+
+def ring_winding_number(index, ring, coordinates, V_now, e):
+    """One level of S7:135-149: ring vertices and their velocities expressed in the tangent basis
+    of vertex `index`, ordered by polar angle (stable, S7:93-100), summed turning / 2 pi (S7:76-87)."""
+    e1, e2 = e[index][0], e[index][1]
+    n = np.cross(e1, e2)
+    keys, vx, vy = [], [], []
+    for w in ring:
+        Br = coordinates[w] - coordinates[index]                           # S7:36-45
+        pr = Br - np.dot(Br, n) * n / np.dot(n, n)
+        keys.append(math.atan2(np.dot(pr, e2), np.dot(pr, e1)))
+        Vt = V_now[w] - np.dot(V_now[w], n) * n / np.dot(n, n)             # S7:26-33
+        vx.append(np.dot(Vt, e1) / np.dot(e1, e1))                         # S7:48-57
+        vy.append(np.dot(Vt, e2) / np.dot(e2, e2))
+    order = np.argsort(np.asarray(keys), kind="stable")
+    total = 0.0
+    m = len(ring)
+    for i in range(m):
+        a, b = order[i], order[(i + 1) % m]
+        total += signed_angle((vx[a], vy[a]), (vx[b], vy[b]))
+    return total / (2 * np.pi)
+
+
+def winding_numbers(coordinates, triangles, singularity_points, V_now, e, max_level=25, adjacency=None):
+    """calculate_winding_numbers, S7:120-165 -> (counts (n,), types (n,) in {-1,0,1}, winding (n,max_level)
+    with NaN where a level was not evaluated).  `types` has one entry per point (0 where the first
+    ring is neither +1 nor -1); the reference's list keeps only the non-zero ones, in order.
+    Where the mesh runs out of rings before max_level the reference raises IndexError; here the
+    count simply stops."""
+    coordinates = np.asarray(coordinates, dtype=np.float64)
+    V_now = np.asarray(V_now, dtype=np.float64)
+    e = np.asarray(e, dtype=np.float64).reshape(len(coordinates), 2, 3)
+    ptr, idx = adjacency if adjacency is not None else one_ring(triangles, len(coordinates))
+    pts = np.asarray(singularity_points, dtype=np.float64).reshape(-1, 3)
+    counts = np.zeros(len(pts), dtype=np.int64)
+    types = np.zeros(len(pts), dtype=np.int64)
+    wind = np.full((len(pts), max_level), np.nan)
+    for q, P in enumerate(pts):
+        index = closest_vertex(coordinates, P)
+        rings = ring_levels(ptr, idx, index, max_level)
+        flag = 0
+        for level, ring in enumerate(rings):
+            w = ring_winding_number(index, ring, coordinates, V_now, e)
+            wind[q, level] = w
+            if level == 0:
+                if -1.01 <= w <= -0.99:
+                    flag = -1
+                elif 0.99 <= w <= 1.01:
+                    flag = 1
+                else:
+                    break                                                   # S7:160 with flag 0: check_property -> None
+                counts[q] += 1
+            elif (flag == 1 and 0.999 <= w <= 1.001) or (flag == -1 and -1.001 <= w <= -0.999):
+                counts[q] += 1
+            else:
+                break
+        types[q] = flag
+    return counts, types, wind

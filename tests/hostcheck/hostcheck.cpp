@@ -9,6 +9,9 @@
 #include "mof_b200.h"
 #include "mof_bodies.h"
 
+#include <cmath>
+#include <vector>
+
 extern "C" {
 
 void hc_geom(const mof_mesh_dev* M, const double* coords, const double* normals, double* e, double* grad_w,
@@ -167,5 +170,52 @@ void hc_detect(int64_t N, int64_t F, const double* coords, const int32_t* tri, c
         }
     }
     delete[] vf;
+}
+// Sequential walk through the steps of csrc/winding.cu for one point (closest vertex, breadth-first
+// rings with a visited mask, rank by (polar key, vertex id), sequential angle sum, acceptance rule).
+void hc_winding(int64_t N, const double* coords, const double* V, const double* e, const int32_t* ring_ptr,
+                const int32_t* ring_idx, const double* P, int max_level, int32_t* closest, int32_t* count, int32_t* type,
+                double* winding) {
+    double best = INFINITY;
+    int arg = 0;
+    for (int64_t v = 0; v < N; ++v) {
+        const double d = mof_dist3_body(coords + 3 * v, P);
+        if (d < best) { best = d; arg = (int)v; }
+    }
+    std::vector<uint8_t> seen(N, 0);
+    std::vector<int32_t> cur{arg}, nxt;
+    seen[arg] = 1;
+    const double* O = coords + 3 * (size_t)arg;
+    const double* e1 = e + 6 * (size_t)arg;
+    const double* e2 = e1 + 3;
+    int flag = 0;
+    *count = 0;
+    for (int l = 0; l < max_level; ++l) winding[l] = NAN;
+    for (int level = 0; level < max_level; ++level) {
+        nxt.clear();
+        for (int32_t v : cur)
+            for (int j = ring_ptr[v]; j < ring_ptr[v + 1]; ++j)
+                if (!seen[ring_idx[j]]) { seen[ring_idx[j]] = 1; nxt.push_back(ring_idx[j]); }
+        const int n = (int)nxt.size();
+        if (n == 0) break;
+        std::vector<double> key(n), vx(n), vy(n), sx(n), sy(n);
+        for (int t = 0; t < n; ++t)
+            mof_winding_element_body(O, coords + 3 * (size_t)nxt[t], V + 3 * (size_t)nxt[t], e1, e2, &key[t], &vx[t], &vy[t]);
+        for (int t = 0; t < n; ++t) {
+            int r = 0;
+            for (int j = 0; j < n; ++j) r += (key[j] < key[t] || (key[j] == key[t] && nxt[j] < nxt[t])) ? 1 : 0;
+            sx[r] = vx[t];
+            sy[r] = vy[t];
+        }
+        double sum = 0.0;
+        for (int t = 0; t < n; ++t) sum += mof_signed_angle_body(sx[t], sy[t], sx[(t + 1) % n], sy[(t + 1) % n]);
+        const double w = sum / (2 * 3.141592653589793);
+        winding[level] = w;
+        if (!mof_winding_accept_body(level, w, &flag)) break;
+        ++*count;
+        cur.swap(nxt);
+    }
+    *closest = arg;
+    *type = flag;
 }
 }
