@@ -58,7 +58,7 @@ def winding_numbers(triangles, coordinates, singularity_points, frame_of_point, 
     e_np = np.ascontiguousarray(np.asarray(e, dtype=np.float64)).reshape(N, 2, 3)
     pts = np.ascontiguousarray(np.asarray(singularity_points, dtype=np.float64)).reshape(-1, 3)
     n = len(pts)
-    fop = np.ascontiguousarray(np.broadcast_to(np.asarray(frame_of_point, dtype=np.int32), (n,)))
+    fop = np.array(np.broadcast_to(np.asarray(frame_of_point, dtype=np.int32), (n,)))
     if n and (fop.min() < 0 or fop.max() >= V.shape[0]):
         raise ValueError("frame_of_point out of range")
     max_level = int(max_level)
@@ -67,7 +67,7 @@ def winding_numbers(triangles, coordinates, singularity_points, frame_of_point, 
     if n == 0:
         return WindingResult(np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros((0, max_level)))
     ring_ptr, ring_idx, _ = mesh_adjacency(triangles, N)
-    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    up = lambda a: torch.from_numpy(np.array(a, copy=True, order='C')).to(dev)
     coords_d, V_d, e_d, rp_d, ri_d, pts_d, fop_d = up(coords), up(V), up(e_np), up(ring_ptr), up(ring_idx), up(pts), up(fop)
     closest = torch.empty((n,), dtype=torch.int32, device=dev)
     counts = torch.empty((n,), dtype=torch.int32, device=dev)
