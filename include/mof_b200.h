@@ -280,6 +280,28 @@ int mof_winding_numbers(int64_t n_vertices, int64_t n_frames, const double* coor
                         int32_t* counts, int8_t* types, double* winding, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * K8 ("next" row 4 of SURVEY 8f, the producer of the hot path's input): radial-basis interpolation
+ * of electrode signals onto the mesh vertices -- `interpolation`, S2_interpolate.py:22-53 and
+ * S2_interpolate_phases.py:22-56, i.e. scipy.interpolate.Rbf(x, y, z, d)(vx, vy, vz) with its
+ * defaults: multiquadric phi(r) = sqrt((r/epsilon)^2 + 1), smooth 0, Euclidean norm.  epsilon is
+ * the caller's (the scipy default is (prod(bounding-box edges)/m)^(1/n_edges)).
+ *
+ * mof_rbf_fit: builds the (m,m) matrix phi(|c_i - c_j|) into lu, factorises it in place (LU, partial
+ * pivoting, piv (m,) LAPACK-style) and solves it for n_rhs right-hand sides data (n_rhs, m) row
+ * stride ld into weights (m, n_rhs) (right-hand side minor).  info (device int32): 0, or k+1 if
+ * pivot k is exactly zero (singular: duplicated electrodes).  Complex data: pass real parts as
+ * rows 0..T-1 and imaginary parts as rows T..2T-1 (n_rhs = 2T).
+ * mof_rbf_evaluate: out (n_frames, N) row stride ld, out[t][n] = sum_j weights[j][t] phi(|v_n - c_j|);
+ * phase_mode 1: weights hold 2*n_frames columns and out = atan2(imaginary, real) (np.angle,
+ * S2_interpolate_phases.py:52).
+ * ------------------------------------------------------------------------- */
+int mof_rbf_fit(int64_t n_centres, const double* centres, double epsilon, int64_t n_rhs, const double* data,
+                int64_t ld, double* lu, int32_t* piv, double* weights, int32_t* info, void* stream);
+int mof_rbf_evaluate(int64_t n_vertices, int64_t n_centres, int64_t n_frames, const double* vertices,
+                     const double* centres, double epsilon, const double* weights, int phase_mode, double* out,
+                     int64_t ld, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * K6 ("next" row of SURVEY 8f): wave speed of S5_compute_wave_v.py.
  * I: device (n_frames, N) row stride ld, REFERENCE vertex order (phases in (-pi,pi] or
  * potentials); dt = 1/SF.  phase_mode 1: wave_velocity_phase (S5:79-123, wrapped time

@@ -29,7 +29,7 @@ EXPORTS = [
     "mof_pack_frames", "mof_assemble_batch",
     "mof_spmv_batch", "mof_pcg_solve_batch", "mof_unpack_solution",
     "mof_tangent_to_xyz", "mof_vmax", "mof_singularity_flags", "mof_singularity_compact",
-    "mof_classify_singularities", "mof_winding_numbers", "mof_wave_speed", "mof_csv_write", "mof_csv_dims", "mof_csv_read",
+    "mof_classify_singularities", "mof_winding_numbers", "mof_wave_speed", "mof_rbf_fit", "mof_rbf_evaluate", "mof_csv_write", "mof_csv_dims", "mof_csv_read",
 ]
 
 
@@ -119,6 +119,10 @@ def _declare(lib):
     lib.mof_classify_singularities.argtypes = [c_int64, c_int64, c_int64] + [P] * 10 + [c_int64, c_int64] + [P] * 8
     lib.mof_winding_numbers.restype = c_int
     lib.mof_winding_numbers.argtypes = [c_int64, c_int64] + [P] * 5 + [c_int64, P, P, c_int] + [P] * 6
+    lib.mof_rbf_fit.restype = c_int
+    lib.mof_rbf_fit.argtypes = [c_int64, P, c_double, c_int64, P, c_int64, P, P, P, P, P]
+    lib.mof_rbf_evaluate.restype = c_int
+    lib.mof_rbf_evaluate.argtypes = [c_int64, c_int64, c_int64, P, P, c_double, P, c_int, P, c_int64, P]
     lib.mof_csv_write.restype = c_int
     lib.mof_csv_write.argtypes = [c_char_p, P, c_int64, c_int64, c_int]
     lib.mof_csv_dims.restype = c_int

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(CSRC, "libmof_b200.so")
 
-SOURCES = ["error.cpp", "pattern.cpp", "csvio.cpp", "geom.cu", "assemble.cu", "pcg.cu", "detect.cu", "wave.cu", "winding.cu"]
+SOURCES = ["error.cpp", "pattern.cpp", "csvio.cpp", "geom.cu", "assemble.cu", "pcg.cu", "detect.cu", "wave.cu", "winding.cu", "rbf.cu"]
 HEADERS = ["mof_error.h", "mof_bodies.h", "mof_common.cuh", os.path.join(INCLUDE, "mof_b200.h")]
 
 NVCC_FLAGS = [

@@ -431,4 +431,12 @@ MOF_HD double mof_dist3_body(const double* a, const double* b) {
     return sqrt(mof_dot3_plain(d, d));
 }
 
+// scipy.interpolate.Rbf multiquadric (scipy/interpolate/_rbf.py _h_multiquadric with cdist's Euclidean
+// norm): phi = sqrt((1/eps * |x - c|)^2 + 1); used by S2_interpolate.py:41-42.
+MOF_HD double mof_rbf_phi_body(const double* x, const double* c, double inv_eps) {
+    const double d[3] = {MOF_ADD(x[0], -c[0]), MOF_ADD(x[1], -c[1]), MOF_ADD(x[2], -c[2])};
+    const double s = MOF_MUL(inv_eps, sqrt(mof_dot3_plain(d, d)));
+    return sqrt(MOF_ADD(MOF_MUL(s, s), 1.0));
+}
+
 #endif  // MOF_BODIES_H

@@ -575,3 +575,52 @@ def winding_numbers(coordinates, triangles, singularity_points, V_now, e, max_le
                 break
         types[q] = flag
     return counts, types, wind
+
+
+# ----------------------------------------------------------------------------
+# RBF interpolation of electrode signals onto the surface (S2_interpolate.py:22-53,
+# S2_interpolate_phases.py:22-68; "next" row 4 of SURVEY 8f, the producer of the hot path's
+# input).  The arithmetic lives in scipy.interpolate.Rbf (legacy class, scipy 1.18.1 in this
+# image, not vendored by the reference) with its defaults: multiquadric phi(r) =
+# sqrt((r/eps)^2 + 1), eps = (prod(bounding-box edges) / m)^(1/n_edges), smooth = 0,
+# weights = solve(phi(pairwise distances), data), value = phi(distances to the centres) . weights.
+# ----------------------------------------------------------------------------
+def rbf_epsilon(centres):
+    """scipy/interpolate/_rbf.py Rbf.__init__: default epsilon."""
+    c = np.asarray(centres, dtype=np.float64)
+    edges = c.max(axis=0) - c.min(axis=0)
+    edges = edges[np.nonzero(edges)]
+    return float(np.power(np.prod(edges) / len(c), 1.0 / edges.size))
+
+
+def rbf_matrix(points, centres, eps):
+    d = points[:, None, :] - centres[None, :, :]
+    r = np.sqrt((d * d).sum(axis=2))
+    return np.sqrt((1.0 / eps * r) ** 2 + 1)
+
+
+def rbf_interpolate(centres, data, vertices, phase=False):
+    """S2:37-47 for all frames at once: data (T, m) real or complex -> (T, N); phase=True
+    returns np.angle of the (complex) interpolant like S2_interpolate_phases.py:51-52."""
+    c = np.asarray(centres, dtype=np.float64)
+    v = np.asarray(vertices, dtype=np.float64)
+    eps = rbf_epsilon(c)
+    A = rbf_matrix(c, c, eps)
+    W = np.linalg.solve(A, np.asarray(data).T)                              # (m, T)
+    out = (rbf_matrix(v, c, eps) @ W).T
+    return np.angle(out) if phase else out
+
+
+def electrode_phases(potentials):
+    """compute_phase_from_potentials, S2_interpolate_phases.py:58-68: scipy.signal.hilbert along the
+    LAST axis (the electrode axis of a (T, m) array, as the reference calls it), then the angle."""
+    x = np.asarray(potentials, dtype=np.float64)
+    n = x.shape[-1]
+    h = np.zeros(n)
+    if n % 2 == 0:
+        h[0] = h[n // 2] = 1
+        h[1:n // 2] = 2
+    else:
+        h[0] = 1
+        h[1:(n + 1) // 2] = 2
+    return np.angle(np.fft.ifft(np.fft.fft(x, axis=-1) * h, axis=-1))

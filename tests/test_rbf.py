@@ -1,0 +1,131 @@
+"""RBF interpolation of electrode signals onto the surface (S2_interpolate.py:22-53,
+S2_interpolate_phases.py:22-68; SURVEY 8f "next" row 4).  Goldens tests/golden/s2_*.npz come from
+the unmodified reference functions (make_golden_s2.py).  Tolerances: potentials 1e-10 of max|I|
+(the m x m multiquadric system has condition 1e3..1e5; LAPACK builds already differ by 1e-13),
+phases 1e-8 rad (wrapped)."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from oracle import mof_oracle as oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ("ico3_m20", "ico4_m61")
+TOL_POT, TOL_PHASE = 1e-10, 1e-8
+
+
+def _wrap(a):
+    return np.abs(np.angle(np.exp(1j * a)))
+
+
+def _gold(tag):
+    g = np.load(os.path.join(GOLD, "s2_" + tag + ".npz"))
+    return g, int(g["start"]), int(g["end"])
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_matches_reference(tag):
+    g, a, b = _gold(tag)
+    out = oracle.rbf_interpolate(g["electrodes"], g["data"][a:b], g["coordinates"])
+    assert np.abs(out - g["potentials"]).max() <= TOL_POT * np.abs(g["potentials"]).max()
+    ph = oracle.electrode_phases(g["data"])
+    assert np.abs(ph - g["electrode_phases"]).max() < 1e-12
+    out = oracle.rbf_interpolate(g["electrodes"], np.exp(1j * ph)[a:b], g["coordinates"], phase=True)
+    assert _wrap(out - g["phases"]).max() <= TOL_PHASE
+
+
+def test_oracle_matches_scipy_rbf():
+    from scipy.interpolate import Rbf
+    rng = np.random.default_rng(3)
+    c = rng.normal(size=(17, 3)) * [30, 20, 5]
+    v = rng.normal(size=(50, 3)) * [30, 20, 5]
+    d = rng.normal(size=(3, 17))
+    ref = np.array([Rbf(c[:, 0], c[:, 1], c[:, 2], f)(v[:, 0], v[:, 1], v[:, 2]) for f in d])
+    assert np.abs(oracle.rbf_interpolate(c, d, v) - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert oracle.rbf_epsilon(c) == Rbf(c[:, 0], c[:, 1], c[:, 2], d[0]).epsilon
+
+
+def test_host_helpers_match_reference():
+    from manifold_based_optical_flow_method_b200 import S2_interpolate as s2, S2_interpolate_phases as s2p
+    g, a, b = _gold("ico4_m61")
+    assert s2.rbf_epsilon(g["electrodes"]) == oracle.rbf_epsilon(g["electrodes"])
+    assert np.abs(s2p.compute_phase_from_potentials(g["data"]) - g["electrode_phases"]).max() < 1e-12
+    flat = g["electrodes"].copy()
+    flat[:, 2] = 7.0                                                  # planar grid: zero-length edge is dropped
+    assert s2.rbf_epsilon(flat) == oracle.rbf_epsilon(flat)
+
+
+# ------------------------------------------------------------------ GPU (through the C ABI)
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", CASES)
+def test_gpu_matches_reference(tag, tmp_path):
+    from manifold_based_optical_flow_method_b200 import S2_interpolate as s2, S2_interpolate_phases as s2p
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    g, a, b = _gold(tag)
+    surf = types.SimpleNamespace(points=g["coordinates"])               # all the reference reads of the surface (S2:36-37)
+    path = str(tmp_path / "interp.csv")
+    out = s2.interpolation(surf, g["data"], g["electrodes"], a, b, path, True)
+    assert out.shape == g["potentials"].shape
+    assert np.abs(out - g["potentials"]).max() <= TOL_POT * np.abs(g["potentials"]).max()
+    assert np.array_equal(cof.load_potentials(path), out)             # what S3 will read back
+    z = np.exp(1j * s2p.compute_phase_from_potentials(g["data"]))
+    out = s2p.interpolation(surf, z, g["electrodes"], a, b, path, False)
+    assert _wrap(out - g["phases"]).max() <= TOL_PHASE
+    assert out.min() >= -np.pi and out.max() <= np.pi
+
+
+@pytest.mark.gpu
+def test_gpu_ragged_sizes_against_scipy():
+    """sizes that are not multiples of the 64 x 64 tile or the 32-centre chunk; pivoting exercised by
+    a randomly ordered cloud; scipy.interpolate.Rbf (the reference's arithmetic) run live."""
+    from scipy.interpolate import Rbf
+    from manifold_based_optical_flow_method_b200 import S2_interpolate as s2
+    rng = np.random.default_rng(5)
+    for m, T, N in ((1, 1, 1), (2, 3, 5), (33, 65, 130), (97, 70, 1000), (128, 5, 63)):
+        c = rng.normal(size=(m, 3)) * [40, 30, 10] if m > 1 else np.array([[1.0, 2.0, 3.0]])
+        v = rng.normal(size=(N, 3)) * [40, 30, 10]
+        d = rng.normal(size=(T, m))
+        if m == 1:
+            with pytest.raises(ValueError):
+                s2.rbf_epsilon(c)
+            got = s2.rbf_interpolate(d, c, v, epsilon=2.0)
+            ref = np.array([Rbf(c[:, 0], c[:, 1], c[:, 2], f, epsilon=2.0)(v[:, 0], v[:, 1], v[:, 2]) for f in d])
+        else:
+            got = s2.rbf_interpolate(d, c, v)
+            ref = np.array([Rbf(c[:, 0], c[:, 1], c[:, 2], f)(v[:, 0], v[:, 1], v[:, 2]) for f in d])
+        assert got.shape == (T, N)
+        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), (m, T, N)
+    assert s2.rbf_interpolate(np.zeros((0, 4)), rng.normal(size=(4, 3)), rng.normal(size=(9, 3))).shape == (0, 9)
+
+
+@pytest.mark.gpu
+def test_gpu_properties_and_errors():
+    """interpolation property (the interpolant reproduces the data at the electrodes), linearity,
+    duplicated electrodes -> LinAlgError, feeding the device result straight into the solver."""
+    import torch
+    from manifold_based_optical_flow_method_b200 import S2_interpolate as s2, synthetic
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    rng = np.random.default_rng(9)
+    coords, tris, normals, areas = synthetic.pial_like(4)
+    sel = rng.choice(len(coords), 48, replace=False)
+    c = coords[sel] + rng.normal(0, 0.3, (48, 3))
+    d1, d2 = rng.normal(size=(12, 48)), rng.normal(size=(12, 48))
+    at = s2.rbf_interpolate(d1, c, c)
+    assert np.abs(at - d1).max() <= 1e-8 * np.abs(d1).max()
+    a, b, ab = (s2.rbf_interpolate(x, c, coords) for x in (d1, d2, 2.0 * d1 - 0.5 * d2))
+    assert np.abs(ab - (2.0 * a - 0.5 * b)).max() <= 1e-9 * np.abs(ab).max()
+    dup = c.copy()
+    dup[7] = dup[3]
+    with pytest.raises(np.linalg.LinAlgError):
+        s2.rbf_interpolate(d1, dup, coords)
+    with pytest.raises(ValueError):
+        s2.rbf_interpolate(np.exp(1j * d1), c, coords)                  # complex needs phase=True
+    # device-resident hand-over: interpolate -> solve without a host round trip
+    t_k = synthetic.time_axis(12, 512.0)
+    I_dev = s2.rbf_interpolate_device(synthetic.travelling_wave(coords, t_k, seed=2)[:, sel], c, coords)
+    a2, grad_w, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    V_dev, info = cof.solve_on_device(a2, I_dev, I_dev, t_k, 0.01, 0, 11)
+    V_ref, _ = cof.compute_velocity_field(1, 12, a2, grad_w, e, integ, tris, t_k, areas, 0.01, I_dev.cpu().numpy(), I_dev.cpu().numpy())
+    assert torch.equal(V_dev.cpu(), torch.from_numpy(np.asarray(V_ref)))
