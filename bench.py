@@ -399,6 +399,45 @@ def run_b200(args):
     except Exception as exc:                        # detection timing is auxiliary: never fail the bench line on it
         detection = {"error": repr(exc)}
 
+    # ---- upstream producer of the signal: RBF interpolation of 128 electrodes onto the mesh,
+    # S2_interpolate.py:22-53; auxiliary like the detection figure
+    interpolation = None
+    try:
+        from manifold_based_optical_flow_method_b200 import S2_interpolate as s2
+        m_el = 128
+        rng = np.random.default_rng(0)
+        cap = np.nonzero(coords[:, 2] > 0.3 * np.abs(coords).max())[0]
+        sel = cap[rng.choice(len(cap), m_el, replace=False)]
+        c_el = coords[sel] + rng.normal(0, 0.3, (m_el, 3))
+        d_el = I_host[:, sel].copy()
+        v_dev = torch.from_numpy(np.ascontiguousarray(coords)).to(dev)
+        I_rbf = torch.empty((T, N), dtype=torch.float64, device=dev)
+        rbf_ms = float("inf")
+        for rep in range(3):
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            s2.rbf_interpolate_device(d_el, c_el, v_dev, out=I_rbf)
+            d1.record()
+            torch.cuda.synchronize()
+            if rep:
+                rbf_ms = min(rbf_ms, d0.elapsed_time(d1))
+        interpolation = {"frames_per_s": T / (rbf_ms * 1e-3), "frames": T, "electrodes": m_el, "ms": rbf_ms,
+                         "tflops_fp64": 2.0 * T * N * m_el / (rbf_ms * 1e-3) / 1e12,
+                         "note": "mof_rbf_fit (matrix, LU, T solves) + mof_rbf_evaluate (GEMM-shaped, kernel matrix on the "
+                                 "fly), host electrode data in, (T, N) signal left in HBM; flops count the 2*T*N*m of the product only"}
+        if cpu is not None:
+            from scipy.interpolate import Rbf
+            tc = time.time()
+            n_cpu = 2
+            for f in d_el[:n_cpu]:
+                ref_frame = Rbf(c_el[:, 0], c_el[:, 1], c_el[:, 2], f)(coords[:, 0], coords[:, 1], coords[:, 2])
+            interpolation["cpu_frames_per_s"] = n_cpu / (time.time() - tc)
+            interpolation["cpu_sample"] = f"{n_cpu} frames of scipy.interpolate.Rbf as the reference calls it (S2:41-42), 1 process"
+            interpolation["max_abs_diff_vs_scipy"] = float(np.abs(I_rbf[n_cpu - 1].cpu().numpy() - ref_frame).max())
+        del I_rbf, v_dev
+    except Exception as exc:
+        interpolation = {"error": repr(exc)}
+
     # ---- end-to-end leg: host buffers in, host buffers out, through the reference-shaped API
     e2e = None
     if not args.no_e2e:
@@ -438,7 +477,7 @@ def run_b200(args):
                        "l2": "no flush: the per-step working set (1.17 GB of matrix values per 32-frame group) is >> 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), one process per GPU"},
             "clocks": clock_report, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "detection": detection,
+            "detection": detection, "interpolation": interpolation,
             "solver": {"converged": converged, "iterations_mean": float(np.mean(info.iterations)),
                        "iterations_max": int(np.max(info.iterations)), "relres_max": float(np.max(info.relres)),
                        "geometry_seconds": geom_s, "setup_seconds": time.time() - t0},
