@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--precond", default=None, choices=["ssor", "jacobi"], help="default: the package default")
     ap.add_argument("--omega", type=float, default=None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-transport", default="auto", choices=["auto", "shm", "nccl"],
+                    help="N > 1: how the fields reach rank 0's host memory (shared host array / NCCL gather + drain)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=None)
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-clock budget of the reference arm")
@@ -449,7 +451,8 @@ def run_b200(args):
             if world == 1:
                 V_k, _ = cof.compute_velocity_field(1, T, op, grad_w, e, integral, tris, t_k, areas, LAMBDA, I_host, I_host)
                 return V_k
-            return mdist.solve_shard_and_gather(op, I_host, I_host, t_k, LAMBDA, counts, gather="root")[0]
+            return mdist.solve_shard_and_gather(op, I_host, I_host, t_k, LAMBDA, counts, gather="root",
+                                                transport=args.e2e_transport)[0]
 
         out = e2e_step()                              # one warm-up pass (allocations, pinned staging)
         del out
@@ -463,6 +466,8 @@ def run_b200(args):
         e2e = {"value": world * n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * e2e_s / args.steps,
                "api": "compute_optical_flow.compute_velocity_field(numpy in, list of numpy out)" if world == 1 else
+                      "distributed.solve_shard_and_gather(numpy shard in; every rank drains its fields into one shared "
+                      "host array that rank 0 returns as numpy)" if args.e2e_transport != "nccl" else
                       "distributed.solve_shard_and_gather(numpy shard in; NCCL gather to rank 0; numpy out)"}
 
     if rank == 0:

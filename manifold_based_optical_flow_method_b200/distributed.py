@@ -2,11 +2,24 @@
 
 Frames are independent units (worker k reads only I_k[k], I_k_2[k+1], t_k[k], t_k[k+1];
 utils/compute_optical_flow.py:162-176), so rank r solves a contiguous range of frames with
-no data-path collective; the only exchange is the gather of the per-frame fields that
-replaces the reference's ``AsyncResult.get()`` loop (:190-191): one NCCL all-gather over
-NVLink of the (frames_r, 2N) fp64 shards.  The helpers are device-agnostic so the host
-logic is testable on CPU with the gloo backend (tests/test_distributed_cpu.py).
+no data-path collective; the only exchange is the delivery of the per-frame fields that
+replaces the reference's ``AsyncResult.get()`` loop (:190-191):
+
+* results wanted on the device: one NCCL all-gather (or gather to rank 0) over NVLink of the
+  (frames_r, 2N) fp64 shards;
+* results wanted on the host (what the reference's caller gets): every rank drains its own
+  shard through its own PCIe link straight into one array in shared host memory that all ranks
+  of the node map (``shared_host_rows``) -- no NVLink hop and no funnel through rank 0's PCIe
+  link; falls back to NCCL gather + drain on rank 0 when the ranks are not on one host.
+
+The helpers are device-agnostic so the host logic is testable on CPU with the gloo backend
+(tests/test_distributed_cpu.py).
 """
+import mmap
+import os
+import socket
+import uuid
+
 import numpy as np
 
 
@@ -68,13 +81,59 @@ def gather_rows(local, counts, group=None, root=None):
     return torch.cat([out[r, :counts[r]] for r in range(world)], dim=0)
 
 
-def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather="all", to_host=True):
+def same_host(group=None):
+    """True when every rank of the group runs on this host (collective call)."""
+    dist = _dist()
+    world = dist.get_world_size(group)
+    names = [None] * world
+    dist.all_gather_object(names, (socket.gethostname(), os.stat("/proc/self/ns/ipc").st_ino), group=group)
+    return all(n == names[0] for n in names)
+
+
+def shared_host_rows(rows, width, group=None):
+    """(rows, width) float64 array in anonymous shared memory (a memfd created by rank 0 and
+    handed to the other ranks over an abstract-namespace unix socket), mapped by every rank of
+    the group; all ranks must be on one host and call this together.  The memory goes away with
+    the last array that refers to it -- nothing is left in /dev/shm, whatever way a rank dies."""
+    dist = _dist()
+    world, me = dist.get_world_size(group), dist.get_rank(group)
+    nbytes = max(int(rows) * int(width) * 8, mmap.PAGESIZE)
+    token = [None]
+    if me == 0:
+        fd = os.memfd_create("mof_rows")
+        os.ftruncate(fd, nbytes)
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        token[0] = f"\0mof-rows-{os.getpid()}-{uuid.uuid4().hex}"
+        srv.bind(token[0])
+        srv.listen(world)
+    dist.broadcast_object_list(token, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if me == 0:
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            socket.send_fds(conn, [b"m"], [fd])
+            conn.close()
+        srv.close()
+    else:
+        conn = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        conn.connect(token[0])
+        _, fds, _, _ = socket.recv_fds(conn, 1, 1)
+        conn.close()
+        fd = fds[0]
+    mm = mmap.mmap(fd, nbytes)                       # MAP_SHARED; the mapping outlives the descriptor
+    os.close(fd)
+    return np.frombuffer(mm, dtype=np.float64, count=int(rows) * int(width)).reshape(int(rows), int(width))
+
+
+def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather="all", to_host=True, transport="auto"):
     """Multi-GPU entry point: this rank solves the frames of its shard -- ``I_shard`` /
     ``I2_shard`` hold rows k0 .. k1 (one-frame halo: frame k1-1 reads I2[k1]) and
-    ``t_k_shard`` the matching k1-k0+1 time stamps -- then the per-frame fields are gathered
-    over NCCL.  gather: "all" (every rank gets all frames), "root" (rank 0 only; other ranks
+    ``t_k_shard`` the matching k1-k0+1 time stamps -- then the per-frame fields are
+    delivered.  gather: "all" (every rank gets all frames), "root" (rank 0 only; other ranks
     get None) or "none" (each rank keeps its shard).  -> (V, SolveInfo); V is a numpy array
-    if to_host else a device tensor."""
+    if to_host else a device tensor.  transport (host delivery with gather "all" / "root"):
+    "shm" -- every rank drains its shard into one shared host array (with "all" every rank
+    returns the SAME memory); "nccl" -- gather over NVLink, rank 0 (or every rank) drains all
+    frames; "auto" -- "shm" when all ranks share a host, else "nccl"."""
     import torch
     from . import compute_optical_flow as cof
     from .solver import SolveInfo
@@ -83,7 +142,12 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
     N = op.n_vertices
     world = len(counts)
     width = 2 * N
-    # Host delivery with equal shards: gather every finished batch over NCCL on a side stream and
+    if transport not in ("auto", "shm", "nccl"):
+        raise ValueError("transport must be 'auto', 'shm' or 'nccl'")
+    if to_host and world > 1 and gather in ("all", "root") and transport != "nccl":
+        if transport == "shm" or same_host():
+            return _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather, r, n_loc, width)
+    # Host delivery over NCCL with equal shards: gather every finished batch over NCCL on a side stream and
     # drain it to the host while the next batch is being solved.
     pipelined = to_host and world > 1 and gather in ("all", "root") and len(set(counts)) == 1 and n_loc > 0
     V_host = None
@@ -147,9 +211,37 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
     return (V_all.cpu().numpy() if to_host else V_all), info
 
 
-def compute_velocity_field_sharded(op, n_frames, t_k, lambda_, I_k, I_k_2, gather="all", to_host=True):
+def _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather, r, n_loc, width):
+    """Host delivery through shared memory: each rank's finished batches are drained (side stream,
+    pinned staging, copy threads) into its own rows of the shared array while the next batch is
+    being solved; the per-frame solve report is the only thing that crosses NCCL."""
+    import torch
+    from . import compute_optical_flow as cof
+    from .solver import SolveInfo
+    V_host = shared_host_rows(sum(counts), width)
+    start = int(np.sum(counts[:r]))
+    mine = V_host[start:start + n_loc]
+    if n_loc > 0:
+        solver = cof._solver(op)
+        drain = solver.drain(width)
+        I_dev, I2_dev = cof._upload_signals(op, I_shard, I2_shard, n_loc)
+        _, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc,
+                                      on_batch=lambda k0, k1, Vd: drain.submit(Vd, mine[k0:k1]))
+        drain.finish()
+        rep = np.stack([info.iterations.astype(np.float64), info.relres, info.status.astype(np.float64)], axis=1)
+    else:
+        info, rep = None, np.zeros((0, 3))
+    # the report gather also orders every rank's writes before the receivers' return
+    rep_all = gather_rows(torch.from_numpy(rep).to(op.device), counts, root=0 if gather == "root" else None)
+    if rep_all is None:
+        return None, (SolveInfo(info.iterations, info.relres, info.status) if info is not None else None)
+    rep_np = rep_all.cpu().numpy()
+    return V_host, SolveInfo(rep_np[:, 0].astype(np.int32), rep_np[:, 1].copy(), rep_np[:, 2].astype(np.int32))
+
+
+def compute_velocity_field_sharded(op, n_frames, t_k, lambda_, I_k, I_k_2, gather="all", to_host=True, transport="auto"):
     """compute_velocity_field under torchrun: every rank holds the full (T,N) signal like
-    the reference's processes do, solves frames shard_range(...) and all-gathers.
+    the reference's processes do, solves frames shard_range(...) and delivers all of them.
     -> (V (n_frames, 2N), SolveInfo)"""
     world, r = world_size(), rank()
     counts = shard_counts(n_frames, world)
@@ -157,4 +249,5 @@ def compute_velocity_field_sharded(op, n_frames, t_k, lambda_, I_k, I_k_2, gathe
     same = I_k_2 is I_k
     I_sh = I_k[k0:k1 + 1]
     I2_sh = I_sh if same else I_k_2[k0:k1 + 1]
-    return solve_shard_and_gather(op, I_sh, I2_sh, t_k[k0:k1 + 1], lambda_, counts, gather=gather, to_host=to_host)
+    return solve_shard_and_gather(op, I_sh, I2_sh, t_k[k0:k1 + 1], lambda_, counts, gather=gather, to_host=to_host,
+                                  transport=transport)

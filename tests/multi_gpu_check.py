@@ -4,7 +4,7 @@
         --master-port 29511 tests/multi_gpu_check.py
 
 Every rank calls the reference-shaped compute_velocity_field with the full signal; frames are
-sharded by rank, solved, and all-gathered over NCCL.  The result must equal the oracle to the
+sharded by rank, solved, and delivered (shared host memory by default, NCCL gather as the alternative).  The result must equal the oracle to the
 parity tolerance and -- because every frame's arithmetic is lane-private and its reductions
 are deterministic -- be bit-identical to what a single GPU computes for the same frames.
 """
@@ -48,12 +48,24 @@ def main():
     V_loc, _ = cof.solve_on_device(a2, I_dev, I_dev, t_k, 0.01, 0, T - 1)
     assert torch.equal(V_loc[k0:k1], h[k0:k1]), "sharded result differs from the single-GPU result"
     assert torch.equal(V_loc, h), "sharding changed a frame's bits"
-    # root gather
-    out, info = mdist.compute_velocity_field_sharded(a2, T - 1, t_k, 0.01, I, I, gather="root")
+    # both host transports (shared host memory / NCCL gather + drain), to every rank and to rank 0 only
+    for transport in ("shm", "nccl"):
+        out, info = mdist.compute_velocity_field_sharded(a2, T - 1, t_k, 0.01, I, I, gather="all", transport=transport)
+        assert np.array_equal(out, V), transport
+        assert len(info.iterations) == T - 1 and info.converged
+        out, info = mdist.compute_velocity_field_sharded(a2, T - 1, t_k, 0.01, I, I, gather="root", transport=transport)
+        if rank == 0:
+            assert np.array_equal(out, V), transport
+            assert len(info.iterations) == T - 1
+        else:
+            assert out is None
+    # equal shards (64 frames): the pipelined NCCL path
+    out, _ = mdist.compute_velocity_field_sharded(a2, 64, t_k, 0.01, I, I, gather="root", transport="nccl")
     if rank == 0:
-        assert np.array_equal(out, V)
-    else:
-        assert out is None
+        assert np.array_equal(out, V[:64])
+    # results that stay on the device
+    out, _ = mdist.compute_velocity_field_sharded(a2, T - 1, t_k, 0.01, I, I, gather="all", to_host=False)
+    assert torch.equal(out, h)
     if rank == 0:
         a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
         for k in (0, 17, 35, 69):

@@ -46,6 +46,17 @@ def _worker(rank, world, port, n_frames, width, out_dir):
             assert torch.equal(got_root, full)
         else:
             assert got_root is None
+        # host delivery through shared memory: every rank writes its rows, everyone sees all of them
+        assert mdist.same_host()
+        shared = mdist.shared_host_rows(n_frames, width)
+        assert shared.shape == (n_frames, width) and shared.dtype == np.float64
+        shared[k0:k1] = full[k0:k1].numpy()
+        dist.barrier()
+        assert np.array_equal(shared, full.numpy())
+        dist.barrier()
+        empty = mdist.shared_host_rows(0, width)
+        assert empty.shape == (0, width)
+        del shared, empty
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     finally:
         dist.destroy_process_group()
