@@ -43,6 +43,7 @@ settings = {
     "batch_groups": None,          # None = sized from free device memory (<= 32 groups of 32 frames)
     "streams": None,               # None = solver default (1; 2 = batches on two concurrent streams)
     "allow_unconverged": False,
+    "pinned_results": True,        # host results land in pinned memory by direct DMA (False: pageable numpy via staging)
     "device": None,                # None = current CUDA device
 }
 
@@ -127,10 +128,15 @@ def solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n):
     """solve_on_device for frames 0..n-1 with the results drained to a host array batch by
     batch, overlapped with the solve of the next batch.  -> (V (n, 2N) numpy, SolveInfo)"""
     s = _solver(op)
-    V = np.empty((n, 2 * op.n_vertices), dtype=np.float64)
     drain = s.drain(2 * op.n_vertices)
-    _, info = solve_on_device(op, I_dev, I2_dev, t_k, lambda_, 0, n,
-                              on_batch=lambda k0, k1, Vd: drain.submit(Vd, V[k0:k1]))
+    if settings["pinned_results"]:
+        from .solver import pinned_rows
+        V_t, V = pinned_rows(s.torch, n, 2 * op.n_vertices)
+        on_batch = lambda k0, k1, Vd: drain.submit_pinned(Vd, V_t[k0:k1])
+    else:
+        V = np.empty((n, 2 * op.n_vertices), dtype=np.float64)
+        on_batch = lambda k0, k1, Vd: drain.submit(Vd, V[k0:k1])
+    _, info = solve_on_device(op, I_dev, I2_dev, t_k, lambda_, 0, n, on_batch=on_batch)
     drain.finish()
     return V, info
 

@@ -278,6 +278,33 @@ def test_ragged_frame_counts(n_frames, mods):
         assert rel_l2(V_k[k], Vo) <= V_TOL
 
 
+def test_pinned_and_pageable_host_delivery_agree(mods):
+    """Results delivered by direct DMA into pinned memory (default) and through the staged drain into
+    pageable memory are the same bits; a held result is not overwritten by the next call."""
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(2)
+    T = 71
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=5)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    cof.settings["batch_groups"] = 1
+    try:
+        assert cof.settings["pinned_results"] is True
+        V_pin, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+        keep = np.array(V_pin)
+        cof.settings["pinned_results"] = False
+        V_page, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+        cof.settings["pinned_results"] = True
+        V_other, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, 2.0 * I, 2.0 * I)
+    finally:
+        cof.settings["batch_groups"] = None
+        cof.settings["pinned_results"] = True
+    assert np.array_equal(np.array(V_page), keep)
+    assert np.array_equal(np.array(V_pin), keep)            # still intact while V_other exists
+    assert not np.array_equal(np.array(V_other), keep)
+    assert V_pin[0].flags.writeable and V_pin[0].dtype == np.float64
+
+
 def test_concurrent_streams_match_single_stream(mods):
     """Batches dealt to two concurrent solve streams give bit-identical fields to the single-stream
     path (every frame's arithmetic is private to its lane; reductions are deterministic)."""
