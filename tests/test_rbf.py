@@ -83,7 +83,8 @@ def test_gpu_ragged_sizes_against_scipy():
     from scipy.interpolate import Rbf
     from manifold_based_optical_flow_method_b200 import S2_interpolate as s2
     rng = np.random.default_rng(5)
-    for m, T, N in ((1, 1, 1), (2, 3, 5), (33, 65, 130), (97, 70, 1000), (128, 5, 63)):
+    # m = 400 exceeds the shared-memory-resident kernel and takes the streaming one (condition 3e8: looser bound)
+    for m, T, N in ((1, 1, 1), (2, 3, 5), (33, 65, 130), (97, 70, 1000), (128, 5, 63), (400, 70, 200)):
         c = rng.normal(size=(m, 3)) * [40, 30, 10] if m > 1 else np.array([[1.0, 2.0, 3.0]])
         v = rng.normal(size=(N, 3)) * [40, 30, 10]
         d = rng.normal(size=(T, m))
@@ -96,7 +97,12 @@ def test_gpu_ragged_sizes_against_scipy():
             got = s2.rbf_interpolate(d, c, v)
             ref = np.array([Rbf(c[:, 0], c[:, 1], c[:, 2], f)(v[:, 0], v[:, 1], v[:, 2]) for f in d])
         assert got.shape == (T, N)
-        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), (m, T, N)
+        assert np.abs(got - ref).max() <= (1e-9 if m < 400 else 1e-7) * np.abs(ref).max(), (m, T, N)
+        if m in (97, 400):                                            # phase mode of both evaluation kernels
+            z = np.exp(1j * rng.uniform(-np.pi, np.pi, size=(T, m)))
+            got = s2.rbf_interpolate(z, c, v, phase=True)
+            want = oracle.rbf_interpolate(c, z, v, phase=True)
+            assert _wrap(got - want).max() <= (1e-7 if m < 400 else 1e-5), (m, "phase")
     assert s2.rbf_interpolate(np.zeros((0, 4)), rng.normal(size=(4, 3)), rng.normal(size=(9, 3))).shape == (0, 9)
 
 
