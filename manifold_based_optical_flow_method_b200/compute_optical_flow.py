@@ -99,6 +99,10 @@ def _upload_signals(op, I_k, I_k_2, n, first=0):
     N = op.n_vertices
 
     def rows(a, lo, hi, name):
+        if torch.is_tensor(a):                       # torch input (CPU or already on a GPU): no numpy detour
+            if a.ndim != 2 or a.shape[1] != N or a.shape[0] < hi:
+                raise ValueError(f"{name} must have shape (>= {hi}, {N}), got {tuple(a.shape)}")
+            return a[lo:hi].to(device=op.device, dtype=torch.float64).contiguous()
         if isinstance(a, (list, tuple)):
             a = np.asarray(a[lo:hi], dtype=np.float64)
             lo, hi = 0, len(a)

@@ -305,6 +305,23 @@ def test_pinned_and_pageable_host_delivery_agree(mods):
     assert V_pin[0].flags.writeable and V_pin[0].dtype == np.float64
 
 
+def test_torch_tensor_inputs(mods):
+    """I_k may be a torch tensor (CPU or CUDA, float32 is promoted) as well as numpy or a list of rows."""
+    import torch
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(2)
+    T = 5
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=6)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    ref, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    for form in (torch.from_numpy(I), torch.from_numpy(I).cuda(), [row for row in I]):
+        got, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, form, form)
+        assert np.array_equal(np.array(got), np.array(ref))
+    with pytest.raises(ValueError):
+        cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, torch.zeros(T, 7), torch.zeros(T, 7))
+
+
 def test_concurrent_streams_match_single_stream(mods):
     """Batches dealt to two concurrent solve streams give bit-identical fields to the single-stream
     path (every frame's arithmetic is private to its lane; reductions are deterministic)."""
