@@ -312,7 +312,32 @@ def find_singularity_points_and_classify_for_all_Vk(V_k_coord, coordinates, tria
     return pts, cls
 
 
+def classify_critical_point(jacobian_matrix):
+    """Reference :463-498 for one 2x2 matrix (host-side convenience; the per-point classes of a whole
+    recording come from ``classify_singularities`` on the GPU with the same rule)."""
+    J = np.asarray(jacobian_matrix, dtype=np.float64).reshape(2, 2)
+    trace = J[0, 0] + J[1, 1]
+    det = J[0, 0] * J[1, 1] - J[0, 1] * J[1, 0]
+    if det > 0:
+        return "Node" if trace ** 2 > 4 * det else "Focus"
+    return "Saddle" if det < 0 else "Indeterminate"
+
+
+def analyze_classification(classification):
+    """Reference :501-527: prints the Focus / Saddle / Node totals over all frames (like the reference,
+    anything that is neither Focus nor Saddle counts as Node); also returns them."""
+    counts = {"Focus": 0, "Saddle": 0, "Node": 0}
+    for frame in classification:
+        for kind in frame:
+            counts[kind if kind in ("Focus", "Saddle") else "Node"] += 1
+    print(f"Focus: {counts['Focus']}")
+    print(f"Saddle: {counts['Saddle']}")
+    print(f"Node: {counts['Node']}")
+    return counts
+
+
 __all__ = ["process_V_k", "speed_magnitude", "find_singularity_points", "find_singularity_points_for_all_Vk",
+           "classify_critical_point", "analyze_classification",
            "detect_singularities", "detect_singularities_device", "tangent_to_xyz_device", "Singularities",
            "find_singularity_points_and_classify_for_all_Vk", "classify_singularities", "mesh_adjacency", "Classified",
            "CLASS_NAMES"]

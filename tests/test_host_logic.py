@@ -383,3 +383,16 @@ def test_product_refuses_to_run_without_cuda():
         compute_optical_flow.compute_geometrical_quantities(coords, normals, tris, areas)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         find_singularity_point.process_V_k(np.zeros((1, 84)), np.zeros((42, 2, 3)))
+
+
+def test_classification_host_helpers(capsys):
+    """classify_critical_point / analyze_classification (reference fsp:463-527) against the oracle's rule."""
+    from manifold_based_optical_flow_method_b200 import find_singularity_point as fsp
+    from oracle import mof_oracle
+    rng = np.random.default_rng(0)
+    for J in list(rng.normal(size=(200, 2, 2))) + [np.zeros((2, 2)), np.eye(2), np.array([[0.0, 1.0], [-1.0, 0.0]]),
+                                                   np.array([[np.nan, 0.0], [0.0, 1.0]])]:
+        assert fsp.classify_critical_point(J) == mof_oracle.CLASS_NAMES[mof_oracle.classify(J)]
+    got = fsp.analyze_classification([["Focus", "Saddle"], [], ["Node", "Indeterminate", "Saddle"]])
+    assert got == {"Focus": 1, "Saddle": 2, "Node": 2}
+    assert capsys.readouterr().out == "Focus: 1\nSaddle: 2\nNode: 2\n"
