@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=1000, help="frames of signal per GPU (frames-1 solves per step)")
     ap.add_argument("--batch-groups", type=int, default=None)
     ap.add_argument("--tol", type=float, default=1e-12)
-    ap.add_argument("--precond", default=None, choices=["ssor", "jacobi"], help="default: the package default")
+    ap.add_argument("--precond", default=None, choices=["ssor", "ssor_level", "jacobi"], help="default: the package default")
     ap.add_argument("--omega", type=float, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-transport", default="auto", choices=["auto", "shm", "nccl"],
@@ -330,12 +330,18 @@ def run_b200(args):
         per_frame = {"sweep_back": 16.0 * (nb - N) + 96.0 * N, "sweep_fwd": 16.0 * (nb - N) + 48.0 * N,
                      "update": 64.0 * N}
         dom_name = "sweep_back_kernel<0> + sweep_fwd_kernel<0> (Eisenstat SSOR operator, all colours of one iteration)"
+        if solver.precond == "ssor_level":
+            per_frame["sweep_fwd"] += 16.0 * N          # per-row shares of p'Ap: written by the sweep, read by level_dot_kernel
+            dom_name = ("level_back_kernel<0> + level_fwd_kernel<0> + level_dot_kernel (Eisenstat SSOR operator, "
+                        f"{op.pattern.n_levels} dependency levels per sweep, one launch per level)")
         dom_bytes = fl * (per_frame["sweep_back"] + per_frame["sweep_fwd"]) + 2 * idx_bytes
         dom_ms = prof.ms_spmv + prof.ms_pupdate
         others = {"sweep_back (all colours)": {"achieved": gbs(fl * per_frame["sweep_back"] + idx_bytes, prof.ms_spmv), "avg_ms": prof.ms_spmv / smp},
                   "sweep_fwd (all colours)": {"achieved": gbs(fl * per_frame["sweep_fwd"] + idx_bytes, prof.ms_pupdate), "avg_ms": prof.ms_pupdate / smp},
                   "update_kernel": {"achieved": gbs(fl * per_frame["update"], prof.ms_update), "avg_ms": prof.ms_update / smp}}
         try:
+            if solver.precond == "ssor_level":
+                raise KeyError("no ncu capture of the level kernels yet")
             with open(os.path.join(ROOT, "profiles", "sweeps_traffic.json")) as fh:
                 traffic_val = json.load(fh)["dram_bytes_per_frame_iteration"] * fl / smp
         except Exception:
@@ -477,8 +483,9 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "n_vertices": N, "n_faces": len(tris), "n_blocks": nb,
                        "frames_per_step": world * n, "batch_frames": solver.batch_groups * 32,
-                       "preconditioner": solver.precond + (f" (omega={solver.omega})" if solver.precond == "ssor" else ""),
-                       "ordering": "block multicolour (RCB patches of 64)" if op.pattern.n_colors else "Cuthill-McKee",
+                       "preconditioner": solver.precond + (f" (omega={solver.omega})" if solver.ssor else ""),
+                       "ordering": "block multicolour (RCB patches of 64)" if op.pattern.n_colors else
+                                   (f"level-scheduled Cuthill-McKee ({op.pattern.n_levels} levels)" if op.pattern.n_levels else "Cuthill-McKee"),
                        "l2": "no flush: the per-step working set (1.17 GB of matrix values per 32-frame group) is >> 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), one process per GPU"},
             "clocks": clock_report, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

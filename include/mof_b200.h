@@ -67,13 +67,20 @@ typedef struct mof_pattern mof_pattern;     /* opaque host object */
  *          2 = block multicolour: patches of MOF_TILE_ROWS vertices (recursive coordinate
  *              bisection of `coords`, host (n_vertices,3) double, required), patch graph
  *              greedily coloured, numbering colour-major (SSOR sweeps run colour by colour,
- *              sequentially inside a patch).  coords may be NULL for reorder 0/1.
+ *              sequentially inside a patch).  coords may be NULL for reorder 0/1/3.
+ *          3 = level-scheduled natural order: the Cuthill-McKee order regrouped by dependency level
+ *              (level(v) = 1 + max level of the neighbours before v), numbering level-major.  Same
+ *              Gauss-Seidel splitting as Cuthill-McKee, but the rows of a level are independent and
+ *              contiguous: the SSOR sweeps run level by level, one warp per row.
  * Errors: vertex id out of range, a face with a repeated vertex. */
 int mof_pattern_create(int64_t n_vertices, int64_t n_faces, const int64_t* triangles,
                        int reorder, const double* coords, mof_pattern** out);
 /* n_colors (0 unless reorder = 2) and color_tile_ptr[n_colors+1]: tiles (= patches of
  * MOF_TILE_ROWS consecutive internal rows) [ptr[c], ptr[c+1]) carry colour c. */
 int mof_pattern_colors(const mof_pattern* p, int32_t* n_colors, int32_t* color_tile_ptr);
+/* Number of dependency levels (0 unless reorder = 3); level_ptr (may be NULL), n_levels+1 entries:
+ * internal rows [ptr[l], ptr[l+1]) form level l. */
+int32_t mof_pattern_levels(const mof_pattern* p, int32_t* level_ptr);
 void mof_pattern_destroy(mof_pattern* p);
 int64_t mof_pattern_num_blocks(const mof_pattern* p);    /* N + 2E                         */
 int64_t mof_pattern_num_contrib(const mof_pattern* p);   /* 9 F (ordered vertex pairs)      */
@@ -107,6 +114,10 @@ typedef struct {
     /* block-multicolour ordering (reorder = 2), host-side launch metadata; n_colors = 0 otherwise */
     int32_t n_colors;
     int32_t color_tile_ptr[MOF_MAX_COLORS + 1];
+    /* level-scheduled ordering (reorder = 3): HOST array of n_levels+1 row offsets; n_levels = 0 otherwise */
+    int32_t n_levels;
+    int32_t reserved_;
+    const int32_t* level_ptr;
 } mof_mesh_dev;
 
 typedef struct {

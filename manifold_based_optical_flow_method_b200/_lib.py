@@ -23,7 +23,7 @@ STATUS_CONVERGED, STATUS_MAXITER, STATUS_BREAKDOWN, STATUS_ZERO_RHS = 0, 1, 2, 3
 EXPORTS = [
     "mof_last_error_string", "mof_version",
     "mof_pattern_create", "mof_pattern_destroy", "mof_pattern_num_blocks", "mof_pattern_num_contrib",
-    "mof_pattern_max_row_blocks", "mof_pattern_bandwidth", "mof_pattern_export", "mof_pattern_colors",
+    "mof_pattern_max_row_blocks", "mof_pattern_bandwidth", "mof_pattern_export", "mof_pattern_colors", "mof_pattern_levels",
     "mof_num_tiles", "mof_state_ints",
     "mof_geom_basis", "mof_geom_gradw", "mof_geom_a2",
     "mof_pack_frames", "mof_assemble_batch",
@@ -47,6 +47,7 @@ class MeshDev(Structure):
         ("cptr", c_void_p), ("centry", c_void_p), ("tri", c_void_p),
         ("e", c_void_p), ("grad_w", c_void_p), ("integral", c_void_p), ("areas", c_void_p), ("a2v", c_void_p),
         ("n_colors", c_int32), ("color_tile_ptr", c_int32 * (MAX_COLORS + 1)),
+        ("n_levels", c_int32), ("reserved_", c_int32), ("level_ptr", c_void_p),     # level_ptr: HOST int32[n_levels+1]
     ]
 
 
@@ -79,6 +80,8 @@ def _declare(lib):
     lib.mof_version.restype = c_int
     lib.mof_pattern_create.restype = c_int
     lib.mof_pattern_create.argtypes = [c_int64, c_int64, P, c_int, P, POINTER(c_void_p)]
+    lib.mof_pattern_levels.restype = c_int32
+    lib.mof_pattern_levels.argtypes = [P, P]
     lib.mof_pattern_colors.restype = c_int
     lib.mof_pattern_colors.argtypes = [P, POINTER(c_int32), P]
     lib.mof_pattern_destroy.restype = None

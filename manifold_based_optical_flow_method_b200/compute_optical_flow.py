@@ -31,15 +31,16 @@ import numpy as np
 
 from . import _lib
 from .mesh import MeshOperator
-from .solver import (DEFAULT_MAX_ITER, DEFAULT_OMEGA, DEFAULT_PRECOND, DEFAULT_TOL, SolveInfo, UnconvergedError,
-                     VelocitySolver, frame_dt)
+from .solver import (DEFAULT_MAX_ITER, DEFAULT_OMEGA, DEFAULT_OMEGA_LEVEL, DEFAULT_PRECOND, DEFAULT_TOL, REORDER_OF,
+                     SolveInfo, UnconvergedError, VelocitySolver, frame_dt)
 
 # solver settings (module-level so the reference's positional signatures stay untouched)
 settings = {
     "tol": DEFAULT_TOL,
     "max_iter": DEFAULT_MAX_ITER,
-    "precond": DEFAULT_PRECOND,    # "ssor": block-multicolour SSOR (Eisenstat form); "jacobi": 2x2 block Jacobi
-    "omega": DEFAULT_OMEGA,        # SSOR relaxation factor
+    "precond": DEFAULT_PRECOND,    # "ssor": block-multicolour SSOR (Eisenstat form); "ssor_level": the same on the
+                                   # level-scheduled natural ordering; "jacobi": 2x2 block Jacobi
+    "omega": None,                 # SSOR relaxation factor; None = 1.4 ("ssor") / 1.85 ("ssor_level")
     "batch_groups": None,          # None = sized from free device memory (<= 32 groups of 32 frames)
     "streams": None,               # None = solver default (1; 2 = batches on two concurrent streams)
     "allow_unconverged": False,
@@ -57,7 +58,7 @@ def compute_geometrical_quantities(coordinates, normals, triangles, areas):
     # the vertex numbering is chosen for the preconditioner: colour-major patches for the SSOR
     # sweeps, Cuthill-McKee (smallest gather window) for block Jacobi
     op = MeshOperator(coordinates, normals, triangles, areas, device=settings["device"],
-                      reorder=2 if settings["precond"] == "ssor" else 1)
+                      reorder=REORDER_OF[settings["precond"]])
     execution_time = time.time() - start
     return op, op.grad_w, op.e, op.integral_wi_wj, execution_time
 
@@ -72,11 +73,16 @@ def _operator(a2, triangles):
 
 def _solver(op):
     key = id(op)
-    precond = settings["precond"] if op.pattern.n_colors > 0 else "jacobi"
-    omega = float(settings["omega"])
+    precond = "ssor" if op.pattern.n_colors > 0 else ("ssor_level" if op.pattern.n_levels > 0 else "jacobi")
+    if settings["precond"] == "jacobi":
+        precond = "jacobi"          # block Jacobi runs on any numbering
+    omega = settings["omega"]
+    if omega is None:
+        omega = DEFAULT_OMEGA_LEVEL if precond == "ssor_level" else DEFAULT_OMEGA
+    omega = float(omega)
     s = _solvers.get(key)
     streams = settings["streams"]
-    if s is None or s.op is not op or s.precond != precond or (precond == "ssor" and s.omega != omega) \
+    if s is None or s.op is not op or s.precond != precond or (precond != "jacobi" and s.omega != omega) \
             or (settings["batch_groups"] is not None and s.batch_groups != settings["batch_groups"]) \
             or (streams is not None and s.n_streams != streams):
         _solvers.clear()           # one mesh at a time keeps device memory bounded

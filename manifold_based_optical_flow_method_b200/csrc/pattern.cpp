@@ -23,6 +23,7 @@ struct mof_pattern {
     int64_t N = 0, F = 0;
     std::vector<int32_t> perm, rowptr, col, diag, cptr, centry, tri;
     std::vector<int32_t> color_tile_ptr;     // block-multicolor ordering only: tiles of colour c
+    std::vector<int32_t> level_ptr;          // level-scheduled ordering only: rows of dependency level l
     int64_t max_row = 0, bandwidth = 0;
 };
 
@@ -158,6 +159,34 @@ void block_multicolor(int64_t N, const double* xyz, const std::vector<int64_t>& 
     }
 }
 
+// Level-scheduled natural ordering for the SSOR sweeps: level(v) = 1 + max level of the neighbours
+// that precede v in the Cuthill-McKee order; numbering level-major, Cuthill-McKee rank inside a
+// level.  Every edge keeps its orientation (an earlier neighbour sits in a strictly lower level),
+// so the Gauss-Seidel splitting -- and with it the SSOR preconditioner -- is exactly the one of the
+// Cuthill-McKee order, while the rows of one level are mutually independent and contiguous.
+void level_schedule(int64_t N, const std::vector<int64_t>& aptr, const std::vector<int32_t>& adj,
+                    const std::vector<int32_t>& cm, std::vector<int32_t>& perm, std::vector<int32_t>& level_ptr) {
+    std::vector<int32_t> rank(N), lev(N, 0);
+    for (int64_t q = 0; q < N; ++q) rank[cm[q]] = int32_t(q);
+    int32_t nlev = 0;
+    for (int64_t q = 0; q < N; ++q) {
+        const int32_t v = cm[q];
+        int32_t l = 0;
+        for (int64_t e = aptr[v]; e < aptr[v + 1]; ++e) {
+            const int32_t r = rank[adj[e]];
+            if (r < q) l = std::max(l, lev[r] + 1);
+        }
+        lev[q] = l;
+        nlev = std::max(nlev, l + 1);
+    }
+    level_ptr.assign(size_t(nlev) + 1, 0);
+    for (int64_t q = 0; q < N; ++q) level_ptr[lev[q] + 1]++;
+    for (int32_t l = 0; l < nlev; ++l) level_ptr[l + 1] += level_ptr[l];
+    std::vector<int32_t> fill(level_ptr.begin(), level_ptr.end() - 1);
+    perm.assign(N, 0);
+    for (int64_t q = 0; q < N; ++q) perm[fill[lev[q]]++] = cm[q];
+}
+
 }  // namespace
 
 extern "C" int mof_pattern_create(int64_t N, int64_t F, const int64_t* triangles, int reorder,
@@ -226,6 +255,10 @@ extern "C" int mof_pattern_create(int64_t N, int64_t F, const int64_t* triangles
                 std::vector<int32_t> bm;
                 block_multicolor(N, coords, aptr, adj, cm_rank, bm, P->color_tile_ptr);
                 P->perm.swap(bm);
+            } else if (reorder == 3) {
+                std::vector<int32_t> lv;
+                level_schedule(N, aptr, adj, P->perm, lv, P->level_ptr);
+                P->perm.swap(lv);
             }
         } else {
             for (int64_t v = 0; v < N; ++v) P->perm[v] = int32_t(v);
@@ -298,6 +331,13 @@ extern "C" int mof_pattern_colors(const mof_pattern* p, int32_t* n_colors, int32
     if (color_tile_ptr)
         for (int32_t c = 0; c <= nc && nc > 0; ++c) color_tile_ptr[c] = p->color_tile_ptr[c];
     return 0;
+}
+
+extern "C" int32_t mof_pattern_levels(const mof_pattern* p, int32_t* level_ptr) {
+    if (!p) return mof_set_error(-1, "mof_pattern_levels: NULL pattern");
+    const int32_t nl = p->level_ptr.empty() ? 0 : int32_t(p->level_ptr.size()) - 1;
+    if (level_ptr && nl > 0) std::memcpy(level_ptr, p->level_ptr.data(), p->level_ptr.size() * sizeof(int32_t));
+    return nl;
 }
 
 extern "C" int mof_pattern_export(const mof_pattern* p, int32_t* perm, int32_t* rowptr, int32_t* col,

@@ -31,7 +31,8 @@ class Pattern:
     n_vertices, n_faces, n_blocks, n_contrib, max_row_blocks, bandwidth."""
 
     def __init__(self, n_vertices, triangles, reorder=True, coordinates=None):
-        """reorder: False/0 identity, True/1 Cuthill-McKee, 2 block multicolour (needs coordinates)."""
+        """reorder: False/0 identity, True/1 Cuthill-McKee, 2 block multicolour (needs coordinates),
+        3 level-scheduled Cuthill-McKee (rows grouped by dependency level)."""
         lib = _lib.load()
         tri64 = np.ascontiguousarray(np.asarray(triangles), dtype=np.int64)
         if tri64.ndim != 2 or tri64.shape[1] != 3:
@@ -53,6 +54,10 @@ class Pattern:
             _lib.check(lib.mof_pattern_colors(handle, ctypes.byref(nc), ctp))
             self.n_colors = int(nc.value)
             self.color_tile_ptr = np.array(list(ctp)[:self.n_colors + 1], dtype=np.int32) if self.n_colors else np.zeros(1, np.int32)
+            self.n_levels = int(lib.mof_pattern_levels(handle, None))
+            self.level_ptr = np.zeros(self.n_levels + 1, np.int32)
+            if self.n_levels:
+                lib.mof_pattern_levels(handle, self.level_ptr.ctypes.data)
             nb = int(lib.mof_pattern_num_blocks(handle))
             nc = int(lib.mof_pattern_num_contrib(handle))
             self.n_vertices, self.n_faces, self.n_blocks, self.n_contrib = N, F, nb, nc
@@ -169,7 +174,8 @@ class MeshOperator:
             self.d_cptr.data_ptr(), self.d_centry.data_ptr(), self.d_tri.data_ptr(),
             self.d_e.data_ptr(), self.d_grad_w.data_ptr(), self.d_integral.data_ptr(), self.d_areas.data_ptr(),
             self.d_a2v.data_ptr(), P.n_colors,
-            (ctypes.c_int32 * (_lib.MAX_COLORS + 1))(*([int(x) for x in P.color_tile_ptr] + [0] * (_lib.MAX_COLORS - P.n_colors))))
+            (ctypes.c_int32 * (_lib.MAX_COLORS + 1))(*([int(x) for x in P.color_tile_ptr] + [0] * (_lib.MAX_COLORS - P.n_colors))),
+            P.n_levels, 0, P.level_ptr.ctypes.data if P.n_levels else None)
 
     # -- reference-compatible views ----------------------------------------------------
     def tocsr(self):

@@ -17,8 +17,12 @@ DEFAULT_TOL = 1e-12          # ||b - A x|| / ||b||, north-star parity setting
 DEFAULT_MAX_ITER = 20000
 DEFAULT_CHECK_EVERY = 32
 DEFAULT_MAX_RESTARTS = 3
-DEFAULT_PRECOND = "ssor"     # "ssor" (block-multicolour SSOR, Eisenstat form) or "jacobi" (2x2 block Jacobi)
-DEFAULT_OMEGA = 1.4          # SSOR relaxation factor
+DEFAULT_PRECOND = "ssor"     # "ssor" (block-multicolour SSOR, Eisenstat form), "ssor_level" (the same on the
+                             # level-scheduled natural ordering) or "jacobi" (2x2 block Jacobi)
+DEFAULT_OMEGA = 1.4          # SSOR relaxation factor of the block-multicolour ordering
+DEFAULT_OMEGA_LEVEL = 1.85   # ... of the level-scheduled natural ordering (148 iterations at ico7; 192 at 1.7)
+SSOR_KINDS = ("ssor", "ssor_level")
+REORDER_OF = {"jacobi": 1, "ssor": 2, "ssor_level": 3}
 DEFAULT_BATCH_GROUPS = 32    # 32 x 32 = 1024 frames per launch (~66 GB at 164k vertices)
 DRAIN_STAGE_ROWS = 256       # rows per pinned staging buffer of the device->host pipeline
 DEFAULT_STREAMS = 1          # concurrent solve streams (2 fills launch tails: +2 % measured, but blurs per-kernel timing)
@@ -94,19 +98,24 @@ class VelocitySolver:
     """Solves batches of frames on one GPU.  Buffers are allocated once and reused."""
 
     def __init__(self, op, batch_groups=None, tol=DEFAULT_TOL, max_iter=DEFAULT_MAX_ITER,
-                 check_every=DEFAULT_CHECK_EVERY, max_restarts=DEFAULT_MAX_RESTARTS, precond=None, omega=DEFAULT_OMEGA,
+                 check_every=DEFAULT_CHECK_EVERY, max_restarts=DEFAULT_MAX_RESTARTS, precond=None, omega=None,
                  n_streams=DEFAULT_STREAMS):
         self.torch = _lib.require_cuda()
         self.lib = _lib.load()
         self.op = op
         if precond is None:
-            precond = DEFAULT_PRECOND if op.pattern.n_colors > 0 else "jacobi"
-        if precond not in ("ssor", "jacobi"):
-            raise ValueError(f"precond must be 'ssor' or 'jacobi', got {precond!r}")
+            precond = "ssor" if op.pattern.n_colors > 0 else ("ssor_level" if op.pattern.n_levels > 0 else "jacobi")
+        if precond not in SSOR_KINDS + ("jacobi",):
+            raise ValueError(f"precond must be 'ssor', 'ssor_level' or 'jacobi', got {precond!r}")
         if precond == "ssor" and op.pattern.n_colors == 0:
             raise ValueError("the SSOR preconditioner needs a mesh built with the block-multicolour ordering (reorder=2)")
+        if precond == "ssor_level" and op.pattern.n_levels == 0:
+            raise ValueError("the level-scheduled SSOR preconditioner needs a mesh built with reorder=3")
         self.precond = precond
-        self.omega = float(omega) if precond == "ssor" else 0.0
+        self.ssor = precond in SSOR_KINDS
+        if omega is None:
+            omega = DEFAULT_OMEGA_LEVEL if precond == "ssor_level" else DEFAULT_OMEGA
+        self.omega = float(omega) if self.ssor else 0.0
         self.tol, self.max_iter, self.check_every, self.max_restarts = tol, max_iter, check_every, max_restarts
         if batch_groups is None:
             free, _total = self.torch.cuda.mem_get_info(op.device)
@@ -124,7 +133,7 @@ class VelocitySolver:
     def batch(self, n_groups):
         if self._batch is None or self._batch.n_groups < n_groups:
             self._batch = None
-            self._batch = FrameBatch(self.op, n_groups, with_t=self.precond == "ssor")
+            self._batch = FrameBatch(self.op, n_groups, with_t=self.ssor)
         return self._batch
 
     def _solve_concurrent(self, ranges, lanes, groups_per_batch, I_dev, I2_dev, dt_dev, lambda_, V_dev, on_batch):
@@ -137,7 +146,7 @@ class VelocitySolver:
         torch, op = self.torch, self.op
         if self._lanes is None or len(self._lanes) < lanes or self._lanes[0][0].n_groups < groups_per_batch:
             self._lanes = None
-            self._lanes = [(FrameBatch(op, groups_per_batch, with_t=self.precond == "ssor"),
+            self._lanes = [(FrameBatch(op, groups_per_batch, with_t=self.ssor),
                             torch.cuda.Stream(device=op.device)) for _ in range(lanes)]
         if self._pool is None:
             self._pool = ThreadPoolExecutor(max_workers=self.n_streams)
@@ -226,7 +235,7 @@ class VelocitySolver:
                                            relres.ctypes.data, status.ctypes.data,
                                            ctypes.byref(profile) if profile is not None else None, st),
                    allow_positive=True)
-        self.aux_launches += 3 + (1 if self.precond == "ssor" else 0)
+        self.aux_launches += 3 + (1 if self.ssor else 0)
         assert V_out.stride(1) == 1
         _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
         return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames])

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8 + 4 + 17 * 4
+    assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8 + 4 + 17 * 4 + 4 + 4 + 8
     assert ctypes.sizeof(_lib.BatchDev) == 8 + 14 * 8
     assert ctypes.sizeof(_lib.PcgProfile) == 8 * 8
 
@@ -129,7 +129,7 @@ class HostMesh:
         p = lambda a: a.ctypes.data
         return _lib.MeshDev(P.n_vertices, P.n_faces, P.n_blocks, P.n_contrib, p(P.perm), p(P.rowptr), p(P.col), p(P.diag),
                             p(P.cptr), p(P.centry), p(P.tri), p(self.e), p(self.grad_w), p(self.integral), p(self.areas),
-                            p(self.a2v), 0, (ctypes.c_int32 * (_lib.MAX_COLORS + 1))())
+                            p(self.a2v), 0, (ctypes.c_int32 * (_lib.MAX_COLORS + 1))(), 0, 0, None)
 
     def assemble(self, I, t_k, lambda_, omega=0.0):
         P, hc = self.P, self.hc
@@ -235,17 +235,55 @@ def test_bodies_ssor_eisenstat_pcg_matches_reference(case):
     the assembly body, colour-by-colour backward / forward sweeps (the bodies the CUDA sweep
     kernels call) inside the same Eisenstat-form PCG the library's host loop runs."""
     g = _fan_case() if case == "fan40" else load_golden(case)
-    omega, tol = 1.4, 1e-12
     hm = HostMesh(g, reorder=2)
-    P, hc = hm.P, hm.hc
+    P = hm.P
     N = P.n_vertices
     assert P.n_colors >= 1 and P.color_tile_ptr[0] == 0 and P.color_tile_ptr[-1] == -(-N // _lib.TILE_ROWS)
+    assert P.n_levels == 0
     # patches of one colour are mutually independent (no block couples two of them)
     tile_of = np.arange(N) // _lib.TILE_ROWS
     color_of_tile = np.repeat(np.arange(P.n_colors), np.diff(P.color_tile_ptr))
     rows, cols = P.block_rows(), P.col.astype(np.int64)
     cross = tile_of[rows] != tile_of[cols]
     assert np.all(color_of_tile[tile_of[rows[cross]]] != color_of_tile[tile_of[cols[cross]]])
+    ptr = [int(x) for x in P.color_tile_ptr]
+    ranges = [(ptr[c], ptr[c + 1]) for c in range(P.n_colors)]
+    _eisenstat_pcg_on_host(hm, g, 1.4, fwd_ranges=ranges, back_ranges=ranges[::-1])
+
+
+@pytest.mark.parametrize("case", ["ico2_wave", "patch8_wave", "ico3_phase", "ico4_wave", "fan40"])
+def test_level_scheduled_ordering_and_its_ssor(case):
+    """reorder = 3: Cuthill-McKee regrouped by dependency level.  Rows of a level are mutually
+    independent, every neighbour with a lower number sits in a strictly lower level (so processing
+    level by level IS the sequential Gauss-Seidel sweep, which is what the harness runs here), and
+    the Eisenstat-form PCG on that ordering reaches the reference's fields."""
+    g = _fan_case() if case == "fan40" else load_golden(case)
+    hm = HostMesh(g, reorder=3)
+    P = hm.P
+    N = P.n_vertices
+    assert P.n_colors == 0 and P.n_levels >= 1
+    lp = P.level_ptr.astype(np.int64)
+    assert lp[0] == 0 and lp[-1] == N and np.all(np.diff(lp) > 0)
+    level_of = np.repeat(np.arange(P.n_levels), np.diff(lp))
+    rows, cols = P.block_rows(), P.col.astype(np.int64)
+    off = rows != cols
+    assert np.all(level_of[rows[off]] != level_of[cols[off]])                        # independent rows inside a level
+    assert np.all((cols[off] < rows[off]) == (level_of[cols[off]] < level_of[rows[off]]))   # orientation = level order
+    # every row of level l > 0 depends on level l-1 (levels are as low as the order allows)
+    lower = off & (cols < rows)
+    deepest = np.full(N, -1)
+    np.maximum.at(deepest, rows[lower], level_of[cols[lower]])
+    assert np.array_equal(deepest + 1, level_of)
+    assert sorted(P.perm.tolist()) == list(range(N))
+    ntiles = -(-N // _lib.TILE_ROWS)
+    iters = _eisenstat_pcg_on_host(hm, g, 1.6, fwd_ranges=[(0, ntiles)], back_ranges=[(t, t + 1) for t in range(ntiles - 1, -1, -1)])
+    assert iters > 0
+
+
+def _eisenstat_pcg_on_host(hm, g, omega, fwd_ranges, back_ranges):
+    tol = 1e-12
+    P, hc = hm.P, hm.hc
+    N = P.n_vertices
     vals0, rhs0, _ = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]), 0.0)       # unscaled system (block-Jacobi layout)
     vals, rhs, S = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]), omega)       # S A S, S b, S = D^-1/2
     n = len(g["V_k"])
@@ -254,18 +292,16 @@ def test_bodies_ssor_eisenstat_pcg_matches_reference(case):
     dblk = vals[:, P.diag]                                                       # (G, N, 4, W)
     assert np.allclose(dblk[:, :, 0, :n % W or W], 1.0, atol=1e-13) and np.allclose(dblk[:, :, 1, :n % W or W], 0.0, atol=1e-13)
     ms = hm.struct()
-    ptr = [int(x) for x in P.color_tile_ptr]
-    C = P.n_colors
     ref = ctypes.byref(ms)
 
     def back(mode, r, p, t, beta=None, zs=None):
-        for c in range(C - 1, -1, -1):
-            hc.hc_sweep_back(ref, G, vals.ctypes.data, r.ctypes.data, p.ctypes.data, t.ctypes.data, ptr[c], ptr[c + 1],
+        for t0, t1 in back_ranges:
+            hc.hc_sweep_back(ref, G, vals.ctypes.data, r.ctypes.data, p.ctypes.data, t.ctypes.data, t0, t1,
                              beta.ctypes.data if beta is not None else None, zs.ctypes.data if zs is not None else None, omega, mode)
 
     def fwd(mode, pin, t, w, dot=None):
-        for c in range(C):
-            hc.hc_sweep_fwd(ref, G, vals.ctypes.data, pin.ctypes.data, t.ctypes.data, w.ctypes.data, ptr[c], ptr[c + 1],
+        for t0, t1 in fwd_ranges:
+            hc.hc_sweep_fwd(ref, G, vals.ctypes.data, pin.ctypes.data, t.ctypes.data, w.ctypes.data, t0, t1,
                             omega, mode, dot.ctypes.data if dot is not None else None)
 
     def apply_S(v):
@@ -315,6 +351,7 @@ def test_bodies_ssor_eisenstat_pcg_matches_reference(case):
         assert rel_l2(V, g["V_k"][k]) <= 1e-8
     # padding lanes stay exactly zero
     assert np.all(xphys[-1, :, :, n % W:] == 0.0) if n % W else True
+    return iters
 
 
 def test_bodies_tangent_and_detection_match_reference(golden):
