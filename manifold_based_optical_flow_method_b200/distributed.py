@@ -175,7 +175,8 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
         # (smaller batches would hide more of the drain but cost more in solve efficiency)
         groups = -(-n_loc // 32)
         saved_groups = solver.batch_groups
-        solver.batch_groups = max(8, min(saved_groups, -(-groups // 2)))
+        if solver.precond != "ssor_level":       # the level path is launch-bound: a half-sized batch costs as much as a full one
+            solver.batch_groups = max(8, min(saved_groups, -(-groups // 2)))
 
         def on_batch(k0, k1, Vd):
             def collect():

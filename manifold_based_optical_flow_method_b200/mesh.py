@@ -118,7 +118,7 @@ class MeshOperator:
     consumers of ``a2`` are ``worker`` / ``compute_velocity_field``, which accept this
     handle.  ``tocsr()`` gives the same matrix as the reference's for comparison."""
 
-    def __init__(self, coordinates, normals, triangles, areas, device=None, reorder=2):
+    def __init__(self, coordinates, normals, triangles, areas, device=None, reorder=3):
         torch = _lib.require_cuda()
         lib = _lib.load()
         t0 = time.time()

@@ -17,10 +17,10 @@ DEFAULT_TOL = 1e-12          # ||b - A x|| / ||b||, north-star parity setting
 DEFAULT_MAX_ITER = 20000
 DEFAULT_CHECK_EVERY = 32
 DEFAULT_MAX_RESTARTS = 3
-DEFAULT_PRECOND = "ssor"     # "ssor" (block-multicolour SSOR, Eisenstat form), "ssor_level" (the same on the
-                             # level-scheduled natural ordering) or "jacobi" (2x2 block Jacobi)
-DEFAULT_OMEGA = 1.4          # SSOR relaxation factor of the block-multicolour ordering
-DEFAULT_OMEGA_LEVEL = 1.85   # ... of the level-scheduled natural ordering (148 iterations at ico7; 192 at 1.7)
+DEFAULT_PRECOND = "ssor_level"   # "ssor_level": SSOR in Eisenstat's form on the level-scheduled natural (Cuthill-McKee)
+                             # ordering; "ssor": the same on the block-multicolour ordering; "jacobi": 2x2 block Jacobi
+DEFAULT_OMEGA = 1.4          # SSOR relaxation factor of the block-multicolour ordering (372 iterations at ico7)
+DEFAULT_OMEGA_LEVEL = 1.9    # ... of the level-scheduled natural ordering (B200, ico7: 143 iterations; 148 at 1.85, 192 at 1.7)
 SSOR_KINDS = ("ssor", "ssor_level")
 REORDER_OF = {"jacobi": 1, "ssor": 2, "ssor_level": 3}
 DEFAULT_BATCH_GROUPS = 32    # 32 x 32 = 1024 frames per launch (~66 GB at 164k vertices)
@@ -104,7 +104,7 @@ class VelocitySolver:
         self.lib = _lib.load()
         self.op = op
         if precond is None:
-            precond = "ssor" if op.pattern.n_colors > 0 else ("ssor_level" if op.pattern.n_levels > 0 else "jacobi")
+            precond = "ssor_level" if op.pattern.n_levels > 0 else ("ssor" if op.pattern.n_colors > 0 else "jacobi")
         if precond not in SSOR_KINDS + ("jacobi",):
             raise ValueError(f"precond must be 'ssor', 'ssor_level' or 'jacobi', got {precond!r}")
         if precond == "ssor" and op.pattern.n_colors == 0:

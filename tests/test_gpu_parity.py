@@ -17,6 +17,8 @@ from conftest import load_golden, rel_l2
 from manifold_based_optical_flow_method_b200 import _lib, synthetic
 from oracle import mof_oracle
 
+from manifold_based_optical_flow_method_b200.solver import DEFAULT_PRECOND  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 W = _lib.GROUP
@@ -24,7 +26,7 @@ V_TOL = 1e-8
 RES_TOL = 1e-12
 
 
-@pytest.fixture(scope="module", params=["ssor", "jacobi", "ssor_level"])
+@pytest.fixture(scope="module", params=["ssor_level", "ssor", "jacobi"])
 def mods(request):
     """Every test runs with all three preconditioners (and therefore all three vertex numberings)."""
     import torch
@@ -485,7 +487,7 @@ def test_c_abi_argument_errors(mods):
 def test_full_size_properties(mods):
     import torch
     cof, fsp = mods
-    if cof.settings["precond"] != "ssor":
+    if cof.settings["precond"] != DEFAULT_PRECOND:
         pytest.skip("full-size properties run once, with the default preconditioner")
     coords, tris, normals, areas = synthetic.pial_like(7)
     N = len(coords)
@@ -534,7 +536,7 @@ def test_full_size_phase_config4(mods):
     """BASELINE.json configs[3]: ~320k-vertex two-component mesh with wrapped-phase input (values in
     (-pi, pi], ill conditioned: cond ~1e6) -> velocity solve + singularity detection."""
     cof, fsp = mods
-    if cof.settings["precond"] != "ssor":
+    if cof.settings["precond"] != DEFAULT_PRECOND:
         pytest.skip("run once, with the default preconditioner")
     coords, tris, normals, areas = synthetic.two_hemispheres(7)
     N = len(coords)
