@@ -198,10 +198,12 @@ int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const d
  * (recurrence residual, confirmed on the true residual b - A x; at most
  * max_restarts restarts from the true residual).
  * omega = 0: block-Jacobi PCG (SpMV + two vector kernels per iteration).
- * omega in (0,2): block-multicolour SSOR PCG in Eisenstat's form (needs a mesh built with
- * reorder = 2 and batch->minv assembled with the same omega): per iteration one backward and
- * one forward block-triangular sweep per colour plus one vector kernel; ~3x fewer
- * iterations than block Jacobi at the same bytes per iteration.  Synchronous: returns after the
+ * omega in (0,2): SSOR PCG in Eisenstat's form (needs batch->minv assembled with the same omega): per
+ * iteration one backward and one forward block-triangular sweep plus one vector kernel.  With a mesh
+ * built with reorder = 3 (mesh->n_levels > 0) the sweeps run level by level, one warp per row, and an
+ * iteration is replayed as a CUDA graph (environment MOF_LEVEL_GRAPH=0: plain launches); with
+ * reorder = 2 (mesh->n_colors > 0) they run colour by colour, one warp per patch.  ~3x (multicolour) to
+ * ~8x (level-scheduled) fewer iterations than block Jacobi at the same bytes per iteration.  Synchronous: returns after the
  * stream has drained.  Host outputs (each MOF_GROUP*n_groups long, may be NULL):
  * iters, relres (true residual), status (MOF_STATUS_*).  Return value: 0 if every
  * valid frame converged (or had a zero rhs), else the largest status met. */

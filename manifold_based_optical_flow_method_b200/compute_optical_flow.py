@@ -17,8 +17,9 @@ Differences a caller can observe (all documented in INTEGRATION.md):
   * ``processes_num`` (the reference's Pool size) is ignored: frames are batched on the
     GPU of this process; under torchrun (torch.distributed initialised) they are also
     sharded across ranks and gathered with NCCL (see distributed.py).
-  * the linear systems are solved by preconditioned CG (block-multicolour SSOR by default,
-    2x2 block Jacobi with settings["precond"] = "jacobi") to ||b-Ax||/||b|| <= 1e-12 instead
+  * the linear systems are solved by preconditioned CG (SSOR on a level-scheduled natural ordering by
+    default; settings["precond"] = "ssor" for the block-multicolour ordering, "jacobi" for 2x2 block
+    Jacobi) to ||b-Ax||/||b|| <= 1e-12 instead
     of SuperLU; frames that fail to converge raise ``UnconvergedError`` (the reference
     would return NaNs with a MatrixRankWarning) unless ``allow_unconverged`` is set.
   * float32 mesh arrays are promoted to float64 (the reference computes grad_w in

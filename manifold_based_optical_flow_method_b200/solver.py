@@ -1,5 +1,5 @@
-"""Frame-batch driver: pack -> assemble (K1) -> batched PCG (K2/K3: block-multicolour SSOR or block
-Jacobi) -> unpack, with the device->host drain of finished batches overlapped with the next solve.
+"""Frame-batch driver: pack -> assemble (K1) -> batched PCG (K2/K3: SSOR on the level-scheduled or the
+block-multicolour ordering, or block Jacobi) -> unpack, with the device->host drain of finished batches overlapped with the next solve.
 
 Host orchestration only (PyTorch provides device memory and streams); all arithmetic is in
 libmof_b200.so.  Replaces the multiprocessing fan-out of compute_velocity_field
