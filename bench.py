@@ -357,6 +357,17 @@ def run_b200(args):
         "iteration_time_share": {"dominant": dom_ms / max(ms_iter, 1e-9), "rest": 1.0 - dom_ms / max(ms_iter, 1e-9)},
     }
 
+    # whole timed step on algorithmic bytes: every frame's iterations x bytes per frame-iteration over the step time
+    # (includes assembly, verification and, for the level-scheduled path, the graph-replayed iterations that the
+    # kernel-by-kernel sample above does not see)
+    try:
+        it_bytes = float(np.sum(info.iterations)) * float(sum(per_frame.values()))
+        step_gbs = it_bytes / (ms_total / args.steps * 1e-3) / 1e9
+        roofline["whole_step"] = {"achieved": step_gbs, "frac": step_gbs / peak,
+                                  "note": "sum over frames of iterations x algorithmic bytes per frame-iteration / step time"}
+    except Exception as exc:
+        roofline["whole_step"] = {"error": repr(exc)}
+
     # ---- SpMV micro-measurement (BASELINE.json names "SpMV HBM GB/s"): the solver's SpMV kernel on
     # the last assembled batch, K launches back to back
     batch = solver._batch if solver._batch is not None else solver._lanes[0][0]
