@@ -652,6 +652,147 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const int32_t* __restric
     if (MODE == 0) dots[((size_t)g * N + i) * MOF_W + lane] = p0 * (t0 + o0) + p1 * (t1 + o1);
 }
 
+// Experimental (environment MOF_LEVEL_PDL=1, off by default, not yet measured): the iteration's level
+// kernels launched with programmatic stream serialization.  A level's indices and matrix values -- most of
+// its bytes -- depend on no earlier kernel, so a CTA of level l+1 may start while level l drains, issue
+// those loads, and only then wait (griddepcontrol.wait) for everything before it to complete; every
+// load of data written by other kernels (vectors, scalars, the group_done flags) and every store come
+// after the wait.  Same arithmetic as level_back_kernel<0> / level_fwd_kernel<0>.
+struct RowStatic {
+    RowPre R;
+    double a[4][4];
+};
+
+__device__ __forceinline__ void level_static_loads(const int32_t* __restrict__ col, const double* __restrict__ vals_l,
+                                                   RowStatic& S) {
+    const int cnt = S.R.be - S.R.bs;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < cnt) {
+            S.R.c[k] = col[S.R.bs + k];
+            const double* ap = vals_l + (size_t)(S.R.bs + k) * 4 * MOF_W;
+            S.a[k][0] = __ldcs(ap);
+            S.a[k][1] = __ldcs(ap + MOF_W);
+            S.a[k][2] = __ldcs(ap + 2 * MOF_W);
+            S.a[k][3] = __ldcs(ap + 3 * MOF_W);
+        }
+}
+
+__device__ __forceinline__ void level_dependent_part(const int32_t* __restrict__ col, const double* __restrict__ vals_l,
+                                                     const double* v_l, const RowStatic& S, double& a0, double& a1) {
+    const int cnt = S.R.be - S.R.bs;
+    double v[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < cnt) {
+            v[k][0] = v_l[(size_t)(2 * (int64_t)S.R.c[k]) * MOF_W];
+            v[k][1] = v_l[(size_t)(2 * (int64_t)S.R.c[k] + 1) * MOF_W];
+        }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < cnt) {
+            a0 -= S.a[k][0] * v[k][0] + S.a[k][1] * v[k][1];
+            a1 -= S.a[k][2] * v[k][0] + S.a[k][3] * v[k][1];
+        }
+    for (int32_t b = S.R.bs + 4; b < S.R.be; ++b) {
+        const int64_t j = col[b];
+        const double* ap = vals_l + (size_t)b * 4 * MOF_W;
+        const double v0 = v_l[(size_t)(2 * j) * MOF_W], v1 = v_l[(size_t)(2 * j + 1) * MOF_W];
+        a0 -= __ldcs(ap) * v0 + __ldcs(ap + MOF_W) * v1;
+        a1 -= __ldcs(ap + 2 * MOF_W) * v0 + __ldcs(ap + 3 * MOF_W) * v1;
+    }
+}
+
+__global__ void __launch_bounds__(256) level_back_pdl_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                             const int32_t* __restrict__ diag, mof_batch_dev B, double* tout,
+                                                             int64_t N, int64_t nb, int r_lo, int r_hi, double omega) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int64_t g = blockIdx.y;
+    const int G = B.n_groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = r_lo + blockIdx.x * kWarps + warp;
+    const bool live = row < r_hi;
+    const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
+    RowStatic S;
+    S.R.bs = S.R.be = 0;
+    if (live) {
+        S.R.be = rowptr[row + 1];
+        S.R.bs = diag[row] + 1;
+        level_static_loads(col, vals_l, S);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!live || group_done_ptr(B.state, G)[g]) return;
+    const size_t i = (size_t)row;
+    const double* r_l = B.r + (size_t)g * N * 2 * MOF_W + lane;
+    double* p_l = B.p + (size_t)g * N * 2 * MOF_W + lane;
+    double* x_l = B.x + (size_t)g * N * 2 * MOF_W + lane;
+    double* t_l = tout + (size_t)g * N * 2 * MOF_W + lane;
+    const double p0 = p_l[(2 * i) * MOF_W], p1 = p_l[(2 * i + 1) * MOF_W];
+    const double x0 = x_l[(2 * i) * MOF_W], x1 = x_l[(2 * i + 1) * MOF_W];
+    const double r0 = r_l[(2 * i) * MOF_W], r1 = r_l[(2 * i + 1) * MOF_W];
+    const double alpha = scal_ptr(B.scal, g, MOF_S_ALPHA)[lane];
+    const double beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
+    const double zsw = scal_ptr(B.scal, g, MOF_S_ZS)[lane] / omega;
+    x_l[(2 * i) * MOF_W] = fma(alpha, p0, x0);
+    x_l[(2 * i + 1) * MOF_W] = fma(alpha, p1, x1);
+    double a0 = zsw * r0 + beta * p0, a1 = zsw * r1 + beta * p1;
+    p_l[(2 * i) * MOF_W] = a0;
+    p_l[(2 * i + 1) * MOF_W] = a1;
+    level_dependent_part(col, vals_l, t_l, S, a0, a1);
+    t_l[(2 * i) * MOF_W] = omega * a0;
+    t_l[(2 * i + 1) * MOF_W] = omega * a1;
+}
+
+__global__ void __launch_bounds__(256) level_fwd_pdl_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                            const int32_t* __restrict__ diag, mof_batch_dev B, const double* pin,
+                                                            double* wout, double* dots, int64_t N, int64_t nb, int r_lo,
+                                                            int r_hi, double omega) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int64_t g = blockIdx.y;
+    const int G = B.n_groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = r_lo + blockIdx.x * kWarps + warp;
+    const bool live = row < r_hi;
+    const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
+    RowStatic S;
+    S.R.bs = S.R.be = 0;
+    if (live) {
+        S.R.bs = rowptr[row];
+        S.R.be = diag[row];
+        level_static_loads(col, vals_l, S);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!live || group_done_ptr(B.state, G)[g]) return;
+    const size_t i = (size_t)row;
+    const double* p_l = pin + (size_t)g * N * 2 * MOF_W + lane;
+    const double* t_l = B.t + (size_t)g * N * 2 * MOF_W + lane;
+    double* w_l = wout + (size_t)g * N * 2 * MOF_W + lane;
+    const double p0 = p_l[(2 * i) * MOF_W], p1 = p_l[(2 * i + 1) * MOF_W];
+    const double t0 = t_l[(2 * i) * MOF_W], t1 = t_l[(2 * i + 1) * MOF_W];
+    const double kscale = (2.0 - omega) / omega;
+    double a0 = p0 - kscale * t0, a1 = p1 - kscale * t1;
+    level_dependent_part(col, vals_l, w_l, S, a0, a1);
+    const double o0 = omega * a0, o1 = omega * a1;
+    w_l[(2 * i) * MOF_W] = o0;
+    w_l[(2 * i + 1) * MOF_W] = o1;
+    dots[((size_t)g * N + i) * MOF_W + lane] = p0 * (t0 + o0) + p1 * (t1 + o1);
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // p'Ap = sum of the per-row shares (tile by tile, rows in order: deterministic), then alpha.
 __global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const double* __restrict__ dots, int64_t N, int ntiles) {
     const int64_t g = blockIdx.y;
@@ -900,13 +1041,20 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     int64_t launches = 0;
 
     double* dots = B.z;                  // SSOR never stores z: its buffer carries the per-row shares of p'Ap
+    const char* pdl_env = getenv("MOF_LEVEL_PDL");
+    const bool use_pdl = levels && pdl_env && pdl_env[0] == '1';      // experimental, see level_back_pdl_kernel
+    bool pdl_failed = false;
     auto sweep_back = [&](int mode, double* tout, cudaStream_t st) {
         if (levels) {
             for (int l = L - 1; l >= 0; --l) {
                 const int r0 = lp[l], r1 = lp[l + 1];
                 if (r1 <= r0) continue;
                 dim3 gs(mof_cdiv(r1 - r0, kWarps), G);
-                if (mode == 0) level_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega);
+                if (mode == 0 && use_pdl) {
+                    if (launch_pdl(level_back_pdl_kernel, gs, st, mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega) != cudaSuccess)
+                        pdl_failed = true;
+                }
+                else if (mode == 0) level_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega);
                 else           level_back_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega);
                 ++launches;
             }
@@ -927,7 +1075,11 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                 const int r0 = lp[l], r1 = lp[l + 1];
                 if (r1 <= r0) continue;
                 dim3 gs(mof_cdiv(r1 - r0, kWarps), G);
-                if (mode == 0) level_fwd_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
+                if (mode == 0 && use_pdl) {
+                    if (launch_pdl(level_fwd_pdl_kernel, gs, st, mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega) != cudaSuccess)
+                        pdl_failed = true;
+                }
+                else if (mode == 0) level_fwd_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
                 else           level_fwd_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
                 ++launches;
             }
@@ -1032,6 +1184,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                 if (sample) cudaEventRecord(ev[3], st);
             }
             MOF_LAUNCH_CHECK("pcg iteration kernels");
+            if (pdl_failed) return mof_set_error(-100, "mof_pcg_solve_batch: a programmatic dependent launch failed (MOF_LEVEL_PDL=1)");
             it += n;
             const int32_t groups_before = h_act[0], lanes_before = h_act[1];
             MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
