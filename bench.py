@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--level", type=int, default=7, help="icosphere level of the pial-like mesh (7 = 163,842 vertices)")
     ap.add_argument("--frames", type=int, default=1000, help="frames of signal per GPU (frames-1 solves per step)")
     ap.add_argument("--batch-groups", type=int, default=None)
+    ap.add_argument("--streams", type=int, default=None, help="concurrent solve streams (default: the package default, 1)")
     ap.add_argument("--tol", type=float, default=1e-12)
     ap.add_argument("--precond", default=None, choices=["ssor", "ssor_level", "jacobi"], help="default: the package default")
     ap.add_argument("--omega", type=float, default=None)
@@ -275,6 +276,8 @@ def run_b200(args):
     del I_np
     cof.settings["tol"] = args.tol
     cof.settings["batch_groups"] = args.batch_groups
+    if args.streams:
+        cof.settings["streams"] = args.streams
     if args.precond:
         cof.settings["precond"] = args.precond
     if args.omega:
