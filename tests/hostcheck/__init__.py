@@ -26,6 +26,9 @@ def load():
     lib.hc_assemble.argtypes = [P, I32, P, P, D, D, P, P, P]
     lib.hc_sweep_back.argtypes = [P, I32, P, P, P, P, I32, I32, P, P, D, I32]
     lib.hc_sweep_fwd.argtypes = [P, I32, P, P, P, P, I32, I32, D, I32, P]
+    lib.hc_sweep_rows_back.argtypes = [P, I32, P, P, P, P, I64, I64, P, P, D, I32]
+    lib.hc_sweep_rows_fwd.argtypes = [P, I32, P, P, P, P, I64, I64, D, I32, P]
+    lib.hc_sweep_rows_back.restype = lib.hc_sweep_rows_fwd.restype = None
     lib.hc_spmv.argtypes = [P, I32, P, P, P]
     lib.hc_tangent.argtypes = [I64, I64, P, I64, P, P, P, P]
     lib.hc_detect.argtypes = [I64, I64, P, P, P, D, D, P, P, P, P, P, P]

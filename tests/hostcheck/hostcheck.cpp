@@ -131,6 +131,30 @@ void hc_sweep_fwd(const mof_mesh_dev* M, int32_t G, const double* vals, const do
             }
 }
 
+// The same sweeps over an arbitrary row range [r0, r1) (level-scheduled path: one dependency level, or a single row)
+void hc_sweep_rows_back(const mof_mesh_dev* M, int32_t G, const double* vals, const double* r, double* p, double* t,
+                        int64_t r0, int64_t r1, const double* beta, const double* zs, double omega, int32_t mode) {
+    const int64_t N = M->n_vertices, nb = M->n_blocks;
+    for (int64_t g = 0; g < G; ++g)
+        for (int l = 0; l < MOF_W; ++l)
+            mof_sweep_back_body(M->rowptr, M->col, M->diag, vals + (size_t)g * nb * 4 * MOF_W + l,
+                                r + (size_t)g * N * 2 * MOF_W + l, p + (size_t)g * N * 2 * MOF_W + l,
+                                t + (size_t)g * N * 2 * MOF_W + l, r0, r1, beta ? beta[g * MOF_W + l] : 0.0,
+                                (zs ? zs[g * MOF_W + l] : 1.0) / omega, omega, mode);
+}
+
+void hc_sweep_rows_fwd(const mof_mesh_dev* M, int32_t G, const double* vals, const double* pin, const double* t, double* w,
+                       int64_t r0, int64_t r1, double omega, int32_t mode, double* dot) {
+    const int64_t N = M->n_vertices, nb = M->n_blocks;
+    for (int64_t g = 0; g < G; ++g)
+        for (int l = 0; l < MOF_W; ++l) {
+            double d = mof_sweep_fwd_body(M->rowptr, M->col, M->diag, vals + (size_t)g * nb * 4 * MOF_W + l,
+                                          pin + (size_t)g * N * 2 * MOF_W + l, t + (size_t)g * N * 2 * MOF_W + l,
+                                          w + (size_t)g * N * 2 * MOF_W + l, r0, r1, omega, mode);
+            if (dot) dot[g * MOF_W + l] += d;
+        }
+}
+
 void hc_tangent(int64_t N, int64_t n_frames, const double* V, int64_t ldV, const double* e, double* Vxyz, double* speed,
                 double* vmax) {
     for (int64_t k = 0; k < n_frames; ++k) {

@@ -433,3 +433,52 @@ def test_classification_host_helpers(capsys):
     got = fsp.analyze_classification([["Focus", "Saddle"], [], ["Node", "Indeterminate", "Saddle"]])
     assert got == {"Focus": 1, "Saddle": 2, "Node": 2}
     assert capsys.readouterr().out == "Focus: 1\nSaddle: 2\nNode: 2\n"
+
+
+def test_level_sweeps_do_not_depend_on_the_order_inside_a_level():
+    """What the level kernels rely on: inside one dependency level the rows can be processed in any order
+    (the GPU runs them concurrently) -- the backward and forward sweeps give bit-identical vectors whether a
+    level's rows are taken ascending, descending or shuffled, and the same as the plain sequential sweep."""
+    g = load_golden("ico3_phase")
+    omega = 1.9
+    hm = HostMesh(g, reorder=3)
+    P, hc = hm.P, hm.hc
+    N = P.n_vertices
+    vals, rhs, S = hm.assemble(g["I"], g["t_k"], float(g["lambda_"]), omega)
+    G = vals.shape[0]
+    ms = hm.struct()
+    ref = ctypes.byref(ms)
+    lp = P.level_ptr.astype(np.int64)
+    rng = np.random.default_rng(0)
+    pin = rng.normal(size=rhs.shape)
+    rvec = rng.normal(size=rhs.shape)
+    beta = rng.normal(size=(G, W))
+    zs = np.ones((G, W))
+
+    def run(order_of_level):
+        p = pin.copy()
+        t = np.zeros_like(rhs)
+        w = np.zeros_like(rhs)
+        dot = np.zeros((G, W))
+        for l in range(P.n_levels - 1, -1, -1):                       # backward sweep: levels descending
+            for row in order_of_level(np.arange(lp[l], lp[l + 1])):
+                hc.hc_sweep_rows_back(ref, G, vals.ctypes.data, rvec.ctypes.data, p.ctypes.data, t.ctypes.data,
+                                      int(row), int(row) + 1, beta.ctypes.data, zs.ctypes.data, omega, 0)
+        for l in range(P.n_levels):                                    # forward sweep: levels ascending
+            for row in order_of_level(np.arange(lp[l], lp[l + 1])):
+                hc.hc_sweep_rows_fwd(ref, G, vals.ctypes.data, p.ctypes.data, t.ctypes.data, w.ctypes.data,
+                                     int(row), int(row) + 1, omega, 0, dot.ctypes.data)
+        return p, t, w
+
+    base = run(lambda rows: rows[::-1])
+    for order in (lambda rows: rows, lambda rows: rng.permutation(rows)):
+        got = run(order)
+        assert all(np.array_equal(a, b) for a, b in zip(got, base))
+    # and equal to the plain sequential sweeps over all rows
+    p = pin.copy()
+    t = np.zeros_like(rhs)
+    w = np.zeros_like(rhs)
+    hc.hc_sweep_rows_back(ref, G, vals.ctypes.data, rvec.ctypes.data, p.ctypes.data, t.ctypes.data, 0, N,
+                          beta.ctypes.data, zs.ctypes.data, omega, 0)
+    hc.hc_sweep_rows_fwd(ref, G, vals.ctypes.data, p.ctypes.data, t.ctypes.data, w.ctypes.data, 0, N, omega, 0, None)
+    assert all(np.array_equal(a, b) for a, b in zip((p, t, w), base))
