@@ -140,9 +140,10 @@ def solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n):
     batch, overlapped with the solve of the next batch.  -> (V (n, 2N) numpy, SolveInfo)"""
     s = _solver(op)
     drain = s.drain(2 * op.n_vertices)
-    if settings["pinned_results"]:
-        from .solver import pinned_rows
-        V_t, V = pinned_rows(s.torch, n, 2 * op.n_vertices)
+    from .solver import try_pinned_rows
+    pinned = try_pinned_rows(s.torch, n, 2 * op.n_vertices) if settings["pinned_results"] else None
+    if pinned is not None:
+        V_t, V = pinned
         on_batch = lambda k0, k1, Vd: drain.submit_pinned(Vd, V_t[k0:k1])
     else:
         V = np.empty((n, 2 * op.n_vertices), dtype=np.float64)

@@ -164,10 +164,12 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
         solver = cof._solver(op)
         # rank 0 alone receiving: its result goes to pinned memory by direct DMA (with "all" every
         # rank would pin world x the data, so that case keeps pageable memory and the staged drain)
-        pinned = receives and gather == "root" and cof.settings["pinned_results"]
+        from .solver import try_pinned_rows
+        block = try_pinned_rows(solver.torch, sum(counts), width) \
+            if receives and gather == "root" and cof.settings["pinned_results"] else None
+        pinned = block is not None
         if pinned:
-            from .solver import pinned_rows
-            V_pin, V_host = pinned_rows(solver.torch, sum(counts), width)
+            V_pin, V_host = block
         elif receives:
             V_host = np.empty((sum(counts), width), dtype=np.float64)
         drain = solver.drain(width)

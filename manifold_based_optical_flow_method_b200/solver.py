@@ -280,6 +280,20 @@ def pinned_rows(torch, rows, width):
     return t, t.numpy()
 
 
+PINNED_RESULT_MAX_BYTES = 16 << 30   # larger results (e.g. rank 0 collecting 8 GPUs x 1000 frames) stay pageable
+
+
+def try_pinned_rows(torch, rows, width):
+    """pinned_rows, or None when the block is larger than PINNED_RESULT_MAX_BYTES or the host refuses to pin it
+    (the caller then delivers into pageable memory through the staged drain)."""
+    if int(rows) * int(width) * 8 > PINNED_RESULT_MAX_BYTES:
+        return None
+    try:
+        return pinned_rows(torch, rows, width)
+    except RuntimeError:
+        return None
+
+
 class HostDrain:
     """Device -> host pipeline that overlaps the D2H copy of finished batches with the solve
     of the next one: rows are copied on a side stream into a ring of pinned staging buffers
