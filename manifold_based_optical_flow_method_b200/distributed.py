@@ -19,6 +19,7 @@ The helpers are device-agnostic so the host logic is testable on CPU with the gl
 import mmap
 import os
 import socket
+import struct
 import uuid
 
 import numpy as np
@@ -109,9 +110,14 @@ def shared_host_rows(rows, width, group=None):
         srv.listen(world)
     dist.broadcast_object_list(token, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     if me == 0:
-        for _ in range(world - 1):
+        served = 0
+        while served < world - 1:
             conn, _ = srv.accept()
-            socket.send_fds(conn, [b"m"], [fd])
+            # abstract sockets have no file permissions: only hand the memory to processes of this user
+            cred = conn.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i"))
+            if struct.unpack("3i", cred)[1] == os.getuid():
+                socket.send_fds(conn, [b"m"], [fd])
+                served += 1
             conn.close()
         srv.close()
     else:
