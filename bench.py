@@ -308,6 +308,8 @@ def run_b200(args):
     solver.profile = None
     launches = int(sum_over_ranks(prof.launches_total + solver.aux_launches))
     converged = bool(info.converged)
+    solver_path = {"path": ["jacobi", "multicolour sweeps", "level sweeps, one launch per level", "level sweeps, persistent kernel"][info.path[0]],
+                   "grid": info.path[1], "ctas_per_sm": info.path[2], "fallback_reason": info.path[3]} if info.path else None
     value = world * n * args.steps / (ms_total * 1e-3)
 
     # ---- roofline of the dominant kernel(s), sampled live inside the timed region
@@ -349,16 +351,53 @@ def run_b200(args):
                 traffic_val = json.load(fh)["dram_bytes_per_frame_iteration"] * fl / smp
         except Exception:
             traffic_val = None
+    persistent = solver.precond == "ssor_level" and prof.iter_launches > 0
+    if persistent:
+        # level_iter_kernel: one cooperative launch = check_every whole iterations of every group still iterating.
+        # Every launch of the timed region is bracketed by CUDA events on the solver's stream (prof.ms_iter); its
+        # algorithmic bytes are (frame-iterations it performed) x bytes per frame-iteration.  The inputs are the
+        # same every step, so the frame-iterations of the region are steps x sum(info.iterations).
+        per_frame = {"sweep_back": 16.0 * (nb - N) + 96.0 * N,           # U blocks; read r, p, x; write p, t, x
+                     "sweep_fwd": 16.0 * (nb - N) + 48.0 * N + 8.0 * N,  # L blocks; read p, t; write w and the row's share of p'Ap
+                     "dot": 8.0 * N,                                     # read the shares back (fixed-order reduction)
+                     "update": 64.0 * N}                                 # read w, t, r; write r
+        shared_per_group_iter = 2 * (32.0 * N + 4.0 * N)                 # row descriptors + ready stamps, both sweeps
+        frame_iters = float(np.sum(info.iterations)) * args.steps
+        group_iters = float(sum(int(np.max(info.iterations[g0:g0 + 32])) for g0 in range(0, n, 32))) * args.steps
+        dom_name = ("level_iter_kernel (persistent cooperative kernel: backward + forward level-scheduled SSOR sweeps, p'Ap, "
+                    f"r update; {op.pattern.n_levels} dependency levels per sweep, row-level dataflow)")
+        dom_bytes = frame_iters * sum(per_frame.values()) + group_iters * shared_per_group_iter
+        dom_ms = prof.ms_iter
+        smp = max(prof.iter_launches, 1)
+        ph = [float(x) * 1e-6 for x in prof.phase_ns]                     # ms, whole timed region
+        phase_bytes = [frame_iters * per_frame["sweep_back"] + group_iters * shared_per_group_iter / 2,
+                       frame_iters * per_frame["sweep_fwd"] + group_iters * shared_per_group_iter / 2,
+                       frame_iters * per_frame["dot"], frame_iters * per_frame["update"]]
+        others = {name: {"achieved": gbs(b, t), "ms_total": t, "time_share": t / max(sum(ph), 1e-9)}
+                  for name, b, t in zip(("phase backward sweep", "phase forward sweep", "phase p'Ap reduction", "phase r update"),
+                                        phase_bytes, ph)}
+        ms_iter = prof.ms_iter
+        try:
+            with open(os.path.join(ROOT, "profiles", "level_traffic.json")) as fh:
+                traffic_val = json.load(fh)["dram_bytes_per_frame_iteration"] * frame_iters / smp
+        except Exception:
+            traffic_val = None
     achieved = gbs(dom_bytes, dom_ms)
     roofline = {
         "kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": (achieved / peak) if achieved else None, "traffic": traffic_val,
         "algorithmic_bytes_per_launch": dom_bytes / smp, "peak_source": peak_src,
         "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-        "algorithmic_bytes_per_frame_iteration": per_frame, "sampled_iterations": int(prof.samples),
-        "avg_active_frames_per_launch": fl / smp, "other_kernels": others,
-        "iteration_time_share": {"dominant": dom_ms / max(ms_iter, 1e-9), "rest": 1.0 - dom_ms / max(ms_iter, 1e-9)},
+        "algorithmic_bytes_per_frame_iteration": per_frame,
+        "other_kernels": others,
     }
+    if persistent:
+        roofline.update({"launches_timed": int(prof.iter_launches), "avg_launch_ms": prof.ms_iter / smp,
+                         "timed_by": "CUDA events around every level_iter_kernel launch of the timed region, on the solver's stream",
+                         "solve_time_share": prof.ms_iter / max(ms_total, 1e-9)})
+    else:
+        roofline.update({"sampled_iterations": int(prof.samples), "avg_active_frames_per_launch": fl / smp,
+                         "iteration_time_share": {"dominant": dom_ms / max(ms_iter, 1e-9), "rest": 1.0 - dom_ms / max(ms_iter, 1e-9)}})
 
     # whole timed step on algorithmic bytes: every frame's iterations x bytes per frame-iteration over the step time
     # (includes assembly, verification and, for the level-scheduled path, the graph-replayed iterations that the
@@ -506,7 +545,8 @@ def run_b200(args):
             "detection": detection, "interpolation": interpolation,
             "solver": {"converged": converged, "iterations_mean": float(np.mean(info.iterations)),
                        "iterations_max": int(np.max(info.iterations)), "relres_max": float(np.max(info.relres)),
-                       "geometry_seconds": geom_s, "setup_seconds": time.time() - t0},
+                       "geometry_seconds": geom_s, "setup_seconds": time.time() - t0,
+                       "path": solver_path},
         }
         _emit(json.dumps(line))
     if world > 1:

@@ -114,10 +114,16 @@ typedef struct {
     /* block-multicolour ordering (reorder = 2), host-side launch metadata; n_colors = 0 otherwise */
     int32_t n_colors;
     int32_t color_tile_ptr[MOF_MAX_COLORS + 1];
-    /* level-scheduled ordering (reorder = 3): HOST array of n_levels+1 row offsets; n_levels = 0 otherwise */
+    /* level-scheduled ordering (reorder = 3); n_levels = 0 otherwise.
+     * level_ptr is the ONE HOST POINTER of this struct: n_levels+1 row offsets read by the host side of
+     * mof_pcg_solve_batch only (launch ranges of the per-level fallback path); kernels never dereference it. */
     int32_t n_levels;
     int32_t reserved_;
     const int32_t* level_ptr;
+    /* device, [2][N][8] int32, filled by mof_level_desc_build (may be NULL: the solver then falls back to one
+     * launch per dependency level): per row {first block, block count, first six columns} of the strictly
+     * upper ([0], backward sweep) and strictly lower ([1], forward sweep) part of the row. */
+    const int32_t* level_desc;
 } mof_mesh_dev;
 
 typedef struct {
@@ -138,6 +144,8 @@ typedef struct {
     double* partial;         /* [G][n_tiles][2][32] per-tile partial dot products       */
     double* scal;            /* [G][MOF_SCAL_SLOTS][32] per-frame scalars (r'z, p'Ap, r'r, ..., see csrc/mof_common.cuh) */
     int32_t* state;          /* [G][4][32]  active, iters, status, spare ; then [G] group_done, [G] tickets, groups_active, frames_active */
+    int32_t* ready;          /* [G][N]      level-scheduled SSOR, persistent kernel: stamp of the last sweep that finished the row
+                                            (may be NULL: per-level launches are used instead) */
 } mof_batch_dev;
 
 int64_t mof_num_tiles(int64_t n_vertices);                      /* ceil(N / MOF_TILE_ROWS) */
@@ -153,6 +161,11 @@ typedef struct {
     int64_t frame_launches;                 /* sum over samples of frames still iterating       */
     int64_t iterations_total;               /* iterations launched by the call(s)               */
     int64_t launches_total;                 /* kernel launches issued by the call(s)            */
+    /* level-scheduled SSOR, persistent kernel (level_iter_kernel: check_every whole iterations per launch) */
+    double ms_iter;                         /* summed CUDA-event duration of the level_iter_kernel launches */
+    int64_t iter_launches;                  /* number of those launches                          */
+    double phase_ns[4];                     /* in-kernel %globaltimer split of ms_iter: backward sweeps, forward
+                                               sweeps, p'Ap reduction, r update (each incl. its grid barrier) */
 } mof_pcg_profile;
 
 /* ------------------------------------------------------------------------- *
@@ -190,6 +203,11 @@ int mof_assemble_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, dou
 /* ------------------------------------------------------------------------- *
  * K2/K3: batched block-Jacobi PCG (replaces spsolve, :147).
  * ------------------------------------------------------------------------- */
+/* Row descriptors of the level-scheduled ordering for the persistent SSOR kernel: fills desc (device,
+ * 2*N*8 int32) from mesh->rowptr/col/diag; store the pointer in mesh->level_desc afterwards.  Synchronous.
+ * Returns 1 (and leaves desc unusable: keep level_desc NULL) if a row has more than 32 blocks on one side
+ * of its diagonal. */
+int mof_level_desc_build(const mof_mesh_dev* mesh, int32_t* desc, void* stream);
 /* y = A x for every group of the batch (x, y in the [G][N][2][32] layout).  Test and
  * roofline hook for the SpMV kernel that the solver uses. */
 int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const double* x,
@@ -211,6 +229,16 @@ int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, do
                         double omega, int32_t max_iter, int32_t check_every, int32_t max_restarts,
                         int32_t* iters, double* relres, int32_t* status, mof_pcg_profile* prof,
                         void* stream);
+/* Which code path the calling thread's last mof_pcg_solve_batch took (tests assert that the default is the
+ * persistent kernel and not a silent fallback).  Returns MOF_PATH_*; info (may be NULL) receives
+ * {path, grid size of the iteration kernel, its CTAs per SM, reason of a fallback to per-level launches:
+ * 0 none, 1 mesh->level_desc NULL, 2 batch->ready NULL, 3 too many groups, 4 switched off or N*G too large,
+ * 5 no cooperative launch, 6 kernel does not fit an SM}. */
+#define MOF_PATH_JACOBI 0
+#define MOF_PATH_MULTICOLOUR 1
+#define MOF_PATH_LEVEL_LAUNCHES 2
+#define MOF_PATH_LEVEL_PERSISTENT 3
+int mof_pcg_last_path(int32_t* info);
 /* x -> V[k][i + N*alpha] (reference order and layout, :149); V: device, row stride ld. */
 int mof_unpack_solution(const mof_mesh_dev* mesh, const mof_batch_dev* batch, double* V,
                         int64_t ld, void* stream);

@@ -17,6 +17,7 @@ DETECT_CHUNK = 1024  # MOF_DETECT_CHUNK
 MAX_COLORS = 16      # MOF_MAX_COLORS
 SCAL_SLOTS = 12      # MOF_SCAL_SLOTS
 
+PATH_JACOBI, PATH_MULTICOLOUR, PATH_LEVEL_LAUNCHES, PATH_LEVEL_PERSISTENT = 0, 1, 2, 3
 STATUS_CONVERGED, STATUS_MAXITER, STATUS_BREAKDOWN, STATUS_ZERO_RHS = 0, 1, 2, 3
 
 # every symbol include/mof_b200.h declares (tests check that the .so exports all of them)
@@ -27,7 +28,7 @@ EXPORTS = [
     "mof_num_tiles", "mof_state_ints",
     "mof_geom_basis", "mof_geom_gradw", "mof_geom_a2",
     "mof_pack_frames", "mof_assemble_batch",
-    "mof_spmv_batch", "mof_pcg_solve_batch", "mof_unpack_solution",
+    "mof_level_desc_build", "mof_spmv_batch", "mof_pcg_solve_batch", "mof_pcg_last_path", "mof_unpack_solution",
     "mof_tangent_to_xyz", "mof_vmax", "mof_singularity_flags", "mof_singularity_compact",
     "mof_classify_singularities", "mof_winding_numbers", "mof_wave_speed", "mof_rbf_fit", "mof_rbf_evaluate", "mof_csv_write", "mof_csv_dims", "mof_csv_read",
 ]
@@ -48,6 +49,7 @@ class MeshDev(Structure):
         ("e", c_void_p), ("grad_w", c_void_p), ("integral", c_void_p), ("areas", c_void_p), ("a2v", c_void_p),
         ("n_colors", c_int32), ("color_tile_ptr", c_int32 * (MAX_COLORS + 1)),
         ("n_levels", c_int32), ("reserved_", c_int32), ("level_ptr", c_void_p),     # level_ptr: HOST int32[n_levels+1]
+        ("level_desc", c_void_p),                                                   # device int32 [2][N][8] or NULL
     ]
 
 
@@ -57,7 +59,7 @@ class BatchDev(Structure):
         ("n_groups", c_int32), ("n_frames", c_int32),
         ("It", c_void_p), ("dIt", c_void_p), ("vals", c_void_p), ("rhs", c_void_p), ("minv", c_void_p),
         ("x", c_void_p), ("r", c_void_p), ("z", c_void_p), ("p", c_void_p), ("ap", c_void_p), ("t", c_void_p),
-        ("partial", c_void_p), ("scal", c_void_p), ("state", c_void_p),
+        ("partial", c_void_p), ("scal", c_void_p), ("state", c_void_p), ("ready", c_void_p),
     ]
 
 
@@ -67,7 +69,19 @@ class PcgProfile(Structure):
         ("ms_spmv", c_double), ("ms_update", c_double), ("ms_pupdate", c_double),
         ("samples", c_int64), ("group_launches", c_int64), ("frame_launches", c_int64),
         ("iterations_total", c_int64), ("launches_total", c_int64),
+        ("ms_iter", c_double), ("iter_launches", c_int64), ("phase_ns", c_double * 4),
     ]
+
+
+def add_profile(dst, src):
+    """dst += src, field by field (PcgProfile)."""
+    for name, ctype in PcgProfile._fields_:
+        a, b = getattr(dst, name), getattr(src, name)
+        if hasattr(a, "__len__"):
+            for i in range(len(a)):
+                a[i] += b[i]
+        else:
+            setattr(dst, name, a + b)
 
 
 _lib = None
@@ -105,11 +119,15 @@ def _declare(lib):
     lib.mof_pack_frames.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, P, c_int64, P, P]
     lib.mof_assemble_batch.restype = c_int
     lib.mof_assemble_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, c_double, P]
+    lib.mof_level_desc_build.restype = c_int
+    lib.mof_level_desc_build.argtypes = [POINTER(MeshDev), P, P]
     lib.mof_spmv_batch.restype = c_int
     lib.mof_spmv_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, P, P]
     lib.mof_pcg_solve_batch.restype = c_int
     lib.mof_pcg_solve_batch.argtypes = [POINTER(MeshDev), POINTER(BatchDev), c_double, c_double, c_int32, c_int32, c_int32, P, P, P,
                                         POINTER(PcgProfile), P]
+    lib.mof_pcg_last_path.restype = c_int
+    lib.mof_pcg_last_path.argtypes = [P]
     lib.mof_unpack_solution.restype = c_int
     lib.mof_unpack_solution.argtypes = [POINTER(MeshDev), POINTER(BatchDev), P, c_int64, P]
     lib.mof_tangent_to_xyz.restype = c_int

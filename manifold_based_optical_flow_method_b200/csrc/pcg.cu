@@ -35,8 +35,12 @@
 // launches per iteration replayed as a CUDA graph.
 // A frame that meets its threshold is frozen with (alpha, beta, zs) = (0, 1, 0) and can resume
 // exactly; a group whose frames are all frozen makes its CTAs return at once.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <vector>
 
 #include "mof_common.cuh"
 
@@ -50,6 +54,7 @@ constexpr int kPrefetchRows = 4;      // SSOR sweeps: matrix values are prefetch
 __device__ __forceinline__ double* scal_ptr(double* scal, int64_t g, int which) {
     return scal + ((size_t)g * MOF_S_COUNT + which) * MOF_W;
 }
+inline double* scal_host_ptr(double* scal, int64_t g, int which) { return scal + ((size_t)g * MOF_S_COUNT + which) * MOF_W; }
 __device__ __forceinline__ int32_t* state_ptr(int32_t* st, int64_t g, int which) {
     return st + ((size_t)g * MOF_I_COUNT + which) * MOF_W;
 }
@@ -213,12 +218,9 @@ __global__ void __launch_bounds__(256) spmv_kernel(const int32_t* __restrict__ r
 // true-residual check (init_kernel, MODE_VERIFY) asks for more iterations.
 // ---------------------------------------------------------------------------------
 template <bool SSOR>
-__global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N, int ntiles, double inv_omega) {
-    const int64_t g = blockIdx.y;
+__device__ __forceinline__ void update_body(const mof_batch_dev& B, int64_t N, int ntiles, double inv_omega, int tile, int64_t g) {
     const int G = B.n_groups;
-    if (group_done_ptr(B.state, G)[g]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x;
     const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
     const double alpha = scal_ptr(B.scal, g, MOF_S_ALPHA)[lane];
     double rz = 0.0, rr = 0.0;
@@ -290,6 +292,12 @@ __global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N,
     }
 }
 
+template <bool SSOR>
+__global__ void __launch_bounds__(256) update_kernel(mof_batch_dev B, int64_t N, int ntiles, double inv_omega) {
+    if (group_done_ptr(B.state, B.n_groups)[blockIdx.y]) return;
+    update_body<SSOR>(B, N, ntiles, inv_omega, blockIdx.x, blockIdx.y);
+}
+
 // K3b (block Jacobi): p = zs z + beta p at the start of an iteration
 __global__ void __launch_bounds__(256) pupdate_kernel(mof_batch_dev B, int64_t N) {
     const int64_t g = blockIdx.y;
@@ -320,6 +328,44 @@ __device__ __forceinline__ void prefetch_block_l2(const double* __restrict__ val
     const double* p = vals_l + (size_t)b * 4 * MOF_W;
 #pragma unroll
     for (int c = 0; c < 4; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c * MOF_W));
+}
+
+// Row arithmetic of the SSOR sweeps with every rounding spelled out (no compiler-chosen contraction), so
+// that the patch sweeps, the per-level launches and the persistent level kernel produce bit-identical
+// rows whatever code surrounds them.
+__device__ __forceinline__ void row_sub_block(double& a0, double& a1, double A0, double A1, double A2, double A3,
+                                              double v0, double v1) {
+    a0 = __dsub_rn(a0, __fma_rn(A1, v1, __dmul_rn(A0, v0)));
+    a1 = __dsub_rn(a1, __fma_rn(A3, v1, __dmul_rn(A2, v0)));
+}
+__device__ __forceinline__ double row_dir(double zsw, double r, double beta, double p) {       // zsw r + beta p
+    return __fma_rn(zsw, r, __dmul_rn(beta, p));
+}
+__device__ __forceinline__ double row_pdot(double p0, double p1, double q0, double q1) {       // p0 q0 + p1 q1
+    return __fma_rn(p1, q1, __dmul_rn(p0, q0));
+}
+
+// Validity bit of the level-scheduled sweeps.  The entries of t (backward sweep) and w (forward sweep) that
+// other rows gather carry, in the least significant mantissa bit, the parity of the frame's iteration counter
+// (state ITERS) at the time they were written: an active frame rewrites every entry once per iteration with
+// the opposite parity, so a reader that knows the frame's counter tells this iteration's value from last
+// iteration's by looking at the value itself -- one 8-byte load is both the "is it ready" poll and the gather,
+// and the writer needs no fence and no flag (a naturally aligned 8-byte store is single-copy atomic).  A frozen
+// frame keeps its counter, p and therefore t and w: for it the old and the new entry are the same number, so
+// either may be read.  The bit costs one ulp of t / w inside the preconditioner application, is a function of
+// the frame's own iteration count only (results stay independent of batching) and is applied by every kernel
+// of the level path, per-level launches included, so the paths stay bit-identical.
+__device__ __forceinline__ double with_parity(double v, int par) {
+    return __longlong_as_double((__double_as_longlong(v) & ~1LL) | (long long)par);
+}
+__device__ __forceinline__ bool has_parity(double v, int par) { return ((int)__double_as_longlong(v) & 1) == par; }
+__device__ __forceinline__ double ld_strong(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_strong(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 // What a sweep knows about a row one step before it is processed: its block range, the first
@@ -365,17 +411,13 @@ __device__ __forceinline__ void sweep_row_consume(const int32_t* __restrict__ co
     const int cnt = R.be - R.bs;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (k < cnt) {
-            a0 -= Bt.a[k][0] * Bt.v[k][0] + Bt.a[k][1] * Bt.v[k][1];
-            a1 -= Bt.a[k][2] * Bt.v[k][0] + Bt.a[k][3] * Bt.v[k][1];
-        }
+        if (k < cnt) row_sub_block(a0, a1, Bt.a[k][0], Bt.a[k][1], Bt.a[k][2], Bt.a[k][3], Bt.v[k][0], Bt.v[k][1]);
     }
     for (int32_t b = R.bs + 4; b < R.be; ++b) {            // rows with more than four blocks in this half (rare)
         const int64_t j = col[b];
         const double* ap = vals_l + (size_t)b * 4 * MOF_W;
         const double v0 = v_l[(size_t)(2 * j) * MOF_W], v1 = v_l[(size_t)(2 * j + 1) * MOF_W];
-        a0 -= __ldcs(ap) * v0 + __ldcs(ap + MOF_W) * v1;
-        a1 -= __ldcs(ap + 2 * MOF_W) * v0 + __ldcs(ap + 3 * MOF_W) * v1;
+        row_sub_block(a0, a1, __ldcs(ap), __ldcs(ap + MOF_W), __ldcs(ap + 2 * MOF_W), __ldcs(ap + 3 * MOF_W), v0, v1);
     }
 }
 
@@ -450,8 +492,8 @@ __global__ void __launch_bounds__(256, 2) sweep_back_kernel(const int32_t* __res
         if (MODE == 0) {
             x_l[(2 * i) * MOF_W] = x0;
             x_l[(2 * i + 1) * MOF_W] = x1;
-            a0 = zsw * cur.s[2] + beta * cur.s[0];
-            a1 = zsw * cur.s[3] + beta * cur.s[1];
+            a0 = row_dir(zsw, cur.s[2], beta, cur.s[0]);
+            a1 = row_dir(zsw, cur.s[3], beta, cur.s[1]);
             p_l[(2 * i) * MOF_W] = a0;
             p_l[(2 * i + 1) * MOF_W] = a1;
         } else {                                                    // back-transform of the complete iterate
@@ -523,14 +565,14 @@ __global__ void __launch_bounds__(256, 2) sweep_fwd_kernel(const int32_t* __rest
             if (MODE == 0) {
                 t0 = cur.s[2];
                 t1 = cur.s[3];
-                a0 -= kscale * t0;
-                a1 -= kscale * t1;
+                a0 = __fma_rn(-kscale, t0, a0);
+                a1 = __fma_rn(-kscale, t1, a1);
             }
             sweep_row_consume(col, vals_l, w_l, cur, bt, a0, a1);
             const double o0 = omega * a0, o1 = omega * a1;
             w_l[(2 * i) * MOF_W] = o0;
             w_l[(2 * i + 1) * MOF_W] = o1;
-            if (MODE == 0) dot += p0 * (t0 + o0) + p1 * (t1 + o1);
+            if (MODE == 0) dot += row_pdot(p0, p1, t0 + o0, t1 + o1);
             cur = nxt;
         }
     }
@@ -598,8 +640,8 @@ __global__ void __launch_bounds__(256) level_back_kernel(const int32_t* __restri
         const double r0 = r_l[(2 * i) * MOF_W], r1 = r_l[(2 * i + 1) * MOF_W];
         x_l[(2 * i) * MOF_W] = y0;
         x_l[(2 * i + 1) * MOF_W] = y1;
-        a0 = zsw * r0 + beta * p0;
-        a1 = zsw * r1 + beta * p1;
+        a0 = row_dir(zsw, r0, beta, p0);
+        a1 = row_dir(zsw, r1, beta, p1);
         p_l[(2 * i) * MOF_W] = a0;
         p_l[(2 * i + 1) * MOF_W] = a1;
     } else {
@@ -607,8 +649,11 @@ __global__ void __launch_bounds__(256) level_back_kernel(const int32_t* __restri
         a1 = y1;
     }
     sweep_row_consume(col, vals_l, t_l, R, bt, a0, a1);
-    t_l[(2 * i) * MOF_W] = omega * a0;
-    t_l[(2 * i + 1) * MOF_W] = omega * a1;
+    // validity bit (see with_parity): iteration -> parity of the frame's counter, back-transform -> the parity of
+    // the last iteration, so that a resumed frame's next sweep still finds the opposite one
+    const int par = (state_ptr(B.state, g, MOF_I_ITERS)[lane] + MODE) & 1;
+    t_l[(2 * i) * MOF_W] = with_parity(omega * a0, par);
+    t_l[(2 * i + 1) * MOF_W] = with_parity(omega * a1, par);
 }
 
 // MODE 0 also leaves the row's share of p'(t+w) in dots[g][row][lane]; level_dot_kernel adds them up.
@@ -642,164 +687,26 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const int32_t* __restric
         const double kscale = (2.0 - omega) / omega;
         t0 = t_l[(2 * i) * MOF_W];
         t1 = t_l[(2 * i + 1) * MOF_W];
-        a0 -= kscale * t0;
-        a1 -= kscale * t1;
+        a0 = __fma_rn(-kscale, t0, a0);
+        a1 = __fma_rn(-kscale, t1, a1);
     }
     sweep_row_consume(col, vals_l, w_l, R, bt, a0, a1);
-    const double o0 = omega * a0, o1 = omega * a1;
+    double o0 = omega * a0, o1 = omega * a1;
+    if (MODE == 0) {
+        const int par = state_ptr(B.state, g, MOF_I_ITERS)[lane] & 1;
+        o0 = with_parity(o0, par);
+        o1 = with_parity(o1, par);
+    }
     w_l[(2 * i) * MOF_W] = o0;
     w_l[(2 * i + 1) * MOF_W] = o1;
-    if (MODE == 0) dots[((size_t)g * N + i) * MOF_W + lane] = p0 * (t0 + o0) + p1 * (t1 + o1);
-}
-
-// Experimental (environment MOF_LEVEL_PDL=1, off by default, not yet measured): the iteration's level
-// kernels launched with programmatic stream serialization.  A level's indices and matrix values -- most of
-// its bytes -- depend on no earlier kernel, so a CTA of level l+1 may start while level l drains, issue
-// those loads, and only then wait (griddepcontrol.wait) for everything before it to complete; every
-// load of data written by other kernels (vectors, scalars, the group_done flags) and every store come
-// after the wait.  Same arithmetic as level_back_kernel<0> / level_fwd_kernel<0>.
-struct RowStatic {
-    RowPre R;
-    double a[4][4];
-};
-
-__device__ __forceinline__ void level_static_loads(const int32_t* __restrict__ col, const double* __restrict__ vals_l,
-                                                   RowStatic& S) {
-    const int cnt = S.R.be - S.R.bs;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (k < cnt) {
-            S.R.c[k] = col[S.R.bs + k];
-            const double* ap = vals_l + (size_t)(S.R.bs + k) * 4 * MOF_W;
-            S.a[k][0] = __ldcs(ap);
-            S.a[k][1] = __ldcs(ap + MOF_W);
-            S.a[k][2] = __ldcs(ap + 2 * MOF_W);
-            S.a[k][3] = __ldcs(ap + 3 * MOF_W);
-        }
-}
-
-__device__ __forceinline__ void level_dependent_part(const int32_t* __restrict__ col, const double* __restrict__ vals_l,
-                                                     const double* v_l, const RowStatic& S, double& a0, double& a1) {
-    const int cnt = S.R.be - S.R.bs;
-    double v[4][2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (k < cnt) {
-            v[k][0] = v_l[(size_t)(2 * (int64_t)S.R.c[k]) * MOF_W];
-            v[k][1] = v_l[(size_t)(2 * (int64_t)S.R.c[k] + 1) * MOF_W];
-        }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (k < cnt) {
-            a0 -= S.a[k][0] * v[k][0] + S.a[k][1] * v[k][1];
-            a1 -= S.a[k][2] * v[k][0] + S.a[k][3] * v[k][1];
-        }
-    for (int32_t b = S.R.bs + 4; b < S.R.be; ++b) {
-        const int64_t j = col[b];
-        const double* ap = vals_l + (size_t)b * 4 * MOF_W;
-        const double v0 = v_l[(size_t)(2 * j) * MOF_W], v1 = v_l[(size_t)(2 * j + 1) * MOF_W];
-        a0 -= __ldcs(ap) * v0 + __ldcs(ap + MOF_W) * v1;
-        a1 -= __ldcs(ap + 2 * MOF_W) * v0 + __ldcs(ap + 3 * MOF_W) * v1;
-    }
-}
-
-__global__ void __launch_bounds__(256) level_back_pdl_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                             const int32_t* __restrict__ diag, mof_batch_dev B, double* tout,
-                                                             int64_t N, int64_t nb, int r_lo, int r_hi, double omega) {
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int64_t g = blockIdx.y;
-    const int G = B.n_groups;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = r_lo + blockIdx.x * kWarps + warp;
-    const bool live = row < r_hi;
-    const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
-    RowStatic S;
-    S.R.bs = S.R.be = 0;
-    if (live) {
-        S.R.be = rowptr[row + 1];
-        S.R.bs = diag[row] + 1;
-        level_static_loads(col, vals_l, S);
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (!live || group_done_ptr(B.state, G)[g]) return;
-    const size_t i = (size_t)row;
-    const double* r_l = B.r + (size_t)g * N * 2 * MOF_W + lane;
-    double* p_l = B.p + (size_t)g * N * 2 * MOF_W + lane;
-    double* x_l = B.x + (size_t)g * N * 2 * MOF_W + lane;
-    double* t_l = tout + (size_t)g * N * 2 * MOF_W + lane;
-    const double p0 = p_l[(2 * i) * MOF_W], p1 = p_l[(2 * i + 1) * MOF_W];
-    const double x0 = x_l[(2 * i) * MOF_W], x1 = x_l[(2 * i + 1) * MOF_W];
-    const double r0 = r_l[(2 * i) * MOF_W], r1 = r_l[(2 * i + 1) * MOF_W];
-    const double alpha = scal_ptr(B.scal, g, MOF_S_ALPHA)[lane];
-    const double beta = scal_ptr(B.scal, g, MOF_S_BETA)[lane];
-    const double zsw = scal_ptr(B.scal, g, MOF_S_ZS)[lane] / omega;
-    x_l[(2 * i) * MOF_W] = fma(alpha, p0, x0);
-    x_l[(2 * i + 1) * MOF_W] = fma(alpha, p1, x1);
-    double a0 = zsw * r0 + beta * p0, a1 = zsw * r1 + beta * p1;
-    p_l[(2 * i) * MOF_W] = a0;
-    p_l[(2 * i + 1) * MOF_W] = a1;
-    level_dependent_part(col, vals_l, t_l, S, a0, a1);
-    t_l[(2 * i) * MOF_W] = omega * a0;
-    t_l[(2 * i + 1) * MOF_W] = omega * a1;
-}
-
-__global__ void __launch_bounds__(256) level_fwd_pdl_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                            const int32_t* __restrict__ diag, mof_batch_dev B, const double* pin,
-                                                            double* wout, double* dots, int64_t N, int64_t nb, int r_lo,
-                                                            int r_hi, double omega) {
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int64_t g = blockIdx.y;
-    const int G = B.n_groups;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = r_lo + blockIdx.x * kWarps + warp;
-    const bool live = row < r_hi;
-    const double* __restrict__ vals_l = B.vals + (size_t)g * nb * 4 * MOF_W + lane;
-    RowStatic S;
-    S.R.bs = S.R.be = 0;
-    if (live) {
-        S.R.bs = rowptr[row];
-        S.R.be = diag[row];
-        level_static_loads(col, vals_l, S);
-    }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (!live || group_done_ptr(B.state, G)[g]) return;
-    const size_t i = (size_t)row;
-    const double* p_l = pin + (size_t)g * N * 2 * MOF_W + lane;
-    const double* t_l = B.t + (size_t)g * N * 2 * MOF_W + lane;
-    double* w_l = wout + (size_t)g * N * 2 * MOF_W + lane;
-    const double p0 = p_l[(2 * i) * MOF_W], p1 = p_l[(2 * i + 1) * MOF_W];
-    const double t0 = t_l[(2 * i) * MOF_W], t1 = t_l[(2 * i + 1) * MOF_W];
-    const double kscale = (2.0 - omega) / omega;
-    double a0 = p0 - kscale * t0, a1 = p1 - kscale * t1;
-    level_dependent_part(col, vals_l, w_l, S, a0, a1);
-    const double o0 = omega * a0, o1 = omega * a1;
-    w_l[(2 * i) * MOF_W] = o0;
-    w_l[(2 * i + 1) * MOF_W] = o1;
-    dots[((size_t)g * N + i) * MOF_W + lane] = p0 * (t0 + o0) + p1 * (t1 + o1);
-}
-
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (MODE == 0) dots[((size_t)g * N + i) * MOF_W + lane] = row_pdot(p0, p1, t0 + o0, t1 + o1);
 }
 
 // p'Ap = sum of the per-row shares (tile by tile, rows in order: deterministic), then alpha.
-__global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const double* __restrict__ dots, int64_t N, int ntiles) {
-    const int64_t g = blockIdx.y;
+__device__ __forceinline__ void level_dot_body(const mof_batch_dev& B, const double* __restrict__ dots, int64_t N, int ntiles,
+                                               int tile, int64_t g) {
     const int G = B.n_groups;
-    if (group_done_ptr(B.state, G)[g]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x;
     const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
     double acc = 0.0;
 #pragma unroll
@@ -810,6 +717,413 @@ __global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const d
     double val[1] = {acc}, tot[1];
     if (!tile_reduce<1>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot)) return;
     if (warp == 0) finalize_alpha(tot[0], B.scal, B.state, g, G, lane);
+}
+
+__global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const double* __restrict__ dots, int64_t N, int ntiles) {
+    if (group_done_ptr(B.state, B.n_groups)[blockIdx.y]) return;
+    level_dot_body(B, dots, N, ntiles, blockIdx.x, blockIdx.y);
+}
+
+// ---------------------------------------------------------------------------------
+// Persistent level-scheduled SSOR iteration (the default of the level path).
+//
+// The per-level launches above cost a kernel boundary (a GPU-wide barrier plus a launch gap) per
+// dependency level, 2 x 1024 per iteration at ico7, and leave every row's loads exposed behind it.  Here
+// ONE cooperative launch runs `n_iter` whole PCG iterations.  Inside a sweep there is no barrier at all:
+// the rows of all active groups form one static work list in dependency order (forward: item J = row * A
+// + a, backward: rows descending; A = groups still iterating), warp w of the grid owns items w, w + W, ...
+// and a row waits only for the rows it actually reads, through one int32 `ready` stamp per (group, row):
+//   consumer: ld.acquire.gpu of the stamps of its <= 6 neighbours, then the gather of their t / w (L2),
+//   producer: stores, __threadfence, stamp.
+// Every item depends on items earlier in the list only, each warp walks its items in list order and all
+// CTAs are co-resident (cooperative launch), so the earliest unfinished item can always run: no deadlock.
+// Everything of a row that does not depend on the sweep (its matrix blocks -- contiguous in the level-major
+// numbering -- and its own entries of p, r, x / p, t) is fetched one item ahead by 1-D bulk async copies
+// (cp.async.bulk -> UBLKCP, completion on an mbarrier) into the warp's shared-memory stage while the warp is
+// still inside the previous item's dependent chain, so that chain is poll -> gather -> FMAs -> store.
+// The four phases of an iteration (backward sweep, forward sweep, p'Ap -> alpha, r update -> beta and the
+// convergence test) are separated by grid barriers; alpha, beta and the group_done flags never leave the
+// device.  Per-row arithmetic and the order of every reduction are those of the per-level kernels: results
+// are bit-identical to them and independent of grid size, batch composition and GPU.
+// ---------------------------------------------------------------------------------
+constexpr int kStageBlocks = 4;                                       // matrix blocks of a row staged in shared memory
+constexpr int kStageValBytes = kStageBlocks * 4 * MOF_W * 8;          // 4096
+constexpr int kStageVecBytes = 2 * MOF_W * 8;                         // one row of one vector: 512
+constexpr int kStageBytes = kStageValBytes + 3 * kStageVecBytes;      // 5632 per warp
+constexpr int kPersistMaxGroups = 1024;                               // active-group list kept in shared memory (uint16)
+constexpr int kDescInts = 8;                                          // per row and direction: bs, cnt, col[0..5]
+constexpr int kDescCols = kDescInts - 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned), streamed through L2
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
+    int32_t v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(int32_t* p, int32_t v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Row descriptors of the level path, built once per mesh: desc[dir][row] = {first block, block count,
+// first six column indices} of the strictly upper (dir 0, backward sweep) / lower (dir 1, forward sweep)
+// part of the row.  One 32-byte load per item replaces the rowptr/diag -> col chain.
+__global__ void level_desc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                  const int32_t* __restrict__ diag, int64_t N, int32_t* __restrict__ desc,
+                                  int32_t* __restrict__ max_cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * N) return;
+    const int dir = i >= N;
+    const int64_t row = dir ? i - N : i;
+    const int32_t bs = dir ? rowptr[row] : diag[row] + 1;
+    const int32_t be = dir ? diag[row] : rowptr[row + 1];
+    int32_t* d = desc + (size_t)i * kDescInts;
+    d[0] = bs;
+    d[1] = be - bs;
+    for (int k = 0; k < kDescCols; ++k) d[2 + k] = bs + k < be ? col[bs + k] : -1;
+    if (be - bs > 32) atomicMax(max_cnt, be - bs);
+}
+
+struct LevelArgs {
+    const int32_t* desc;          // [2][N][8]
+    const int32_t* col;
+    mof_batch_dev B;
+    int64_t N, nb;
+    int ntiles;
+    double omega, inv_omega;
+    unsigned long long* probe;    // development probe (MOF_LEVEL_PROBE=1), else NULL: [0..15] summed SM cycles per item
+                                  // segment and item counts, [16 + dir*N + row] = %globaltimer when group act[0] finished the row
+};
+
+// One warp, one sweep.  DIR 0: backward (rows descending, upper blocks), DIR 1: forward.
+//   DIR 0 MODE 0: x += alpha p_old ; p <- zs r/omega + beta p_old ; t = (Dt+U)^-1 p        (vout = B.t)
+//   DIR 0 MODE 1: vout = (Dt+U)^-1 (x + alpha p)                                           (back-transform)
+//   DIR 1 MODE 0: w = (Dt+L)^-1 (p - ((2-omega)/omega) t) ; dots[row] = p.(t + w)          (vin = B.p, vout = B.ap)
+//   DIR 1 MODE 1: vout = (Dt+L)^-1 vin
+// act == nullptr: all groups (A = n_groups).
+template <int DIR, int MODE, bool PROBE = false>
+__device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const double* vin, double* vout, double* dots,
+                                                  const uint16_t* act, int A, int32_t stamp, unsigned char* stage,
+                                                  uint32_t bar, uint32_t& parity, uint64_t policy) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t N = (uint32_t)a.N;
+    const uint32_t total = N * (uint32_t)A;                           // host guarantees N * n_groups < 2^31
+    const uint32_t W = gridDim.x * kWarps, uA = (uint32_t)A;
+    uint32_t J = blockIdx.x * kWarps + warp;
+    if (J >= total) return;
+    const int32_t* __restrict__ desc = a.desc + (DIR ? (size_t)N * kDescInts : 0);
+    const mof_batch_dev& B = a.B;
+    const double omega = a.omega;
+    constexpr int nvec = (DIR == 0) ? (MODE == 0 ? 3 : 2) : (MODE == 0 ? 2 : 1);
+    const uint32_t stage_s = smem_u32(stage);
+    const double* sv = reinterpret_cast<const double*>(stage) + lane;
+    const double* sx = reinterpret_cast<const double*>(stage + kStageValBytes) + lane;
+
+    // item J -> (row, group); everything of the item that does not depend on the sweep goes into the stage
+    auto item = [&](uint32_t j, uint32_t& irow, uint32_t& ig) {
+        const uint32_t q = j / uA;
+        irow = DIR ? q : N - 1 - q;
+        ig = act ? act[j - q * uA] : j - q * uA;
+    };
+    auto issue = [&](uint32_t irow, uint32_t ig, int32_t d) {
+        const int32_t bs = __shfl_sync(kFull, d, 0), cnt = __shfl_sync(kFull, d, 1);
+        if (lane == 0) {
+            const int nstage = cnt < kStageBlocks ? cnt : kStageBlocks;
+            const size_t vo = ((size_t)ig * N + irow) * 2 * MOF_W;
+            mbar_expect_tx(bar, (uint32_t)(nstage * 4 * MOF_W * 8 + nvec * kStageVecBytes));
+            if (nstage > 0)
+                bulk_g2s(stage_s, B.vals + ((size_t)ig * a.nb + bs) * 4 * MOF_W, (uint32_t)(nstage * 4 * MOF_W * 8), bar, policy);
+            if (DIR == 0) {
+                bulk_g2s(stage_s + kStageValBytes, B.p + vo, kStageVecBytes, bar, policy);
+                bulk_g2s(stage_s + kStageValBytes + kStageVecBytes, B.x + vo, kStageVecBytes, bar, policy);
+                if (MODE == 0) bulk_g2s(stage_s + kStageValBytes + 2 * kStageVecBytes, B.r + vo, kStageVecBytes, bar, policy);
+            } else {
+                bulk_g2s(stage_s + kStageValBytes, vin + vo, kStageVecBytes, bar, policy);
+                if (MODE == 0) bulk_g2s(stage_s + kStageValBytes + kStageVecBytes, B.t + vo, kStageVecBytes, bar, policy);
+            }
+        }
+    };
+    uint32_t row, g, gprev = 0xffffffffu;
+    item(J, row, g);
+    int32_t cd = __ldg(desc + (size_t)row * kDescInts + (lane & 7)), nd = 0;
+    issue(row, g, cd);
+    // per-frame scalars of the item's group: re-read only when the group changes (with W a multiple of A, never)
+    double s_alpha = 0.0, s_beta = 0.0, s_zsw = 0.0;
+    int par = 0;
+    long long probe_prev = PROBE ? clock64() : 0, pacc[5] = {0, 0, 0, 0, 0};
+
+    for (;;) {
+        const uint32_t Jn = J + W;
+        const bool more = Jn < total;
+        uint32_t rown = 0, gn = 0;
+        if (more) {
+            item(Jn, rown, gn);
+            nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
+        }
+        if (g != gprev) {                                // these loads overlap the gather below
+            const int iters = __ldcg(state_ptr(B.state, g, MOF_I_ITERS) + lane);
+            par = (MODE == 0 ? iters : iters + 1) & 1;
+            if (DIR == 0) {
+                s_alpha = __ldcg(scal_ptr(B.scal, g, MOF_S_ALPHA) + lane);
+                if (MODE == 0) {
+                    s_beta = __ldcg(scal_ptr(B.scal, g, MOF_S_BETA) + lane);
+                    s_zsw = __ldcg(scal_ptr(B.scal, g, MOF_S_ZS) + lane) / omega;
+                }
+            }
+            gprev = g;
+        }
+        const int32_t bs = __shfl_sync(kFull, cd, 0), cnt = __shfl_sync(kFull, cd, 1);
+        double* v_l = vout + ((size_t)g * N) * 2 * MOF_W + lane;          // the sweep's own output, gathered from finished rows
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+        if (PROBE) tk0 = clock64();
+        // MODE 0: the gathered entries carry their own validity bit (with_parity); MODE 1: ready stamps
+        if (MODE == 1) {
+            int32_t mycol = __shfl_sync(kFull, cd, 2 + (lane < kDescCols ? lane : 0));
+            if (lane < cnt) {
+                if (lane >= kDescCols) mycol = __ldg(a.col + bs + lane);
+                const int32_t* f = B.ready + (size_t)g * N + mycol;
+                while (ld_acquire(f) < stamp) {}
+            }
+            __syncwarp();
+        }
+        double gv[kStageBlocks][2];
+        {
+            uint32_t co[kStageBlocks];
+#pragma unroll
+            for (int k = 0; k < kStageBlocks; ++k) co[k] = (uint32_t)__shfl_sync(kFull, cd, 2 + k) * (2 * MOF_W);
+            for (;;) {
+#pragma unroll
+                for (int k = 0; k < kStageBlocks; ++k)
+                    if (k < cnt) {
+                        gv[k][0] = ld_strong(v_l + co[k]);
+                        gv[k][1] = ld_strong(v_l + co[k] + MOF_W);
+                    }
+                if (MODE == 1) break;
+                bool ok = true;
+#pragma unroll
+                for (int k = 0; k < kStageBlocks; ++k)
+                    if (k < cnt) ok = ok && has_parity(gv[k][0], par) && has_parity(gv[k][1], par);
+                if (__all_sync(kFull, ok)) break;
+            }
+        }
+        if (PROBE) tk1 = clock64();
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        if (PROBE) tk2 = clock64();
+        v_l += (size_t)row * 2 * MOF_W;                                   // -> this row's entry of the output
+        double a0, a1, q0 = 0.0, q1 = 0.0;                                // q: what the row's share of p'Ap needs (forward, MODE 0)
+        if (DIR == 0) {
+            const double p0 = sx[0], p1 = sx[MOF_W];
+            const double y0 = fma(s_alpha, p0, sx[2 * MOF_W]), y1 = fma(s_alpha, p1, sx[3 * MOF_W]);   // pending step of the previous iteration
+            if (MODE == 0) {
+                const size_t vo = ((size_t)g * N + row) * 2 * MOF_W + lane;
+                a0 = row_dir(s_zsw, sx[4 * MOF_W], s_beta, p0);
+                a1 = row_dir(s_zsw, sx[5 * MOF_W], s_beta, p1);
+                __stcs(B.x + vo, y0);
+                __stcs(B.x + vo + MOF_W, y1);
+                __stcs(B.p + vo, a0);
+                __stcs(B.p + vo + MOF_W, a1);
+            } else {
+                a0 = y0;
+                a1 = y1;
+            }
+        } else {
+            a0 = sx[0];
+            a1 = sx[MOF_W];
+            if (MODE == 0) {
+                const double kscale = (2.0 - omega) / omega;
+                a0 = __fma_rn(-kscale, sx[2 * MOF_W], a0);
+                a1 = __fma_rn(-kscale, sx[3 * MOF_W], a1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kStageBlocks; ++k)
+            if (k < cnt)
+                row_sub_block(a0, a1, sv[(4 * k) * MOF_W], sv[(4 * k + 1) * MOF_W], sv[(4 * k + 2) * MOF_W], sv[(4 * k + 3) * MOF_W],
+                              gv[k][0], gv[k][1]);
+        if (cnt > kStageBlocks) {                                        // rows with more blocks in this half (rare)
+            const double* vals_l = B.vals + (size_t)g * a.nb * 4 * MOF_W + lane;
+            const double* g_l = vout + ((size_t)g * N) * 2 * MOF_W + lane;
+#pragma unroll 1
+            for (int k = kStageBlocks; k < cnt; ++k) {
+                const int32_t dk = __shfl_sync(kFull, cd, 2 + (k < kDescCols ? k : 0));
+                const int64_t j = k < kDescCols ? dk : __ldg(a.col + bs + k);
+                const double* ap = vals_l + (size_t)(bs + k) * 4 * MOF_W;
+                double v0, v1;
+                for (;;) {
+                    v0 = ld_strong(g_l + (size_t)(2 * j) * MOF_W);
+                    v1 = ld_strong(g_l + (size_t)(2 * j + 1) * MOF_W);
+                    if (MODE == 1 || __all_sync(kFull, has_parity(v0, par) && has_parity(v1, par))) break;
+                }
+                row_sub_block(a0, a1, __ldcs(ap), __ldcs(ap + MOF_W), __ldcs(ap + 2 * MOF_W), __ldcs(ap + 3 * MOF_W), v0, v1);
+            }
+        }
+        double o0 = omega * a0, o1 = omega * a1;
+        if (MODE == 0 || DIR == 0) {
+            o0 = with_parity(o0, par);
+            o1 = with_parity(o1, par);
+        }
+        st_strong(v_l, o0);
+        st_strong(v_l + MOF_W, o1);
+        if (DIR == 1 && MODE == 0) {
+            q0 = sx[2 * MOF_W] + o0;
+            q1 = sx[3 * MOF_W] + o1;
+            q0 = row_pdot(sx[0], sx[MOF_W], q0, q1);
+        }
+        __syncwarp();                                                    // every lane is done with the stage
+        if (MODE == 1) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) st_relaxed(B.ready + (size_t)g * N + row, stamp);
+        }
+        if (PROBE) tk3 = clock64();
+        if (more) issue(rown, gn, nd);                                   // the next item's static data
+        if (DIR == 1 && MODE == 0) __stcs(dots + ((size_t)g * N + row) * MOF_W + lane, q0);
+        if (PROBE) {
+            pacc[0] += tk1 - tk0;                  // poll + gather
+            pacc[1] += tk2 - tk1;                  // stage wait
+            pacc[2] += tk3 - tk2;                  // arithmetic + result stores
+            pacc[3] += tk0 - probe_prev;           // previous item's tail + loop head
+            pacc[4] += 1;
+            probe_prev = clock64();
+            if (lane == 0 && act && g == act[0]) a.probe[16 + (size_t)DIR * N + row] = global_ns();
+        }
+        if (!more) break;
+        J = Jn; row = rown; g = gn; cd = nd;
+    }
+    if (PROBE && lane == 0)
+        for (int k = 0; k < 5; ++k) atomicAdd(a.probe + DIR * 8 + k, (unsigned long long)pacc[k]);
+}
+
+// Ordered list of the groups still iterating -> act[0..A) (shared memory); returns A to every thread.
+__device__ __forceinline__ int build_active_list(const int32_t* group_done, int G, uint16_t* act, int* s_count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (warp == 0) {
+        int n = 0;
+        for (int g0 = 0; g0 < G; g0 += 32) {
+            const int g = g0 + lane;
+            const bool on = g < G && __ldcg(group_done + g) == 0;
+            const unsigned m = __ballot_sync(kFull, on);
+            if (on) act[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)g;
+            n += __popc(m);
+        }
+        if (lane == 0) *s_count = n;
+    }
+    __syncthreads();
+    return *s_count;
+}
+
+struct PersistShared {
+    uint64_t bar[kWarps];
+    uint16_t act[kPersistMaxGroups];
+    int count;
+    unsigned long long tprev, tacc[4];     // phase clock of CTA 0 (profile)
+};
+
+__device__ __forceinline__ void persist_setup(PersistShared& S) {
+    if (threadIdx.x < kWarps) mbar_init(smem_u32(&S.bar[threadIdx.x]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+}
+
+// grid barrier + make what other SMs wrote with ordinary stores visible to this thread's bulk copies
+__device__ __forceinline__ void phase_barrier(cooperative_groups::grid_group& grid) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    grid.sync();
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// n_iter PCG iterations (or fewer if every group converges earlier).  stamp0: value of the last stamp used
+// in B.ready; the sweeps of iteration i use stamp0 + 2 i + 1 and stamp0 + 2 i + 2.
+template <int MINB, bool PROBE>   // MINB: CTAs per SM the register budget is cut for (4: 64 registers, 3: 80)
+__global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int n_iter, int32_t stamp0, int timing) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ PersistShared S;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int warp = threadIdx.x >> 5;
+    const mof_batch_dev& B = a.B;
+    const int G = B.n_groups;
+    persist_setup(S);
+    unsigned char* stage = dyn_smem + (size_t)warp * kStageBytes;
+    const uint32_t bar = smem_u32(&S.bar[warp]);
+    uint32_t parity = 0;
+    const uint64_t policy = policy_evict_first();
+    double* dots = B.z;
+    const bool clock = timing && blockIdx.x == 0 && threadIdx.x == 0;
+    if (clock) {
+        S.tprev = global_ns();
+        for (int k = 0; k < 4; ++k) S.tacc[k] = 0;
+    }
+    auto lap = [&](int k) {
+        if (clock) { const unsigned long long t = global_ns(); S.tacc[k] += t - S.tprev; S.tprev = t; }
+    };
+    for (int it = 0; it < n_iter; ++it) {
+        const int A = build_active_list(group_done_ptr(B.state, G), G, S.act, &S.count);
+        if (A == 0) break;
+        level_sweep_phase<0, 0, PROBE>(a, nullptr, B.t, nullptr, S.act, A, stamp0 + 2 * it + 1, stage, bar, parity, policy);
+        phase_barrier(grid);
+        lap(0);
+        level_sweep_phase<1, 0, PROBE>(a, B.p, B.ap, dots, S.act, A, stamp0 + 2 * it + 2, stage, bar, parity, policy);
+        phase_barrier(grid);
+        lap(1);
+        const int64_t items = (int64_t)a.ntiles * A;
+        for (int64_t q = blockIdx.x; q < items; q += gridDim.x) {
+            level_dot_body(B, dots, a.N, a.ntiles, (int)(q / A), S.act[q % A]);
+            __syncthreads();
+        }
+        phase_barrier(grid);
+        lap(2);
+        for (int64_t q = blockIdx.x; q < items; q += gridDim.x) {
+            update_body<true>(B, a.N, a.ntiles, a.inv_omega, (int)(q / A), S.act[q % A]);
+            __syncthreads();
+        }
+        phase_barrier(grid);
+        lap(3);
+    }
+    if (clock) {                                   // accumulated phase times (ns) of this solve: profile only
+        double* acc = scal_ptr(B.scal, 0, MOF_S_SPARE);
+        for (int k = 0; k < 4; ++k) acc[k] += (double)S.tacc[k];
+    }
+}
+
+// A single sweep of all groups (start: r = (Dt+L)^-1 b ; end: xs = (Dt+U)^-1 (xhat + alpha p)).
+template <int DIR>
+__global__ void __launch_bounds__(256, 4) level_sweep_kernel(LevelArgs a, const double* vin, double* vout, int32_t stamp) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ PersistShared S;
+    const int warp = threadIdx.x >> 5;
+    persist_setup(S);
+    uint32_t parity = 0;
+    level_sweep_phase<DIR, 1>(a, vin, vout, nullptr, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * kStageBytes,
+                              smem_u32(&S.bar[warp]), parity, policy_evict_first());
 }
 
 // ---------------------------------------------------------------------------------
@@ -823,8 +1137,11 @@ __global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const d
 // ---------------------------------------------------------------------------------
 enum { MODE_START_JACOBI = 0, MODE_NORM = 1, MODE_START_SSOR = 2, MODE_VERIFY = 3 };
 
+// fill_parity (level path, MODE_START_SSOR): t and w start with the validity bit of "one iteration ago".
+// ax: A x of MODE_VERIFY.
 __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, int ntiles, int mode, double tol2,
-                                                   int last_round, int ssor, double inv_omega) {
+                                                   int last_round, int ssor, double inv_omega, int fill_parity,
+                                                   const double* __restrict__ ax) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -839,7 +1156,7 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
         double r0, r1;
         if (mode == MODE_START_SSOR) { r0 = B.r[i0]; r1 = B.r[i1]; }
         else                         { r0 = B.rhs[i0]; r1 = B.rhs[i1]; }
-        if (mode == MODE_VERIFY) { r0 -= B.ap[i0]; r1 -= B.ap[i1]; }
+        if (mode == MODE_VERIFY) { r0 -= ax[i0]; r1 -= ax[i1]; }
         if (ssor && (mode == MODE_VERIFY || mode == MODE_NORM)) {      // back to the unscaled system: S^-1 r
             const double s0 = B.minv[im], s1 = B.minv[im + MOF_W], s2 = B.minv[im + 2 * MOF_W];
             const double rdet = 1.0 / (s0 * s2 - s1 * s1);
@@ -857,6 +1174,11 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
         if (mode == MODE_START_JACOBI || mode == MODE_START_SSOR) {
             B.x[i0] = 0.0; B.x[i1] = 0.0;
             B.p[i0] = 0.0; B.p[i1] = 0.0;
+        }
+        if (fill_parity) {
+            const double stale = with_parity(0.0, 1);
+            B.t[i0] = stale; B.t[i1] = stale;
+            B.ap[i0] = stale; B.ap[i1] = stale;
         }
         rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
     }
@@ -923,6 +1245,29 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
     }
 }
 
+// Level path, after a verification that makes frames resume: a resuming frame's counter did not move while
+// it was frozen, so its stale w entries (and, had the back-transform not rewritten them, t) carry exactly the
+// parity its next sweep will wait for.  Give every entry of the resuming frames the opposite one; their old
+// values are never used as data again.
+__global__ void __launch_bounds__(256) restamp_kernel(mof_batch_dev B, int64_t N) {
+    const int64_t g = blockIdx.y;
+    const int G = B.n_groups;
+    if (group_done_ptr(B.state, G)[g]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (!state_ptr(B.state, g, MOF_I_ACTIVE)[lane]) return;
+    const int stale = (state_ptr(B.state, g, MOF_I_ITERS)[lane] + 1) & 1;
+    const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int64_t v = row0 + q;
+        if (v >= N) break;
+        const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
+        B.t[i0] = with_parity(B.t[i0], stale);
+        B.t[i1] = with_parity(B.t[i1], stale);
+        B.ap[i0] = with_parity(B.ap[i0], stale);
+        B.ap[i1] = with_parity(B.ap[i1], stale);
+    }
+}
+
 // SSOR path, end of the solve: x = S xs with xs (solution of the scaled system) in B.t
 __global__ void __launch_bounds__(256) unscale_kernel(mof_batch_dev B, int64_t N) {
     const int64_t g = blockIdx.y;
@@ -935,8 +1280,10 @@ __global__ void __launch_bounds__(256) unscale_kernel(mof_batch_dev B, int64_t N
         const size_t im = mof_ix_minv(N, g, v, 0) + lane;
         const double s0 = B.minv[im], s1 = B.minv[im + MOF_W], s2 = B.minv[im + 2 * MOF_W];
         const double t0 = B.t[i0], t1 = B.t[i1];
-        B.x[i0] = s0 * t0 + s1 * t1;
-        B.x[i1] = s1 * t0 + s2 * t1;
+        // a frame with f = 0 has V = 0 exactly (spsolve(a, 0) = 0); its t may carry the validity bit of the level path
+        const bool zero = state_ptr(B.state, g, MOF_I_STATUS)[lane] == MOF_STATUS_ZERO_RHS;
+        B.x[i0] = zero ? 0.0 : s0 * t0 + s1 * t1;
+        B.x[i1] = zero ? 0.0 : s1 * t0 + s2 * t1;
     }
 }
 
@@ -977,8 +1324,36 @@ int check_batch(const mof_mesh_dev* mesh, const mof_batch_dev* b) {
 
 }  // namespace
 
+namespace {
+thread_local int32_t g_last_path[4] = {0, 0, 0, 0};   // path, grid of the iteration kernel, CTAs per SM, reason of a fallback
+}
+extern "C" int mof_pcg_last_path(int32_t* info) {
+    if (info) for (int k = 0; k < 4; ++k) info[k] = g_last_path[k];
+    return g_last_path[0];
+}
+
 extern "C" int64_t mof_state_ints(int32_t n_groups) {
     return (int64_t)n_groups * MOF_I_COUNT * MOF_W + 2 * (int64_t)n_groups + 2;
+}
+
+extern "C" int mof_level_desc_build(const mof_mesh_dev* mesh, int32_t* desc, void* stream) {
+    MOF_REQUIRE(mesh && desc && mesh->rowptr && mesh->col && mesh->diag, "NULL argument");
+    cudaStream_t st = mof_stream(stream);
+    const int64_t N = mesh->n_vertices;
+    int32_t* d_max = nullptr;
+    MOF_CUDA_TRY(cudaMalloc(&d_max, sizeof(int32_t)));
+    cudaError_t e = cudaMemsetAsync(d_max, 0, sizeof(int32_t), st);
+    if (e == cudaSuccess) {
+        level_desc_kernel<<<mof_cdiv(2 * N, 256), 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, N, desc, d_max);
+        e = cudaGetLastError();
+    }
+    int32_t h_max = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_max, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_max);
+    if (e != cudaSuccess) return mof_set_error(-100 - (int)e, "mof_level_desc_build failed: %s", cudaGetErrorString(e));
+    if (h_max > 32) return mof_set_error(1, "mof_level_desc_build: a row has %d blocks on one side of its diagonal (limit 32)", h_max);
+    return 0;
 }
 
 extern "C" int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const double* x, double* y,
@@ -1041,20 +1416,84 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     int64_t launches = 0;
 
     double* dots = B.z;                  // SSOR never stores z: its buffer carries the per-row shares of p'Ap
-    const char* pdl_env = getenv("MOF_LEVEL_PDL");
-    const bool use_pdl = levels && pdl_env && pdl_env[0] == '1';      // experimental, see level_back_pdl_kernel
-    bool pdl_failed = false;
+
+    // Persistent level kernels (default of the level path): cooperative launches sized to the device.
+    const char* persist_env = getenv("MOF_LEVEL_PERSIST");
+    bool persist = levels && mesh->level_desc && B.ready && G <= kPersistMaxGroups &&
+                   (double)N * (double)G < 2147483648.0 - 65536.0 && !(persist_env && persist_env[0] == '0');
+    g_last_path[3] = persist ? 0 : (!levels ? 0 : !mesh->level_desc ? 1 : !B.ready ? 2 : G > kPersistMaxGroups ? 3 : 4);
+    int grid_iter = 0, grid_sweep = 0;
+    const void* iter_fn = nullptr;
+    const size_t persist_smem = (size_t)kWarps * kStageBytes;
+    LevelArgs largs{mesh->level_desc, mesh->col, B, N, nb, ntiles, omega, inv_omega, nullptr};
+    unsigned long long* probe_buf = nullptr;
+    struct ProbeGuard {
+        unsigned long long*& p;
+        ~ProbeGuard() { if (p) cudaFree(p); }
+    } probe_guard{probe_buf};
+    int32_t stamp = 0;                   // last stamp written to B.ready by a sweep of this solve
+    if (persist) {
+        int dev = 0, coop = 0, sms = 0, occ_iter = 0, occ_f = 0, occ_b = 0;
+        MOF_CUDA_TRY(cudaGetDevice(&dev));
+        MOF_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        MOF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const char* minb_env = getenv("MOF_LEVEL_MINB");             // tuning knob: register budget variant
+        const char* probe_env = getenv("MOF_LEVEL_PROBE");           // development probe: per-item cycle breakdown on stderr
+        const bool probe = probe_env && probe_env[0] == '1';
+        const bool minb3 = !(minb_env && minb_env[0] == '4');      // default: 3 CTAs per SM, 80 registers, no spills
+        iter_fn = probe ? (minb3 ? (const void*)level_iter_kernel<3, true> : (const void*)level_iter_kernel<4, true>)
+                        : (minb3 ? (const void*)level_iter_kernel<3, false> : (const void*)level_iter_kernel<4, false>);
+        if (probe) {
+            const size_t pb = (16 + 2 * (size_t)N) * sizeof(unsigned long long);
+            MOF_CUDA_TRY(cudaMalloc(&probe_buf, pb));
+            MOF_CUDA_TRY(cudaMemsetAsync(probe_buf, 0, pb, st));
+            largs.probe = probe_buf;
+        }
+        MOF_CUDA_TRY(cudaFuncSetAttribute(iter_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        // static + dynamic shared memory exceeds 48 KB: opt in
+        MOF_CUDA_TRY(cudaFuncSetAttribute(iter_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
+        MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_iter, iter_fn, 256, persist_smem));
+        MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, level_sweep_kernel<0>, 256, persist_smem));
+        MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, level_sweep_kernel<1>, 256, persist_smem));
+        const int occ_s = occ_b < occ_f ? occ_b : occ_f;
+        if (!coop || occ_iter < 1 || occ_s < 1) {
+            persist = false;             // no co-residency guarantee: per-level launches
+            g_last_path[3] = !coop ? 5 : 6;
+        } else {
+            g_last_path[2] = occ_iter;
+            const char* cta_env = getenv("MOF_LEVEL_CTAS_PER_SM");   // tuning knob (1..occupancy)
+            int want = cta_env ? atoi(cta_env) : 0;
+            grid_iter = sms * ((want >= 1 && want < occ_iter) ? want : occ_iter);
+            grid_sweep = sms * ((want >= 1 && want < occ_s) ? want : occ_s);
+            MOF_CUDA_TRY(cudaMemsetAsync(B.ready, 0, (size_t)G * N * sizeof(int32_t), st));
+        }
+    }
+    g_last_path[0] = !ssor ? MOF_PATH_JACOBI : !levels ? MOF_PATH_MULTICOLOUR : persist ? MOF_PATH_LEVEL_PERSISTENT : MOF_PATH_LEVEL_LAUNCHES;
+    g_last_path[1] = grid_iter;
+    auto persist_sweep = [&](int dir, const double* vin, double* vout, cudaStream_t st) -> cudaError_t {
+        ++stamp;
+        void* args[] = {(void*)&largs, (void*)&vin, (void*)&vout, (void*)&stamp};
+        return cudaLaunchCooperativeKernel(dir ? (const void*)level_sweep_kernel<1> : (const void*)level_sweep_kernel<0>,
+                                           dim3(grid_sweep), dim3(256), args, persist_smem, st);
+    };
+    cudaError_t persist_err = cudaSuccess;
     auto sweep_back = [&](int mode, double* tout, cudaStream_t st) {
+        if (levels && persist && mode == 1) {
+            const cudaError_t e = persist_sweep(0, nullptr, tout, st);
+            if (e != cudaSuccess) persist_err = e;
+            ++launches;
+            return;
+        }
         if (levels) {
             for (int l = L - 1; l >= 0; --l) {
                 const int r0 = lp[l], r1 = lp[l + 1];
                 if (r1 <= r0) continue;
                 dim3 gs(mof_cdiv(r1 - r0, kWarps), G);
-                if (mode == 0 && use_pdl) {
-                    if (launch_pdl(level_back_pdl_kernel, gs, st, mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega) != cudaSuccess)
-                        pdl_failed = true;
-                }
-                else if (mode == 0) level_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega);
+                if (mode == 0) level_back_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega);
                 else           level_back_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, tout, N, nb, r0, r1, omega);
                 ++launches;
             }
@@ -1070,16 +1509,18 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         }
     };
     auto sweep_fwd = [&](int mode, const double* pin, double* wout, cudaStream_t st) {
+        if (levels && persist && mode == 1) {
+            const cudaError_t e = persist_sweep(1, pin, wout, st);
+            if (e != cudaSuccess) persist_err = e;
+            ++launches;
+            return;
+        }
         if (levels) {
             for (int l = 0; l < L; ++l) {
                 const int r0 = lp[l], r1 = lp[l + 1];
                 if (r1 <= r0) continue;
                 dim3 gs(mof_cdiv(r1 - r0, kWarps), G);
-                if (mode == 0 && use_pdl) {
-                    if (launch_pdl(level_fwd_pdl_kernel, gs, st, mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega) != cudaSuccess)
-                        pdl_failed = true;
-                }
-                else if (mode == 0) level_fwd_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
+                if (mode == 0) level_fwd_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
                 else           level_fwd_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
                 ++launches;
             }
@@ -1102,24 +1543,26 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     // group_done, tickets, groups_active, lanes_active <- 0
     MOF_CUDA_TRY(cudaMemsetAsync(B.state + (size_t)G * MOF_I_COUNT * MOF_W, 0, (2 * (size_t)G + 2) * sizeof(int32_t), st));
     if (!ssor) {
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_JACOBI, tol2, 0, 0, 0.0);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_JACOBI, tol2, 0, 0, 0.0, 0, nullptr);
         launches += 1;
     } else {
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_NORM, tol2, 0, 1, inv_omega);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_NORM, tol2, 0, 1, inv_omega, 0, nullptr);
         sweep_fwd(1, B.rhs, B.r, st);                               // r = (Dt+L)^-1 b
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_SSOR, tol2, 0, 1, inv_omega);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_START_SSOR, tol2, 0, 1, inv_omega, levels ? 1 : 0, nullptr);
         launches += 2;
     }
     MOF_LAUNCH_CHECK("pcg start kernels");
 
     // optional sampled per-kernel timing (one iteration per check interval) for the roofline report
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (prof)
-        for (int q = 0; q < 4; ++q) MOF_CUDA_TRY(cudaEventCreate(&ev[q]));
+        for (int q = 0; q < 6; ++q) MOF_CUDA_TRY(cudaEventCreate(&ev[q]));
     struct EventGuard {
         cudaEvent_t* e;
-        ~EventGuard() { for (int q = 0; q < 4; ++q) if (e[q]) cudaEventDestroy(e[q]); }
+        ~EventGuard() { for (int q = 0; q < 6; ++q) if (e[q]) cudaEventDestroy(e[q]); }
     } guard{ev};
+    if (prof && persist)                 // in-kernel phase clocks accumulate in scal[0][SPARE][0..3]
+        MOF_CUDA_TRY(cudaMemsetAsync(scal_host_ptr(B.scal, 0, MOF_S_SPARE), 0, 4 * sizeof(double), st));
 
     int32_t h_act[2] = {0, 0};          // groups, frames still iterating
     int32_t& h_active = h_act[0];
@@ -1141,7 +1584,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); if (s) cudaStreamDestroy(s); }
     } graph_guard{graph, graph_exec, cap};
     const char* graph_env = getenv("MOF_LEVEL_GRAPH");
-    const bool use_graph = levels && !(graph_env && graph_env[0] == '0');
+    const bool use_graph = levels && !persist && !(graph_env && graph_env[0] == '0');
     int64_t launches_per_graph = 0;
     if (use_graph && h_active > 0 && max_iter > 0) {
         MOF_CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -1159,6 +1602,16 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     for (;;) {
         while (h_active > 0 && it < max_iter) {
             const int n = (max_iter - it) < check_every ? (max_iter - it) : check_every;
+            if (persist) {               // one cooperative launch = n whole iterations
+                int timing = prof ? 1 : 0;
+                int n_arg = n;
+                void* args[] = {(void*)&largs, (void*)&n_arg, (void*)&stamp, (void*)&timing};
+                if (prof) cudaEventRecord(ev[4], st);
+                MOF_CUDA_TRY(cudaLaunchCooperativeKernel(iter_fn, dim3(grid_iter), dim3(256), args, persist_smem, st));
+                if (prof) cudaEventRecord(ev[5], st);
+                stamp += 2 * n;
+                launches += 1;
+            } else
             for (int q = 0; q < n; ++q) {
                 const bool sample = prof && q == 0;
                 if (sample) cudaEventRecord(ev[0], st);
@@ -1184,12 +1637,17 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                 if (sample) cudaEventRecord(ev[3], st);
             }
             MOF_LAUNCH_CHECK("pcg iteration kernels");
-            if (pdl_failed) return mof_set_error(-100, "mof_pcg_solve_batch: a programmatic dependent launch failed (MOF_LEVEL_PDL=1)");
             it += n;
             const int32_t groups_before = h_act[0], lanes_before = h_act[1];
             MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             MOF_CUDA_TRY(cudaStreamSynchronize(st));
-            if (prof) {
+            if (prof && persist) {
+                float ms = 0;
+                MOF_CUDA_TRY(cudaEventElapsedTime(&ms, ev[4], ev[5]));
+                prof->ms_iter += ms;
+                prof->iter_launches += 1;
+                prof->iterations_total += n;
+            } else if (prof) {
                 float ms[3] = {0, 0, 0};
                 for (int q = 0; q < 3; ++q) MOF_CUDA_TRY(cudaEventElapsedTime(&ms[q], ev[q], ev[q + 1]));
                 // block Jacobi: [pupdate, spmv, update]; SSOR: [backward sweeps, forward sweeps, update]
@@ -1204,15 +1662,25 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         }
         // confirm on the true residual b - A x; frames that miss tol resume with a tighter threshold
         if (ssor) sweep_back(1, B.t, st);                            // xs = (Dt+U)^-1 (xhat + pending alpha p)
-        spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, xphys, B.ap, N, nb, ntiles, nullptr,
+        // A x goes to z on the SSOR paths (free there; the level path's w must keep its validity bits for a resume)
+        double* ax = ssor ? B.z : B.ap;
+        spmv_kernel<false><<<grid, 256, 0, st>>>(mesh->rowptr, mesh->col, B.vals, xphys, ax, N, nb, ntiles, nullptr,
                                                 nullptr, nullptr, G);
         const int last_round = (rounds >= max_restarts || it >= max_iter) ? 1 : 0;
-        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_VERIFY, tol2, last_round, ssor ? 1 : 0, inv_omega);
+        init_kernel<<<grid, 256, 0, st>>>(B, N, ntiles, MODE_VERIFY, tol2, last_round, ssor ? 1 : 0, inv_omega, 0, ax);
         launches += 2;
         MOF_LAUNCH_CHECK("verification kernels");
+        if (persist_err != cudaSuccess)
+            return mof_set_error(-100 - (int)persist_err, "mof_pcg_solve_batch: cooperative launch of a level sweep failed: %s",
+                                 cudaGetErrorString(persist_err));
         MOF_CUDA_TRY(cudaMemcpyAsync(h_act, d_active_groups, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         MOF_CUDA_TRY(cudaStreamSynchronize(st));
         if (h_active <= 0 || last_round) break;
+        if (levels) {
+            restamp_kernel<<<grid, 256, 0, st>>>(B, N);
+            MOF_LAUNCH_CHECK("restamp_kernel");
+            launches += 1;
+        }
         ++rounds;
     }
     if (ssor) {  // hand the solution of the original system back in batch->x (mof_unpack_solution reads it)
@@ -1220,7 +1688,30 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         MOF_LAUNCH_CHECK("unscale_kernel");
         launches += 1;
     }
+    if (probe_buf) {
+        std::vector<unsigned long long> h(16 + 2 * (size_t)N);
+        MOF_CUDA_TRY(cudaMemcpyAsync(h.data(), probe_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        MOF_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int d = 0; d < 2; ++d) {
+            const double n = (double)(h[d * 8 + 4] ? h[d * 8 + 4] : 1);
+            fprintf(stderr, "[mof probe] %s sweep: items %llu; cycles per item: poll + gather %.0f, stage wait %.0f, "
+                            "arithmetic + result stores %.0f, tail + head %.0f\n",
+                    d ? "forward" : "backward", h[d * 8 + 4], h[d * 8 + 0] / n, h[d * 8 + 1] / n, h[d * 8 + 2] / n, h[d * 8 + 3] / n);
+        }
+        if (const char* path = getenv("MOF_LEVEL_PROBE_FILE")) {       // per-row finish times of the last iteration (group act[0])
+            if (FILE* f = fopen(path, "wb")) {
+                fwrite(h.data() + 16, sizeof(unsigned long long), 2 * (size_t)N, f);
+                fclose(f);
+            }
+        }
+    }
     if (prof) prof->launches_total += launches;
+    if (prof && persist) {
+        double ns[4] = {0, 0, 0, 0};
+        MOF_CUDA_TRY(cudaMemcpyAsync(ns, scal_host_ptr(B.scal, 0, MOF_S_SPARE), sizeof(ns), cudaMemcpyDeviceToHost, st));
+        MOF_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int k = 0; k < 4; ++k) prof->phase_ns[k] += ns[k];
+    }
 
     // per-frame report
     const size_t nf = (size_t)G * MOF_W;

@@ -140,6 +140,7 @@ class MeshOperator:
         def up(a):
             return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
+        self.d_level_desc = None
         with torch.cuda.device(dev):
             self.d_perm, self.d_rowptr, self.d_col, self.d_diag = up(P.perm), up(P.rowptr), up(P.col), up(P.diag)
             self.d_cptr, self.d_centry, self.d_tri = up(P.cptr), up(P.centry), up(P.tri)
@@ -155,6 +156,10 @@ class MeshOperator:
             _lib.check(lib.mof_geom_gradw(P.n_faces, d_coords.data_ptr(), self.d_tri.data_ptr(), self.d_areas.data_ptr(),
                                           self.d_grad_w.data_ptr(), self.d_integral.data_ptr(), st))
             _lib.check(lib.mof_geom_a2(ctypes.byref(self.struct()), self.d_a2v.data_ptr(), st))
+            if P.n_levels:           # row descriptors of the persistent level-scheduled SSOR kernel
+                desc = torch.empty((2, N, 8), dtype=torch.int32, device=dev)
+                if _lib.check(lib.mof_level_desc_build(ctypes.byref(self.struct()), desc.data_ptr(), st), allow_positive=True) == 0:
+                    self.d_level_desc = desc
             # host copies in the reference's vertex order (what the reference returns, :97)
             e_int = self.d_e.cpu().numpy()
             self.e = np.empty_like(e_int)
@@ -175,7 +180,8 @@ class MeshOperator:
             self.d_e.data_ptr(), self.d_grad_w.data_ptr(), self.d_integral.data_ptr(), self.d_areas.data_ptr(),
             self.d_a2v.data_ptr(), P.n_colors,
             (ctypes.c_int32 * (_lib.MAX_COLORS + 1))(*([int(x) for x in P.color_tile_ptr] + [0] * (_lib.MAX_COLORS - P.n_colors))),
-            P.n_levels, 0, P.level_ptr.ctypes.data if P.n_levels else None)
+            P.n_levels, 0, P.level_ptr.ctypes.data if P.n_levels else None,
+            self.d_level_desc.data_ptr() if self.d_level_desc is not None else None)
 
     # -- reference-compatible views ----------------------------------------------------
     def tocsr(self):

@@ -35,6 +35,7 @@ class SolveInfo:
     relres: np.ndarray          # (n_frames,) true ||b - A x|| / ||b||
     status: np.ndarray          # (n_frames,) _lib.STATUS_*
     seconds: float = 0.0
+    path: tuple = ()            # mof_pcg_last_path of the last batch: (path, grid, CTAs per SM, fallback reason)
 
     @property
     def converged(self):
@@ -74,6 +75,8 @@ class FrameBatch:
         self.partial = torch.zeros((G, self.n_tiles, 2, W), **f64)
         self.scal = torch.zeros((G, _lib.SCAL_SLOTS, W), **f64)
         self.state = torch.zeros((int(lib.mof_state_ints(G)),), dtype=torch.int32, device=dev)
+        # per-(group, row) sweep stamps of the persistent level-scheduled kernel
+        self.ready = torch.zeros((G, N), dtype=torch.int32, device=dev) if (with_t and op.pattern.n_levels > 0) else None
         self.n_frames = 0
 
     def struct(self, n_frames=None, n_groups=None):
@@ -87,11 +90,12 @@ class FrameBatch:
             G, self.n_frames, self.It.data_ptr(), self.dIt.data_ptr(), self.vals.data_ptr(),
             self.rhs.data_ptr(), self.minv.data_ptr(), self.x.data_ptr(), self.r.data_ptr(), self.z.data_ptr(),
             self.p.data_ptr(), self.ap.data_ptr(), self.t.data_ptr() if self.t is not None else None,
-            self.partial.data_ptr(), self.scal.data_ptr(), self.state.data_ptr())
+            self.partial.data_ptr(), self.scal.data_ptr(), self.state.data_ptr(),
+            self.ready.data_ptr() if self.ready is not None else None)
 
     @staticmethod
     def bytes_per_group(n_vertices, n_blocks):
-        return 8 * GROUP * (4 * n_blocks + n_vertices * (2 + 2 * 7 + 3))
+        return 8 * GROUP * (4 * n_blocks + n_vertices * (2 + 2 * 7 + 3)) + 4 * n_vertices
 
 
 class VelocitySolver:
@@ -193,8 +197,7 @@ class VelocitySolver:
             raise errors[0]
         if self.profile is not None:
             for p in profiles:
-                for name, _ in _lib.PcgProfile._fields_:
-                    setattr(self.profile, name, getattr(self.profile, name) + getattr(p, name))
+                _lib.add_profile(self.profile, p)
         return infos
 
     def drain(self, width, rows=None):
@@ -235,10 +238,12 @@ class VelocitySolver:
                                            relres.ctypes.data, status.ctypes.data,
                                            ctypes.byref(profile) if profile is not None else None, st),
                    allow_positive=True)
+        path = (ctypes.c_int32 * 4)()
+        lib.mof_pcg_last_path(path)
         self.aux_launches += 3 + (1 if self.ssor else 0)
         assert V_out.stride(1) == 1
         _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
-        return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames])
+        return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames], path=tuple(path))
 
     def solve_frames(self, I_dev, I2_dev, dt_dev, lambda_, V_dev=None, on_batch=None):
         """All frames k = 0 .. n-1 with (I_dev[k], I2_dev[k+1]) (compute_optical_flow.py:174-175).
@@ -265,7 +270,7 @@ class VelocitySolver:
             infos = self._solve_concurrent(ranges, lanes, step // GROUP, I_dev, I2_dev, dt_dev, lambda_, V_dev, on_batch)
         if infos:
             info = SolveInfo(np.concatenate([i.iterations for i in infos]), np.concatenate([i.relres for i in infos]),
-                             np.concatenate([i.status for i in infos]))
+                             np.concatenate([i.status for i in infos]), path=infos[-1].path)
         else:
             info = SolveInfo(np.zeros(0, np.int32), np.zeros(0), np.zeros(0, np.int32))
         return V_dev, info

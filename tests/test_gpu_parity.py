@@ -594,3 +594,36 @@ def test_full_size_level_scheduled_path():
     (Va, ita), (Vb, itb) = out["ssor"], out["ssor_level"]
     assert max(rel_l2(Vb[k], Va[k]) for k in range(T - 1)) <= 1e-9
     assert itb < 0.6 * ita, (ita, itb)
+
+
+@pytest.mark.parametrize("level,frames", [(3, 5), (5, 70), (6, 33)])
+def test_persistent_level_kernel_bit_identical_to_per_level_launches(level, frames):
+    """The persistent cooperative kernel (row-level dataflow, bulk-async prefetch) and the one-launch-per-level
+    path run the same per-row arithmetic and the same reduction order: fields, iteration counts and residuals
+    must be identical bit for bit (cof:147 replacement, default path vs its fallback)."""
+    import os
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    coords, tris, normals, areas = synthetic.pial_like(level)
+    T = frames + 1
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=3)
+    old = cof.settings["precond"]
+    cof.settings["precond"] = "ssor_level"
+    out = {}
+    try:
+        a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+        assert a2.d_level_desc is not None
+        for persist in ("1", "0"):
+            os.environ["MOF_LEVEL_PERSIST"] = persist
+            V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+            info = cof.last_solve_info
+            assert info.converged and info.relres.max() <= RES_TOL
+            out[persist] = (np.array(V_k), info.iterations.copy(), info.relres.copy())
+            want = _lib.PATH_LEVEL_PERSISTENT if persist == "1" else _lib.PATH_LEVEL_LAUNCHES
+            assert info.path[0] == want, info.path          # no silent fallback
+    finally:
+        os.environ.pop("MOF_LEVEL_PERSIST", None)
+        cof.settings["precond"] = old
+    assert np.array_equal(out["1"][1], out["0"][1])
+    assert np.array_equal(out["1"][0], out["0"][0])
+    assert np.array_equal(out["1"][2], out["0"][2])

@@ -33,9 +33,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8 + 4 + 17 * 4 + 4 + 4 + 8
-    assert ctypes.sizeof(_lib.BatchDev) == 8 + 14 * 8
-    assert ctypes.sizeof(_lib.PcgProfile) == 8 * 8
+    assert ctypes.sizeof(_lib.MeshDev) == 4 * 8 + 12 * 8 + 4 + 17 * 4 + 4 + 4 + 8 + 8
+    assert ctypes.sizeof(_lib.BatchDev) == 8 + 15 * 8
+    assert ctypes.sizeof(_lib.PcgProfile) == 8 * 8 + 8 + 8 + 4 * 8
 
 
 @pytest.mark.parametrize("reorder", [False, True])
