@@ -69,10 +69,19 @@ template <int NV>
 __device__ __forceinline__ void reduce_all_tiles(const double* __restrict__ partial_g, int ntiles, double (&tot)[NV],
                                                  double (*red)[NV][MOF_W]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kBatch = 8;                          // loads in flight per warp; the additions keep their order
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double acc = 0.0;
-        for (int t = warp; t < ntiles; t += kWarps) acc += __ldcg(partial_g + ((size_t)t * 2 + k) * MOF_W + lane);
+        int t = warp;
+        for (; t + (kBatch - 1) * kWarps < ntiles; t += kBatch * kWarps) {
+            double v[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) v[u] = __ldcg(partial_g + ((size_t)(t + u * kWarps) * 2 + k) * MOF_W + lane);
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) acc += v[u];
+        }
+        for (; t < ntiles; t += kWarps) acc += __ldcg(partial_g + ((size_t)t * 2 + k) * MOF_W + lane);
         red[warp][k][lane] = acc;
     }
     __syncthreads();
@@ -85,6 +94,27 @@ __device__ __forceinline__ void reduce_all_tiles(const double* __restrict__ part
             tot[k] = s;
         }
     }
+}
+
+// First half of tile_reduce for the persistent kernel: the CTA's partial of tile `tile` goes to `partial_g`;
+// the cross-tile sum happens after a grid barrier (group_reduce), so no fence and no ticket per tile.
+template <int NV>
+__device__ __forceinline__ void tile_partial(const double (&val)[NV], double* __restrict__ partial_g, int tile,
+                                             double (*red)[NV][MOF_W]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[warp][k][lane] = val[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = red[0][k][lane];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s += red[w][k][lane];
+            partial_g[((size_t)tile * 2 + k) * MOF_W + lane] = s;
+        }
+    }
+    __syncthreads();
 }
 
 // Deterministic CTA + cross-tile reduction of NV per-lane values.  Returns true (for every
@@ -217,9 +247,63 @@ __global__ void __launch_bounds__(256) spmv_kernel(const int32_t* __restrict__ r
 // leaves x, r, z, p and r'z untouched, so that it can resume exactly where it stopped if the
 // true-residual check (init_kernel, MODE_VERIFY) asks for more iterations.
 // ---------------------------------------------------------------------------------
+// beta and the convergence test of group g from (r'z, r'r); called by warp 0 of one CTA per group.
+__device__ __forceinline__ void update_scalar_step(const mof_batch_dev& B, int64_t g, const double (&tot)[2]) {
+    const int G = B.n_groups;
+    const int lane = threadIdx.x & 31;
+    int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
+    double beta = 1.0, zs = 0.0;                    // frozen: p stays as it is
+    int act = active[lane];
+    const int was = act;
+    if (act) {
+        const double rz_old = scal_ptr(B.scal, g, MOF_S_RZ)[lane];
+        const double bb = scal_ptr(B.scal, g, MOF_S_BB)[lane];
+        const double thr = scal_ptr(B.scal, g, MOF_S_THR)[lane];
+        state_ptr(B.state, g, MOF_I_ITERS)[lane] += 1;
+        scal_ptr(B.scal, g, MOF_S_RZ)[lane] = tot[0];
+        scal_ptr(B.scal, g, MOF_S_RR)[lane] = tot[1];
+        if (!isfinite(tot[0]) || !isfinite(tot[1])) {
+            state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
+            act = 0;
+        } else if (tot[1] <= thr * bb) {
+            state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_CONVERGED;
+            scal_ptr(B.scal, g, MOF_S_BETA_SAVED)[lane] = tot[0] / rz_old;   // used if the frame resumes
+            act = 0;
+        } else {
+            beta = tot[0] / rz_old;
+            zs = 1.0;
+        }
+        active[lane] = act;
+    }
+    scal_ptr(B.scal, g, MOF_S_BETA)[lane] = beta;
+    scal_ptr(B.scal, g, MOF_S_ZS)[lane] = zs;
+    const int any = __any_sync(kFull, act);
+    const int dropped = __popc(__ballot_sync(kFull, was && !act));
+    if (lane == 0) {
+        if (dropped) atomicSub(lanes_active_ptr(B.state, G), dropped);
+        if (!any) {
+            group_done_ptr(B.state, G)[g] = 1;
+            atomicSub(groups_active_ptr(B.state, G), 1);
+        }
+    }
+}
+
+// Tile-level end of the vector update: deterministic reduction of (r'z, r'r), then beta and the convergence
+// test in the last CTA of the group.
+template <bool SSOR>
+__device__ __forceinline__ void update_finish(const mof_batch_dev& B, int ntiles, double inv_omega, int tile, int64_t g,
+                                              double rz, double rr) {
+    const int G = B.n_groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (SSOR) rz = rr * inv_omega;                     // r'z with z = r / omega (linear, so per-lane partials add up)
+    double val[2] = {rz, rr}, tot[2];
+    if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
+        return;
+    if (warp == 0) update_scalar_step(B, g, tot);
+}
+
 template <bool SSOR>
 __device__ __forceinline__ void update_body(const mof_batch_dev& B, int64_t N, int ntiles, double inv_omega, int tile, int64_t g) {
-    const int G = B.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
     const double alpha = scal_ptr(B.scal, g, MOF_S_ALPHA)[lane];
@@ -249,47 +333,7 @@ __device__ __forceinline__ void update_body(const mof_batch_dev& B, int64_t N, i
         }
         rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
     }
-    if (SSOR) rz = rr * inv_omega;                     // r'z with z = r / omega (linear, so per-lane partials add up)
-    double val[2] = {rz, rr}, tot[2];
-    if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
-        return;
-    if (warp == 0) {
-        int32_t* active = state_ptr(B.state, g, MOF_I_ACTIVE);
-        double beta = 1.0, zs = 0.0;                // frozen: p stays as it is
-        int act = active[lane];
-        const int was = act;
-        if (act) {
-            const double rz_old = scal_ptr(B.scal, g, MOF_S_RZ)[lane];
-            const double bb = scal_ptr(B.scal, g, MOF_S_BB)[lane];
-            const double thr = scal_ptr(B.scal, g, MOF_S_THR)[lane];
-            state_ptr(B.state, g, MOF_I_ITERS)[lane] += 1;
-            scal_ptr(B.scal, g, MOF_S_RZ)[lane] = tot[0];
-            scal_ptr(B.scal, g, MOF_S_RR)[lane] = tot[1];
-            if (!isfinite(tot[0]) || !isfinite(tot[1])) {
-                state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_BREAKDOWN;
-                act = 0;
-            } else if (tot[1] <= thr * bb) {
-                state_ptr(B.state, g, MOF_I_STATUS)[lane] = MOF_STATUS_CONVERGED;
-                scal_ptr(B.scal, g, MOF_S_BETA_SAVED)[lane] = tot[0] / rz_old;   // used if the frame resumes
-                act = 0;
-            } else {
-                beta = tot[0] / rz_old;
-                zs = 1.0;
-            }
-            active[lane] = act;
-        }
-        scal_ptr(B.scal, g, MOF_S_BETA)[lane] = beta;
-        scal_ptr(B.scal, g, MOF_S_ZS)[lane] = zs;
-        const int any = __any_sync(kFull, act);
-        const int dropped = __popc(__ballot_sync(kFull, was && !act));
-        if (lane == 0) {
-            if (dropped) atomicSub(lanes_active_ptr(B.state, G), dropped);
-            if (!any) {
-                group_done_ptr(B.state, G)[g] = 1;
-                atomicSub(groups_active_ptr(B.state, G), 1);
-            }
-        }
-    }
+    update_finish<SSOR>(B, ntiles, inv_omega, tile, g, rz, rr);
 }
 
 template <bool SSOR>
@@ -703,9 +747,16 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const int32_t* __restric
 }
 
 // p'Ap = sum of the per-row shares (tile by tile, rows in order: deterministic), then alpha.
+__device__ __forceinline__ void level_dot_finish(const mof_batch_dev& B, int ntiles, int tile, int64_t g, double acc) {
+    const int G = B.n_groups;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double val[1] = {acc}, tot[1];
+    if (!tile_reduce<1>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot)) return;
+    if (warp == 0) finalize_alpha(tot[0], B.scal, B.state, g, G, lane);
+}
+
 __device__ __forceinline__ void level_dot_body(const mof_batch_dev& B, const double* __restrict__ dots, int64_t N, int ntiles,
                                                int tile, int64_t g) {
-    const int G = B.n_groups;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
     double acc = 0.0;
@@ -714,9 +765,7 @@ __device__ __forceinline__ void level_dot_body(const mof_batch_dev& B, const dou
         const int64_t v = row0 + q;
         if (v < N) acc += __ldcs(dots + ((size_t)g * N + v) * MOF_W + lane);
     }
-    double val[1] = {acc}, tot[1];
-    if (!tile_reduce<1>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot)) return;
-    if (warp == 0) finalize_alpha(tot[0], B.scal, B.state, g, G, lane);
+    level_dot_finish(B, ntiles, tile, g, acc);
 }
 
 __global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const double* __restrict__ dots, int64_t N, int ntiles) {
@@ -749,7 +798,11 @@ __global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const d
 constexpr int kStageBlocks = 4;                                       // matrix blocks of a row staged in shared memory
 constexpr int kStageValBytes = kStageBlocks * 4 * MOF_W * 8;          // 4096
 constexpr int kStageVecBytes = 2 * MOF_W * 8;                         // one row of one vector: 512
-constexpr int kStageBytes = kStageValBytes + 3 * kStageVecBytes;      // 5632 per warp
+constexpr int kStageBytes = 6144;                                     // per warp: sweeps use 4096 + 3 x 512, the vector
+                                                                      // phases 3 x 2048 (three vectors x four rows / three
+                                                                      // slots of eight rows of p'Ap shares)
+constexpr int kSlotBytes = 2048;
+static_assert(kStageValBytes + 3 * kStageVecBytes <= kStageBytes, "stage too small");
 constexpr int kPersistMaxGroups = 1024;                               // active-group list kept in shared memory (uint16)
 constexpr int kDescInts = 8;                                          // per row and direction: bs, cnt, col[0..5]
 constexpr int kDescCols = kDescInts - 2;
@@ -761,9 +814,13 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Every wait inside the persistent kernels is bounded: a protocol error must end in a trap (a CUDA error the
+// host reports), never in a hung GPU.  The bounds are seconds of spinning, far beyond any legitimate wait.
+constexpr uint32_t kSpinLimit = 1u << 26;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
+    uint32_t ok, spins = 0;
     do {
+        if (++spins > kSpinLimit) __trap();
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
@@ -909,7 +966,9 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             if (lane < cnt) {
                 if (lane >= kDescCols) mycol = __ldg(a.col + bs + lane);
                 const int32_t* f = B.ready + (size_t)g * N + mycol;
-                while (ld_acquire(f) < stamp) {}
+                uint32_t spins = 0;
+                while (ld_acquire(f) < stamp)
+                    if (++spins > kSpinLimit) __trap();
             }
             __syncwarp();
         }
@@ -918,7 +977,8 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             uint32_t co[kStageBlocks];
 #pragma unroll
             for (int k = 0; k < kStageBlocks; ++k) co[k] = (uint32_t)__shfl_sync(kFull, cd, 2 + k) * (2 * MOF_W);
-            for (;;) {
+            for (uint32_t spins = 0;; ++spins) {
+                if (spins > kSpinLimit) __trap();
 #pragma unroll
                 for (int k = 0; k < kStageBlocks; ++k)
                     if (k < cnt) {
@@ -934,7 +994,7 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             }
         }
         if (PROBE) tk1 = clock64();
-        mbar_wait(bar, parity);
+        mbar_wait(bar, parity & 1u);
         parity ^= 1u;
         if (PROBE) tk2 = clock64();
         v_l += (size_t)row * 2 * MOF_W;                                   // -> this row's entry of the output
@@ -977,7 +1037,8 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
                 const int64_t j = k < kDescCols ? dk : __ldg(a.col + bs + k);
                 const double* ap = vals_l + (size_t)(bs + k) * 4 * MOF_W;
                 double v0, v1;
-                for (;;) {
+                for (uint32_t spins = 0;; ++spins) {
+                    if (spins > kSpinLimit) __trap();
                     v0 = ld_strong(g_l + (size_t)(2 * j) * MOF_W);
                     v1 = ld_strong(g_l + (size_t)(2 * j + 1) * MOF_W);
                     if (MODE == 1 || __all_sync(kFull, has_parity(v0, par) && has_parity(v1, par))) break;
@@ -1042,16 +1103,160 @@ __device__ __forceinline__ int build_active_list(const int32_t* group_done, int 
 }
 
 struct PersistShared {
-    uint64_t bar[kWarps];
+    uint64_t bar[kWarps][3];               // [0]: sweeps and the r update, [0..2]: slots of the p'Ap phase
     uint16_t act[kPersistMaxGroups];
     int count;
     unsigned long long tprev, tacc[4];     // phase clock of CTA 0 (profile)
+    double red[kWarps][2][MOF_W];          // cross-warp scratch of the reductions
 };
 
 __device__ __forceinline__ void persist_setup(PersistShared& S) {
-    if (threadIdx.x < kWarps) mbar_init(smem_u32(&S.bar[threadIdx.x]), 1);
+    if (threadIdx.x < kWarps * 3) mbar_init(smem_u32(&S.bar[threadIdx.x / 3][threadIdx.x % 3]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+}
+
+// p'Ap = sum of the per-row shares the forward sweep left in `dots` -> alpha.  level_dot_kernel's arithmetic (a
+// warp adds its eight rows in order, tile_reduce does the rest); a warp's rows are one contiguous 2 KB piece,
+// fetched by one bulk copy per item, two items ahead (three slots).
+__device__ __forceinline__ void level_dot_phase(const LevelArgs& a, const double* dots, const uint16_t* act, int A,
+                                                unsigned char* stage, uint32_t bar0, uint32_t& parity3, uint64_t policy,
+                                                double (*red)[1][MOF_W]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t N = a.N;
+    const int64_t items = (int64_t)a.ntiles * A;
+    const uint32_t stage_s = smem_u32(stage);
+    auto rows_of = [&](int64_t q) {
+        const int64_t row0 = (q / A) * MOF_TILE_ROWS + warp * kRowsPerWarp;
+        const int64_t n = N - row0;
+        return (int)(n < 0 ? 0 : (n > kRowsPerWarp ? kRowsPerWarp : n));
+    };
+    auto issue = [&](int64_t q, int slot) {
+        const int n = rows_of(q);
+        if (lane == 0 && n > 0) {
+            const int64_t row0 = (q / A) * MOF_TILE_ROWS + warp * kRowsPerWarp;
+            const uint32_t b = bar0 + 8u * slot;
+            mbar_expect_tx(b, (uint32_t)(n * MOF_W * 8));
+            bulk_g2s(stage_s + slot * kSlotBytes, dots + ((size_t)act[q % A] * N + row0) * MOF_W, (uint32_t)(n * MOF_W * 8), b, policy);
+        }
+    };
+    int64_t q = blockIdx.x;
+    if (q < items) issue(q, 0);
+    if (q + gridDim.x < items) issue(q + gridDim.x, 1);
+    int slot = 0;
+    for (; q < items; q += gridDim.x) {
+        const int64_t q2 = q + 2 * (int64_t)gridDim.x;
+        if (q2 < items) issue(q2, slot == 0 ? 2 : slot - 1);
+        const int n = rows_of(q);
+        double acc = 0.0;
+        if (n > 0) {
+            mbar_wait(bar0 + 8u * slot, (parity3 >> slot) & 1u);
+            parity3 ^= 1u << slot;
+            const double* sd = reinterpret_cast<const double*>(stage + slot * kSlotBytes) + lane;
+#pragma unroll
+            for (int j = 0; j < kRowsPerWarp; ++j)
+                if (j < n) acc += sd[j * MOF_W];
+        }
+        {
+            double val[1] = {acc};
+            tile_partial<1>(val, a.B.partial + (size_t)act[q % A] * a.ntiles * 2 * MOF_W, (int)(q / A), red);
+        }
+        slot = slot == 2 ? 0 : slot + 1;
+    }
+}
+
+// r -= alpha (t + w) ; r'r -> beta and the convergence test.  update_body<true>'s arithmetic; the three vectors
+// of a warp's rows come in by bulk copies, four rows (3 x 2 KB) at a time, the next piece requested as soon as
+// the stage has been read.
+__device__ __forceinline__ void level_update_phase(const LevelArgs& a, const uint16_t* act, int A, unsigned char* stage,
+                                                   uint32_t bar, uint32_t& parity, uint64_t policy, double (*red)[2][MOF_W]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const mof_batch_dev& B = a.B;
+    const int64_t N = a.N;
+    const int64_t items = (int64_t)a.ntiles * A;
+    const uint32_t stage_s = smem_u32(stage);
+    constexpr int kPiece = 4;                                             // rows per bulk step
+    auto rows_of = [&](int64_t q, int h) {
+        const int64_t row0 = (q / A) * MOF_TILE_ROWS + warp * kRowsPerWarp + h * kPiece;
+        const int64_t n = N - row0;
+        return (int)(n < 0 ? 0 : (n > kPiece ? kPiece : n));
+    };
+    auto issue = [&](int64_t q, int h) {
+        const int n = rows_of(q, h);
+        if (lane == 0 && n > 0) {
+            const int64_t row0 = (q / A) * MOF_TILE_ROWS + warp * kRowsPerWarp + h * kPiece;
+            const size_t off = ((size_t)act[q % A] * N + row0) * 2 * MOF_W;
+            const uint32_t bytes = (uint32_t)(n * 2 * MOF_W * 8);
+            mbar_expect_tx(bar, 3 * bytes);
+            bulk_g2s(stage_s, B.ap + off, bytes, bar, policy);
+            bulk_g2s(stage_s + kSlotBytes, B.t + off, bytes, bar, policy);
+            bulk_g2s(stage_s + 2 * kSlotBytes, B.r + off, bytes, bar, policy);
+        }
+    };
+    const double* sw = reinterpret_cast<const double*>(stage) + lane;
+    const double* st = reinterpret_cast<const double*>(stage + kSlotBytes) + lane;
+    const double* sr = reinterpret_cast<const double*>(stage + 2 * kSlotBytes) + lane;
+    int64_t q = blockIdx.x;
+    if (q < items) issue(q, 0);
+    for (; q < items; q += gridDim.x) {
+        const int tile = (int)(q / A);
+        const int64_t g = act[q % A];
+        const double alpha = __ldcg(scal_ptr(B.scal, g, MOF_S_ALPHA) + lane);
+        double rr = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n = rows_of(q, h);
+            double rn[kPiece][2];
+            if (n > 0) {
+                mbar_wait(bar, parity & 1u);
+                parity ^= 1u;
+#pragma unroll
+                for (int j = 0; j < kPiece; ++j)
+                    if (j < n) {
+                        const double a0 = sw[(2 * j) * MOF_W] + st[(2 * j) * MOF_W], a1 = sw[(2 * j + 1) * MOF_W] + st[(2 * j + 1) * MOF_W];
+                        rn[j][0] = fma(-alpha, a0, sr[(2 * j) * MOF_W]);
+                        rn[j][1] = fma(-alpha, a1, sr[(2 * j + 1) * MOF_W]);
+                    }
+            }
+            __syncwarp();                                                 // the stage has been read
+            if (h == 0) issue(q, 1);
+            else if (q + gridDim.x < items) issue(q + gridDim.x, 0);
+            if (n > 0) {
+                double* r_l = B.r + ((size_t)g * N + (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp + h * kPiece) * 2 * MOF_W + lane;
+#pragma unroll
+                for (int j = 0; j < kPiece; ++j)
+                    if (j < n) {
+                        r_l[(2 * j) * MOF_W] = rn[j][0];
+                        r_l[(2 * j + 1) * MOF_W] = rn[j][1];
+                        rr = fma(rn[j][0], rn[j][0], rr);
+                        rr = fma(rn[j][1], rn[j][1], rr);
+                    }
+            }
+        }
+        {
+            double val[2] = {rr * a.inv_omega, rr};                      // r'z with z = r / omega, r'r
+            tile_partial<2>(val, B.partial + (size_t)g * a.ntiles * 2 * MOF_W, tile, red);
+        }
+    }
+}
+
+// Second half of the two reductions, after a grid barrier: one CTA per group adds the tile partials in
+// tile_reduce's order and takes the scalar step (STEP 0: alpha from p'Ap, STEP 1: beta and convergence).
+template <int STEP>
+__device__ __forceinline__ void level_group_phase(const LevelArgs& a, const uint16_t* act, int A,
+                                                  double (*red)[STEP + 1][MOF_W]) {
+    const mof_batch_dev& B = a.B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = blockIdx.x; q < A; q += gridDim.x) {
+        const int64_t g = act[q];
+        double tot[STEP + 1];
+        reduce_all_tiles<STEP + 1>(B.partial + (size_t)g * a.ntiles * 2 * MOF_W, a.ntiles, tot, red);
+        if (warp == 0) {
+            if constexpr (STEP == 0) finalize_alpha(tot[0], B.scal, B.state, g, B.n_groups, lane);
+            else update_scalar_step(B, g, tot);
+        }
+        __syncthreads();
+    }
 }
 
 // grid barrier + make what other SMs wrote with ordinary stores visible to this thread's bulk copies
@@ -1073,8 +1278,8 @@ __global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int 
     const int G = B.n_groups;
     persist_setup(S);
     unsigned char* stage = dyn_smem + (size_t)warp * kStageBytes;
-    const uint32_t bar = smem_u32(&S.bar[warp]);
-    uint32_t parity = 0;
+    const uint32_t bar = smem_u32(&S.bar[warp][0]);
+    uint32_t parity = 0;                   // bit s: phase parity of this warp's mbarrier s (bit 0 is shared by all phases)
     const uint64_t policy = policy_evict_first();
     double* dots = B.z;
     const bool clock = timing && blockIdx.x == 0 && threadIdx.x == 0;
@@ -1094,17 +1299,14 @@ __global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int 
         level_sweep_phase<1, 0, PROBE>(a, B.p, B.ap, dots, S.act, A, stamp0 + 2 * it + 2, stage, bar, parity, policy);
         phase_barrier(grid);
         lap(1);
-        const int64_t items = (int64_t)a.ntiles * A;
-        for (int64_t q = blockIdx.x; q < items; q += gridDim.x) {
-            level_dot_body(B, dots, a.N, a.ntiles, (int)(q / A), S.act[q % A]);
-            __syncthreads();
-        }
+        level_dot_phase(a, dots, S.act, A, stage, bar, parity, policy, reinterpret_cast<double(*)[1][MOF_W]>(S.red));
+        phase_barrier(grid);
+        level_group_phase<0>(a, S.act, A, reinterpret_cast<double(*)[1][MOF_W]>(S.red));
         phase_barrier(grid);
         lap(2);
-        for (int64_t q = blockIdx.x; q < items; q += gridDim.x) {
-            update_body<true>(B, a.N, a.ntiles, a.inv_omega, (int)(q / A), S.act[q % A]);
-            __syncthreads();
-        }
+        level_update_phase(a, S.act, A, stage, bar, parity, policy, S.red);
+        phase_barrier(grid);
+        level_group_phase<1>(a, S.act, A, S.red);
         phase_barrier(grid);
         lap(3);
     }
@@ -1123,7 +1325,7 @@ __global__ void __launch_bounds__(256, 4) level_sweep_kernel(LevelArgs a, const 
     persist_setup(S);
     uint32_t parity = 0;
     level_sweep_phase<DIR, 1>(a, vin, vout, nullptr, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * kStageBytes,
-                              smem_u32(&S.bar[warp]), parity, policy_evict_first());
+                              smem_u32(&S.bar[warp][0]), parity, policy_evict_first());
 }
 
 // ---------------------------------------------------------------------------------
