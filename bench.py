@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--tol", type=float, default=1e-12)
     ap.add_argument("--precond", default=None, choices=["ssor", "ssor_level", "jacobi"], help="default: the package default")
     ap.add_argument("--omega", type=float, default=None)
+    ap.add_argument("--check-every", type=int, default=None, help="iterations per convergence poll (= per launch of the persistent kernel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-transport", default="auto", choices=["auto", "shm", "nccl"],
                     help="N > 1: how the fields reach rank 0's host memory (shared host array / NCCL gather + drain)")
@@ -286,6 +287,8 @@ def run_b200(args):
     op, grad_w, e, integral, geom_s = cof.compute_geometrical_quantities(coords, normals, tris, areas)
     nb = op.n_blocks
     solver = cof._solver(op)
+    if args.check_every:
+        solver.check_every = args.check_every
 
     # ---- device-resident leg ("value")
     I_dev = I_pin.to(dev, non_blocking=False)
@@ -513,6 +516,9 @@ def run_b200(args):
             return mdist.solve_shard_and_gather(op, I_host, I_host, t_k, LAMBDA, counts, gather="root",
                                                 transport=args.e2e_transport)[0]
 
+        transport_used = args.e2e_transport
+        if world > 1 and transport_used == "auto":       # what "auto" resolves to (distributed.solve_shard_and_gather)
+            transport_used = "shm" if mdist._result_pool.same_host() else "nccl"
         out = e2e_step()                              # one warm-up pass (allocations, pinned staging)
         del out
         barrier()
@@ -525,9 +531,12 @@ def run_b200(args):
         e2e = {"value": world * n * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * e2e_s / args.steps,
                "api": "compute_optical_flow.compute_velocity_field(numpy in, list of numpy out)" if world == 1 else
-                      "distributed.solve_shard_and_gather(numpy shard in; every rank drains its fields into one shared "
-                      "host array that rank 0 returns as numpy)" if args.e2e_transport != "nccl" else
-                      "distributed.solve_shard_and_gather(numpy shard in; NCCL gather to rank 0; numpy out)"}
+                      ("distributed.solve_shard_and_gather(numpy shard in; NCCL gather of every batch to rank 0, which copies it to "
+                       "the host; numpy out)" if transport_used == "nccl" else
+                       "distributed.solve_shard_and_gather(numpy shard in; every rank drains its own fields over its own PCIe link "
+                       "into its rows of a pooled, CUDA-registered shared host array that rank 0 returns as numpy; no data-path "
+                       "collective)"),
+               "transport": None if world == 1 else transport_used}
 
     if rank == 0:
         line = {

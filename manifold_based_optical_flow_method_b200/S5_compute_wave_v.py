@@ -34,7 +34,11 @@ def _surface_arrays(surface):
 def _operator(coordinates, triangles, areas, e=None):
     """Mesh handle cached per (coordinates, triangles) buffers; normals only define e, which S5
     receives from the caller, so the handle is built with dummy normals and e is uploaded."""
-    key = (coordinates.shape, triangles.shape, float(coordinates.sum()), int(np.asarray(triangles).sum()))
+    import hashlib
+    digest = hashlib.blake2b(digest_size=16)             # content hash: equal sums do not mean equal meshes
+    digest.update(np.ascontiguousarray(coordinates, dtype=np.float64).tobytes())
+    digest.update(np.ascontiguousarray(triangles, dtype=np.int64).tobytes())
+    key = (coordinates.shape, triangles.shape, digest.hexdigest())
     op = _ops.get(key)
     if op is None:
         _ops.clear()

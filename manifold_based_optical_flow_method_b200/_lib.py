@@ -157,13 +157,26 @@ def _declare(lib):
 
 
 def load():
-    """Load (building first if needed) libmof_b200.so.  Raises if it cannot be had."""
+    """Load libmof_b200.so, (re)building it first when it is missing or older than its sources.
+    Raises if it cannot be had.  The build is serialised across processes (torchrun starts every
+    rank at once) with a file lock; nvcc writes to a temporary name that is renamed into place."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    try:
+        stale = _build.needs_build()
+    except OSError:
+        stale = not os.path.exists(LIB_PATH)
+    if stale:
+        try:
+            _build.build_locked()
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
+            import warnings
+            warnings.warn(f"{LIB_PATH} is older than its sources and could not be rebuilt (nvcc missing?); "
+                          "loading the existing binary")
     try:
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as exc:

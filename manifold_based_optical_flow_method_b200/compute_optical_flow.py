@@ -41,7 +41,7 @@ settings = {
     "max_iter": DEFAULT_MAX_ITER,
     "precond": DEFAULT_PRECOND,    # "ssor": block-multicolour SSOR (Eisenstat form); "ssor_level": the same on the
                                    # level-scheduled natural ordering; "jacobi": 2x2 block Jacobi
-    "omega": None,                 # SSOR relaxation factor; None = 1.4 ("ssor") / 1.85 ("ssor_level")
+    "omega": None,                 # SSOR relaxation factor; None = 1.4 ("ssor") / 1.9 ("ssor_level")
     "batch_groups": None,          # None = sized from free device memory (<= 32 groups of 32 frames)
     "streams": None,               # None = solver default (1; 2 = batches on two concurrent streams)
     "allow_unconverged": False,
@@ -86,7 +86,9 @@ def _solver(op):
     if s is None or s.op is not op or s.precond != precond or (precond != "jacobi" and s.omega != omega) \
             or (settings["batch_groups"] is not None and s.batch_groups != settings["batch_groups"]) \
             or (streams is not None and s.n_streams != streams):
-        _solvers.clear()           # one mesh at a time keeps device memory bounded
+        for old in _solvers.values():     # one mesh at a time keeps device memory bounded; stop the old drain thread
+            old.close()
+        _solvers.clear()
         kw = {} if streams is None else {"n_streams": streams}
         s = _solvers[key] = VelocitySolver(op, batch_groups=settings["batch_groups"], precond=precond, omega=omega, **kw)
     s.tol, s.max_iter = settings["tol"], settings["max_iter"]

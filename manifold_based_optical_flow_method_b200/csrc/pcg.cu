@@ -806,6 +806,7 @@ static_assert(kStageValBytes + 3 * kStageVecBytes <= kStageBytes, "stage too sma
 constexpr int kPersistMaxGroups = 1024;                               // active-group list kept in shared memory (uint16)
 constexpr int kDescInts = 8;                                          // per row and direction: bs, cnt, col[0..5]
 constexpr int kDescCols = kDescInts - 2;
+constexpr uint32_t kRowBlock = 8;                                     // rows per block of the sweeps' work list (= warps per CTA)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -891,7 +892,12 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
                                                   uint32_t bar, uint32_t& parity, uint64_t policy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t N = (uint32_t)a.N;
-    const uint32_t total = N * (uint32_t)A;                           // host guarantees N * n_groups < 2^31
+    // Work list: blocks of kRowBlock consecutive rows, inside a block group by group, inside a group row by
+    // row -- the eight warps of a CTA take eight consecutive rows of ONE group, so a CTA's bulk copies walk
+    // contiguous memory (matrix blocks and vector rows of neighbouring rows are neighbours in HBM).  Any order
+    // that is monotone in the row within a group keeps "an item depends on earlier items only".
+    const uint32_t nblk = (N + kRowBlock - 1) / kRowBlock;
+    const uint32_t total = nblk * kRowBlock * (uint32_t)A;            // host guarantees (N + kRowBlock) * n_groups < 2^31
     const uint32_t W = gridDim.x * kWarps, uA = (uint32_t)A;
     uint32_t J = blockIdx.x * kWarps + warp;
     if (J >= total) return;
@@ -903,12 +909,21 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
     const double* sv = reinterpret_cast<const double*>(stage) + lane;
     const double* sx = reinterpret_cast<const double*>(stage + kStageValBytes) + lane;
 
-    // item J -> (row, group); everything of the item that does not depend on the sweep goes into the stage
+    // item J -> (row, group); row >= N: padding of the last block (skipped)
     auto item = [&](uint32_t j, uint32_t& irow, uint32_t& ig) {
-        const uint32_t q = j / uA;
-        irow = DIR ? q : N - 1 - q;
-        ig = act ? act[j - q * uA] : j - q * uA;
+        const uint32_t blk = j / (kRowBlock * uA), rem = j - blk * (kRowBlock * uA);
+        const uint32_t ia = rem / kRowBlock, q = blk * kRowBlock + (rem - ia * kRowBlock);
+        irow = DIR ? q : nblk * kRowBlock - 1 - q;
+        ig = act ? act[ia] : ia;
     };
+    // first real item of this warp
+    uint32_t row, g, gprev = 0xffffffffu;
+    for (;;) {
+        item(J, row, g);
+        if (row < N) break;
+        J += W;
+        if (J >= total) return;
+    }
     auto issue = [&](uint32_t irow, uint32_t ig, int32_t d) {
         const int32_t bs = __shfl_sync(kFull, d, 0), cnt = __shfl_sync(kFull, d, 1);
         if (lane == 0) {
@@ -927,8 +942,6 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             }
         }
     };
-    uint32_t row, g, gprev = 0xffffffffu;
-    item(J, row, g);
     int32_t cd = __ldg(desc + (size_t)row * kDescInts + (lane & 7)), nd = 0;
     issue(row, g, cd);
     // per-frame scalars of the item's group: re-read only when the group changes (with W a multiple of A, never)
@@ -937,13 +950,15 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
     long long probe_prev = PROBE ? clock64() : 0, pacc[5] = {0, 0, 0, 0, 0};
 
     for (;;) {
-        const uint32_t Jn = J + W;
-        const bool more = Jn < total;
-        uint32_t rown = 0, gn = 0;
-        if (more) {
+        uint32_t Jn = J + W, rown = 0, gn = 0;
+        bool more = Jn < total;
+        while (more) {                                   // skip the padding rows of the last block
             item(Jn, rown, gn);
-            nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
+            if (rown < N) break;
+            Jn += W;
+            more = Jn < total;
         }
+        if (more) nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
         if (g != gprev) {                                // these loads overlap the gather below
             const int iters = __ldcg(state_ptr(B.state, g, MOF_I_ITERS) + lane);
             par = (MODE == 0 ? iters : iters + 1) & 1;
@@ -1119,7 +1134,7 @@ __device__ __forceinline__ void persist_setup(PersistShared& S) {
 // p'Ap = sum of the per-row shares the forward sweep left in `dots` -> alpha.  level_dot_kernel's arithmetic (a
 // warp adds its eight rows in order, tile_reduce does the rest); a warp's rows are one contiguous 2 KB piece,
 // fetched by one bulk copy per item, two items ahead (three slots).
-__device__ __forceinline__ void level_dot_phase(const LevelArgs& a, const double* dots, const uint16_t* act, int A,
+__device__ __noinline__ void level_dot_phase(const LevelArgs& a, const double* dots, const uint16_t* act, int A,
                                                 unsigned char* stage, uint32_t bar0, uint32_t& parity3, uint64_t policy,
                                                 double (*red)[1][MOF_W]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1168,7 +1183,7 @@ __device__ __forceinline__ void level_dot_phase(const LevelArgs& a, const double
 // r -= alpha (t + w) ; r'r -> beta and the convergence test.  update_body<true>'s arithmetic; the three vectors
 // of a warp's rows come in by bulk copies, four rows (3 x 2 KB) at a time, the next piece requested as soon as
 // the stage has been read.
-__device__ __forceinline__ void level_update_phase(const LevelArgs& a, const uint16_t* act, int A, unsigned char* stage,
+__device__ __noinline__ void level_update_phase(const LevelArgs& a, const uint16_t* act, int A, unsigned char* stage,
                                                    uint32_t bar, uint32_t& parity, uint64_t policy, double (*red)[2][MOF_W]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const mof_batch_dev& B = a.B;
@@ -1243,7 +1258,7 @@ __device__ __forceinline__ void level_update_phase(const LevelArgs& a, const uin
 // Second half of the two reductions, after a grid barrier: one CTA per group adds the tile partials in
 // tile_reduce's order and takes the scalar step (STEP 0: alpha from p'Ap, STEP 1: beta and convergence).
 template <int STEP>
-__device__ __forceinline__ void level_group_phase(const LevelArgs& a, const uint16_t* act, int A,
+__device__ __noinline__ void level_group_phase(const LevelArgs& a, const uint16_t* act, int A,
                                                   double (*red)[STEP + 1][MOF_W]) {
     const mof_batch_dev& B = a.B;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1622,7 +1637,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     // Persistent level kernels (default of the level path): cooperative launches sized to the device.
     const char* persist_env = getenv("MOF_LEVEL_PERSIST");
     bool persist = levels && mesh->level_desc && B.ready && G <= kPersistMaxGroups &&
-                   (double)N * (double)G < 2147483648.0 - 65536.0 && !(persist_env && persist_env[0] == '0');
+                   ((double)N + kRowBlock) * (double)G < 2147483648.0 - 65536.0 && !(persist_env && persist_env[0] == '0');
     g_last_path[3] = persist ? 0 : (!levels ? 0 : !mesh->level_desc ? 1 : !B.ready ? 2 : G > kPersistMaxGroups ? 3 : 4);
     int grid_iter = 0, grid_sweep = 0;
     const void* iter_fn = nullptr;
@@ -1671,6 +1686,10 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
             int want = cta_env ? atoi(cta_env) : 0;
             grid_iter = sms * ((want >= 1 && want < occ_iter) ? want : occ_iter);
             grid_sweep = sms * ((want >= 1 && want < occ_s) ? want : occ_s);
+            // a grid that is a multiple of the group count keeps every warp on one group from item to item
+            // (its per-frame scalars stay in registers) while all groups are active
+            if (2 * G <= grid_iter) grid_iter = grid_iter / G * G;
+            if (2 * G <= grid_sweep) grid_sweep = grid_sweep / G * G;
             MOF_CUDA_TRY(cudaMemsetAsync(B.ready, 0, (size_t)G * N * sizeof(int32_t), st));
         }
     }

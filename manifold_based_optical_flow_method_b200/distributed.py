@@ -131,6 +131,90 @@ def shared_host_rows(rows, width, group=None):
     return np.frombuffer(mm, dtype=np.float64, count=int(rows) * int(width)).reshape(int(rows), int(width))
 
 
+class SharedResultPool:
+    """Result buffers of the multi-GPU host delivery: (rows, width) float64 arrays in shared memory that every
+    rank of the host maps (shared_host_rows), kept across calls.  When a buffer is created every rank touches
+    its own rows (the page faults of fresh shared memory happen once, in parallel, outside any later timed
+    path) and registers them with CUDA (cudaHostRegister), so that from then on a rank's drain is one direct
+    DMA per batch over its own PCIe link.  A buffer is handed out again only after the caller has let go of
+    every array that refers to it (reference count of the mapping's root array, decided by the receiving
+    rank and broadcast), so results a caller still holds are never overwritten."""
+
+    def __init__(self):
+        self.entries = []
+        self._same_host = {}
+
+    def same_host(self, group=None):
+        key = id(group)
+        if key not in self._same_host:
+            self._same_host[key] = same_host(group)
+        return self._same_host[key]
+
+    @staticmethod
+    def _in_use(entry):
+        import sys
+        return sys.getrefcount(entry["root"]) > entry["baseline"]
+
+    def acquire(self, rows, width, my_rows, receiver, register=True, group=None):
+        """Collective.  -> entry dict: ``array`` (rows, width) view of the whole buffer (make a fresh view per
+        hand-out with ``view()``), ``mine`` numpy view of rows my_rows[0]:my_rows[1], ``mine_t`` torch CPU tensor
+        over the same memory (pinned when ``pinned`` is True)."""
+        import sys
+        import torch
+        dist = _dist()
+        rows, width = int(rows), int(width)
+        pick = [-1]
+        if receiver:
+            for i, e in enumerate(self.entries):
+                if e["shape"] == (rows, width) and e["my_rows"] == tuple(my_rows) and not self._in_use(e):
+                    pick[0] = i
+                    break
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(pick, src=src, group=group)
+        if pick[0] >= 0:
+            return self.entries[pick[0]]
+        # receivers drop buffers of other shapes that nobody holds any more (a new mesh, a new frame count)
+        for e in [e for e in self.entries if e["shape"] != (rows, width) and not self._in_use(e)]:
+            self._release(e)
+        arr = shared_host_rows(rows, width, group=group)
+        root = arr.base if isinstance(arr.base, np.ndarray) else arr
+        a, b = int(my_rows[0]), int(my_rows[1])
+        mine = arr[a:b]
+        mine[...] = 0.0                                   # first touch of this rank's pages
+        mine_t = torch.from_numpy(mine)
+        pinned = False
+        if register and b > a and torch.cuda.is_available():
+            rc = torch.cuda.cudart().cudaHostRegister(mine.ctypes.data, mine.nbytes, 0)
+            pinned = int(rc) == 0
+        entry = {"shape": (rows, width), "my_rows": (a, b), "root": root, "mine": mine, "mine_t": mine_t,
+                 "pinned": pinned, "ptr": mine.ctypes.data}
+        del arr, root, mine
+        entry["baseline"] = sys.getrefcount(entry["root"])   # the pool's own references; more = a caller holds a view
+        self.entries.append(entry)
+        dist.barrier(group=group)                        # every rank has faulted and registered its rows
+        return entry
+
+    @staticmethod
+    def view(entry):
+        """A fresh (rows, width) array over the buffer for the caller; while it (or anything derived from it)
+        lives, the buffer is not reused."""
+        return entry["root"].reshape(entry["shape"])
+
+    def _release(self, entry):
+        import torch
+        if entry["pinned"]:
+            torch.cuda.cudart().cudaHostUnregister(entry["ptr"])
+            entry["pinned"] = False
+        self.entries.remove(entry)
+
+    def close(self):
+        for e in list(self.entries):
+            self._release(e)
+
+
+_result_pool = SharedResultPool()
+
+
 def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather="all", to_host=True, transport="auto"):
     """Multi-GPU entry point: this rank solves the frames of its shard -- ``I_shard`` /
     ``I2_shard`` hold rows k0 .. k1 (one-frame halo: frame k1-1 reads I2[k1]) and
@@ -138,13 +222,15 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
     delivered.  gather: "all" (every rank gets all frames), "root" (rank 0 only; other ranks
     get None) or "none" (each rank keeps its shard).  -> (V, SolveInfo); V is a numpy array
     if to_host else a device tensor.  transport (host delivery with gather "all" / "root"):
-    "nccl" -- every finished batch is gathered over NVLink on a side stream and drained by
-    rank 0 (straight into pinned memory) or by every rank while the next batch is solved;
-    "shm" -- every rank drains its shard into one shared host array that all ranks of the host
-    map (with "all" every rank returns the SAME memory; needs all ranks on one host);
-    "auto" = "nccl": on 2 GPUs it measured 434 frames/s end to end against 396 for "shm", whose
-    first-touch page faults on fresh shared memory (4 KB pages, one lock) cost more than the
-    NVLink hop saves."""
+    "shm" -- no collective on the data path: every rank drains its own shard over its own PCIe link, one
+    direct DMA per batch, into its rows of a pooled shared host array that all ranks of the host map and
+    that was faulted in and registered with CUDA when it was created (SharedResultPool); with "all" every
+    rank returns the SAME memory; needs all ranks on one host;
+    "nccl" -- every finished batch is gathered over NVLink on a side stream and drained by rank 0 (straight
+    into pinned memory when the block can be pinned) or by every rank;
+    "auto" -- "shm" when all ranks share the host, else "nccl".  (Round 1 funnelled everything through rank 0's
+    link: 0.79 end-to-end efficiency at 8 GPUs; fresh unregistered shared memory had lost to it at 2 GPUs only
+    because of first-touch faults inside the timed path.)"""
     import torch
     from . import compute_optical_flow as cof
     from .solver import SolveInfo
@@ -155,10 +241,11 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
     width = 2 * N
     if transport not in ("auto", "shm", "nccl"):
         raise ValueError("transport must be 'auto', 'shm' or 'nccl'")
-    if to_host and world > 1 and gather in ("all", "root") and transport == "shm":
-        if not same_host():
+    if to_host and world > 1 and gather in ("all", "root") and transport in ("shm", "auto"):
+        if _result_pool.same_host():
+            return _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather, r, n_loc, width)
+        if transport == "shm":
             raise RuntimeError("transport='shm' needs every rank on the same host")
-        return _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather, r, n_loc, width)
     # Host delivery over NCCL with equal shards: gather every finished batch over NCCL on a side stream and
     # drain it to the host while the next batch is being solved.
     pipelined = to_host and world > 1 and gather in ("all", "root") and len(set(counts)) == 1 and n_loc > 0
@@ -179,12 +266,10 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
         elif receives:
             V_host = np.empty((sum(counts), width), dtype=np.float64)
         drain = solver.drain(width)
-        # two batches per shard: gather + drain of the first hide behind the solve of the second
-        # (smaller batches would hide more of the drain but cost more in solve efficiency)
-        groups = -(-n_loc // 32)
-        saved_groups = solver.batch_groups
-        if solver.precond != "ssor_level":       # the level path is launch-bound: a half-sized batch costs as much as a full one
-            solver.batch_groups = max(8, min(saved_groups, -(-groups // 2)))
+        if receives and gather == "root" and cof.settings["pinned_results"] and not pinned:
+            import warnings
+            warnings.warn(f"result of {sum(counts) * width * 8 / 2**30:.1f} GiB was not pinned (above the cap or refused by "
+                          "the host): delivering into pageable memory through the staged drain")
 
         def on_batch(k0, k1, Vd):
             def collect():
@@ -214,7 +299,6 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
         rep = np.zeros((0, 3))
     rep_dev = torch.from_numpy(rep).to(op.device)
     if pipelined:
-        solver.batch_groups = saved_groups
         drain.finish()
         torch.cuda.current_stream(op.device).wait_stream(drain.stream)
         rep_all = gather_rows(rep_dev, counts, root=0 if gather == "root" else None)
@@ -236,21 +320,26 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
 
 
 def _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather, r, n_loc, width):
-    """Host delivery through shared memory: each rank's finished batches are drained (side stream,
-    pinned staging, copy threads) into its own rows of the shared array while the next batch is
-    being solved; the per-frame solve report is the only thing that crosses NCCL."""
+    """Host delivery through pooled shared memory: each rank's finished batches go straight into its own
+    rows of the shared array (one DMA per batch on a side stream, over the rank's own PCIe link) while the
+    next batch is being solved; the per-frame solve report is the only thing that crosses NCCL."""
     import torch
     from . import compute_optical_flow as cof
     from .solver import SolveInfo
-    V_host = shared_host_rows(sum(counts), width)
     start = int(np.sum(counts[:r]))
-    mine = V_host[start:start + n_loc]
+    receiver = gather == "all" or r == 0
+    entry = _result_pool.acquire(sum(counts), width, (start, start + n_loc), receiver)
     if n_loc > 0:
         solver = cof._solver(op)
         drain = solver.drain(width)
         I_dev, I2_dev = cof._upload_signals(op, I_shard, I2_shard, n_loc)
-        _, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc,
-                                      on_batch=lambda k0, k1, Vd: drain.submit(Vd, mine[k0:k1]))
+        if entry["pinned"]:
+            mine_t = entry["mine_t"]
+            on_batch = lambda k0, k1, Vd: drain.submit_pinned(Vd, mine_t[k0:k1])
+        else:                                            # registration refused: staged copies into the same rows
+            mine = entry["mine"]
+            on_batch = lambda k0, k1, Vd: drain.submit(Vd, mine[k0:k1])
+        _, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc, on_batch=on_batch)
         drain.finish()
         rep = np.stack([info.iterations.astype(np.float64), info.relres, info.status.astype(np.float64)], axis=1)
     else:
@@ -260,7 +349,7 @@ def _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, count
     if rep_all is None:
         return None, (SolveInfo(info.iterations, info.relres, info.status) if info is not None else None)
     rep_np = rep_all.cpu().numpy()
-    return V_host, SolveInfo(rep_np[:, 0].astype(np.int32), rep_np[:, 1].copy(), rep_np[:, 2].astype(np.int32))
+    return _result_pool.view(entry), SolveInfo(rep_np[:, 0].astype(np.int32), rep_np[:, 1].copy(), rep_np[:, 2].astype(np.int32))
 
 
 def compute_velocity_field_sharded(op, n_frames, t_k, lambda_, I_k, I_k_2, gather="all", to_host=True, transport="auto"):

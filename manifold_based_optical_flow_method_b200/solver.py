@@ -131,6 +131,7 @@ class VelocitySolver:
         self._lanes = None           # per-stream (FrameBatch, torch Stream, PcgProfile) of the concurrent path
         self._pool = None
         self._drain = None
+        self._drain_finalizer = None
         self.profile = None          # set to _lib.PcgProfile() to accumulate sampled kernel timings
         self.aux_launches = 0        # pack / assemble / unpack launches issued so far
 
@@ -204,8 +205,23 @@ class VelocitySolver:
         """Cached HostDrain with pinned staging buffers of ``rows`` x width doubles."""
         rows = int(rows or DRAIN_STAGE_ROWS)
         if self._drain is None or not self._drain.fits(rows, width):
+            if self._drain is not None:
+                self._drain.close()
             self._drain = HostDrain(self.torch, self.op.device, rows, width)
+            if self._drain_finalizer is not None:
+                self._drain_finalizer.detach()
+            import weakref
+            self._drain_finalizer = weakref.finalize(self, HostDrain.close, self._drain)
         return self._drain
+
+    def close(self):
+        """Release the host-side helpers (drain thread, pinned staging, stream pool)."""
+        if self._drain is not None:
+            self._drain.close()
+            self._drain = None
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
 
     def assemble(self, batch, I_now, I_next, dt, lambda_, n_frames):
         """pack + K1 for the first n_frames rows of I_now / I_next (device, (>=n_frames, N))."""
@@ -311,21 +327,47 @@ class HostDrain:
         from concurrent.futures import ThreadPoolExecutor
         self.torch, self.device = torch, device
         self.max_rows, self.width = int(max_rows), int(width)
-        self.stages = [torch.empty((self.max_rows, self.width), dtype=torch.float64).pin_memory() for _ in range(n_stages)]
-        self.free = [threading.Event() for _ in range(n_stages)]
-        for f in self.free:
-            f.set()
+        self.n_stages = n_stages
+        self.stages = None                # pinned staging ring, copy pool and worker thread: created by the first
+        self.free = None                  # submit(); the direct-DMA path (submit_pinned) never needs them
         self.stream = torch.cuda.Stream(device=device)
         self.queue = queue.Queue()
         if copy_threads is None:          # staging -> destination memcpy is the slow half of the drain
             import os
             copy_threads = max(4, min(12, (os.cpu_count() or 8) - 2))
-        self.pool = ThreadPoolExecutor(copy_threads)
+        self.pool = None
         self.copy_threads = copy_threads
         self.count = 0
         self.error = None
+        self.thread = None
+        self.closed = False
+
+    def _start_staging(self):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        torch = self.torch
+        self.stages = [torch.empty((self.max_rows, self.width), dtype=torch.float64).pin_memory() for _ in range(self.n_stages)]
+        self.free = [threading.Event() for _ in range(self.n_stages)]
+        for f in self.free:
+            f.set()
+        self.pool = ThreadPoolExecutor(self.copy_threads)
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+
+    def close(self):
+        """Stop the worker thread and the copy pool and drop the pinned staging buffers (a replaced or
+        garbage-collected drain must not keep ~2.7 GB of pinned memory and a thread alive)."""
+        if self.closed:
+            return
+        self.closed = True
+        if self.thread is not None:
+            self.queue.put(None)
+            self.thread.join()
+            self.thread = None
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+            self.pool = None
+        self.stages = None
 
     def fits(self, rows, width):
         return rows <= self.max_rows and width == self.width
@@ -350,6 +392,10 @@ class HostDrain:
                 self.submit(src_dev[a:a + self.max_rows], dst_host[a:a + self.max_rows])
             return
         torch = self.torch
+        if self.closed:
+            raise RuntimeError("HostDrain is closed")
+        if self.stages is None:
+            self._start_staging()
         i = self.count % len(self.stages)
         self.count += 1
         self.free[i].wait()
@@ -397,7 +443,8 @@ class HostDrain:
                 self.queue.task_done()
 
     def finish(self):
-        self.queue.join()
+        if self.thread is not None:
+            self.queue.join()
         if getattr(self, "direct_pending", False):
             self.stream.synchronize()
             self.direct_pending = False

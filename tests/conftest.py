@@ -16,6 +16,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_ready():
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """On a box without a CUDA device the gpu-marked tests are skipped (they would otherwise fail in their
+    fixtures); on a GPU box nothing is skipped, and a missing library is an error, not a skip."""
+    if _cuda_ready():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200); run with -m gpu on the GPU box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
 

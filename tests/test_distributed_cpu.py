@@ -57,6 +57,23 @@ def _worker(rank, world, port, n_frames, width, out_dir):
         empty = mdist.shared_host_rows(0, width)
         assert empty.shape == (0, width)
         del shared, empty
+        # pooled result buffers: reused once the caller has dropped every view, never while one is held
+        pool = mdist.SharedResultPool()
+        assert pool.same_host()
+        e1 = pool.acquire(n_frames, width, (k0, k1), receiver=(rank == 0), register=False)
+        e1["mine"][...] = full[k0:k1].numpy()
+        dist.barrier()
+        V1 = pool.view(e1)
+        assert np.array_equal(V1, full.numpy())
+        rows = list(V1)                                   # what compute_velocity_field hands to the caller
+        del V1
+        e2 = pool.acquire(n_frames, width, (k0, k1), receiver=(rank == 0), register=False)
+        assert e2 is not e1                               # rank 0 still holds rows of the first buffer
+        del rows
+        e3 = pool.acquire(n_frames, width, (k0, k1), receiver=(rank == 0), register=False)
+        assert e3 is e1 or e3 is e2                       # both free now: no third buffer
+        assert len(pool.entries) == 2
+        pool.close()
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     finally:
         dist.destroy_process_group()
