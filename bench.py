@@ -43,13 +43,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--level", type=int, default=7, help="icosphere level of the pial-like mesh (7 = 163,842 vertices)")
-    ap.add_argument("--frames", type=int, default=1000, help="frames of signal per GPU (frames-1 solves per step)")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c4"],
+                    help="BASELINE.json workload: c2 (default, the headline: pial-like ico7, 1000-frame travelling wave; c3 = c2 on N GPUs), "
+                         "c4 (two hemispheres, 327,684 vertices, wrapped-phase input, 257 frames), c1 (icosphere 5, 64 frames)")
+    ap.add_argument("--level", type=int, default=None, help="icosphere level of the mesh (default: 7, c1: 5)")
+    ap.add_argument("--frames", type=int, default=None, help="frames of signal per GPU (frames-1 solves per step); default 1000 / 257 (c4) / 64 (c1)")
     ap.add_argument("--batch-groups", type=int, default=None)
     ap.add_argument("--streams", type=int, default=None, help="concurrent solve streams (default: the package default, 1)")
     ap.add_argument("--tol", type=float, default=1e-12)
     ap.add_argument("--precond", default=None, choices=["ssor", "ssor_level", "jacobi"], help="default: the package default")
     ap.add_argument("--omega", type=float, default=None)
+    ap.add_argument("--tune-omega", action="store_true",
+                    help="probe omega in {1.7, 1.8, 1.9} on the first 32 frames during setup (default for --config c4)")
     ap.add_argument("--check-every", type=int, default=None, help="iterations per convergence poll (= per launch of the persistent kernel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-transport", default="auto", choices=["auto", "shm", "nccl"],
@@ -57,12 +62,30 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=None)
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="wall-clock budget of the reference arm")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.level is None:
+        args.level = 5 if args.config == "c1" else 7
+    if args.frames is None:
+        args.frames = {"c1": 64, "c2": 1000, "c4": 257}[args.config]
+    return args
 
 
 def workload_name(args, n_gpus):
-    return (f"C2/C3 pial-like ico{args.level} mesh, {args.frames}-frame travelling-wave signal per GPU "
+    head = {"c1": f"C1 icosphere level {args.level}", "c2": f"C2/C3 pial-like ico{args.level} mesh",
+            "c4": f"C4 two pial-like ico{args.level} hemispheres"}[args.config]
+    sig = "wrapped-phase signal (value range of S2_interpolate_phases.py:52)" if args.config == "c4" else "travelling-wave signal"
+    return (f"{head}, {args.frames}-frame {sig} per GPU "
             f"({args.frames - 1} solves/step/GPU, {n_gpus} GPU(s)), lambda={LAMBDA}, PCG tol={args.tol:g}")
+
+
+def make_workload(args, t_k, frame_offset=0):
+    """-> (mesh tuple, (T, N) signal) of the configured BASELINE.json workload."""
+    from manifold_based_optical_flow_method_b200 import synthetic
+    if args.config == "c4":
+        mesh = synthetic.two_hemispheres(args.level)
+        return mesh, synthetic.wrapped_phase(mesh[0], t_k, seed=0)
+    mesh = synthetic.icosphere(args.level) if args.config == "c1" else synthetic.pial_like(args.level)
+    return mesh, synthetic.travelling_wave(mesh[0], t_k, seed=0, frame_offset=frame_offset)
 
 
 # --------------------------------------------------------------------------------------
@@ -156,10 +179,9 @@ def run_reference(args):
     if rank != 0:
         return
     from manifold_based_optical_flow_method_b200 import synthetic
-    mesh = synthetic.pial_like(args.level)
     procs = cpu_procs(args.cpu_procs)
     t_k = synthetic.time_axis(procs + 1, SF)
-    I = synthetic.travelling_wave(mesh[0], t_k, seed=0)
+    mesh, I = make_workload(args, t_k)
     t_start = time.time()
     fps, secs = cpu_wave(mesh, I, t_k, procs)          # first wave doubles as the size probe
     warm_done = 1
@@ -224,12 +246,11 @@ def run_b200(args):
     # ---- workload: every rank owns frames [rank*T, (rank+1)*T) of a world*T-frame signal
     T = args.frames
     n = T - 1
-    mesh = synthetic.pial_like(args.level)
-    coords, tris, normals, areas = mesh
-    N = len(coords)
     t_all = synthetic.time_axis(world * T, SF)
     t_k = t_all[rank * T:(rank + 1) * T]
-    I_np = synthetic.travelling_wave(coords, t_k, seed=0, frame_offset=rank * T)
+    mesh, I_np = make_workload(args, t_k, frame_offset=rank * T)
+    coords, tris, normals, areas = mesh
+    N = len(coords)
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only); runs BEFORE CUDA is initialised
     # because it forks one process per frame like the reference's Pool
@@ -286,6 +307,11 @@ def run_b200(args):
     t0 = time.time()
     op, grad_w, e, integral, geom_s = cof.compute_geometrical_quantities(coords, normals, tris, areas)
     nb = op.n_blocks
+    omega_probe = None
+    if (args.tune_omega or args.config == "c4") and not args.omega and cof.settings["precond"] != "jacobi":
+        t_probe = time.time()
+        best, rep = cof.tune_omega(op, tris, list(t_k), LAMBDA, I_host, I_host)
+        omega_probe = {"chosen": best, "mean_iterations_on_first_32_frames": rep, "seconds": time.time() - t_probe}
     solver = cof._solver(op)
     if args.check_every:
         solver.check_every = args.check_every
@@ -555,7 +581,7 @@ def run_b200(args):
             "solver": {"converged": converged, "iterations_mean": float(np.mean(info.iterations)),
                        "iterations_max": int(np.max(info.iterations)), "relres_max": float(np.max(info.relres)),
                        "geometry_seconds": geom_s, "setup_seconds": time.time() - t0,
-                       "path": solver_path},
+                       "path": solver_path, "omega_probe": omega_probe},
         }
         _emit(json.dumps(line))
     if world > 1:

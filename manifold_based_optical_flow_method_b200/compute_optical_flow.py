@@ -155,6 +155,37 @@ def solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n):
     return V, info
 
 
+def tune_omega(a2, triangles, t_k, lambda_, I_k, I_k_2, candidates=(1.7, 1.8, 1.9), n_frames=32, apply=True):
+    """Pick the SSOR relaxation factor for a data set: solve its first ``n_frames`` frames (one 32-frame group)
+    with every candidate and keep the one with the fewest iterations (the iteration count of this solver
+    depends on the input: ~143 at omega 1.9 for smooth travelling waves at ico7, fewer at ~1.7-1.8 for
+    wrapped-phase input).  No counterpart in the reference (spsolve has no parameters); the
+    result does not change what is computed, only how fast.  -> (omega, {candidate: mean iterations});
+    with ``apply`` the choice is stored in ``settings["omega"]``."""
+    torch = _lib.require_cuda()
+    op = _operator(a2, triangles)
+    n = min(int(n_frames), len(t_k) - 1)
+    if n <= 0:
+        raise ValueError("need at least two frames")
+    I_dev, I2_dev = _upload_signals(op, I_k, I_k_2, n)
+    old = settings["omega"]
+    report = {}
+    try:
+        for w in candidates:
+            settings["omega"] = float(w)
+            s = _solver(op)
+            if not s.ssor:
+                raise ValueError("tune_omega needs an SSOR preconditioner (settings['precond'] 'ssor_level' or 'ssor')")
+            _, info = solve_on_device(op, I_dev, I2_dev, list(t_k[:n + 1]), lambda_, 0, n)
+            report[float(w)] = float(np.mean(info.iterations)) if info.converged else float("inf")
+    finally:
+        settings["omega"] = old
+    best = min(report, key=report.get)
+    if apply:
+        settings["omega"] = best
+    return best, report
+
+
 def compute_velocity_field(processes_num, time_steps, a2, grad_w, e, integral_wi_wj, triangles, t_k, areas,
                            lambda_, I_k, I_k_2):
     """Reference :152-194.  Frame k (k = 0 .. time_steps-2) uses (I_k[k], I_k_2[k+1]) (:174-175).
