@@ -19,6 +19,7 @@ scaling, no data-path collective).  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -462,6 +463,72 @@ def run_b200(args):
                         "note": "mof_spmv_batch (block-CSR, frame-minor) on the assembled batch; in-solver use: "
                                 + ("every iteration" if solver.precond == "jacobi" else "true-residual verification")}
 
+    # ---- assembly (K1: pack + the two assemble launches) timed alone on the first batch of the workload
+    # (north star: "fraction of the HBM roofline for the assembly ... bytes moved")
+    try:
+        from manifold_based_optical_flow_method_b200.solver import frame_dt
+        nfr = min(n, batch.n_groups * 32)
+        dt_dev = torch.from_numpy(frame_dt(list(t_k), 0, nfr)).to(dev)
+        as0, as1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        solver.assemble(batch, I_dev[:nfr], I_dev[1:nfr + 1], dt_dev, LAMBDA, nfr)
+        n_as = 5
+        as0.record()
+        for _ in range(n_as):
+            solver.assemble(batch, I_dev[:nfr], I_dev[1:nfr + 1], dt_dev, LAMBDA, nfr)
+        as1.record()
+        torch.cuda.synchronize()
+        as_ms = as0.elapsed_time(as1) / n_as
+        lanes = -(-nfr // 32) * 32
+        # pack: read I_now, I_next rows (16 N), write It, dIt (16 N); diagonal launch: read It, dIt (16 N), write rhs (16 N),
+        # minv (24 N) and the diagonal blocks; off-diagonal launch: read It (8 N) and minv (24 N), write the other blocks;
+        # all blocks together 32 nb.  Mesh constants (contributor lists, face geometry, lambda a2: ~75 MB) once per group.
+        as_frame = 32.0 * nb + (16 + 16 + 16 + 16 + 24 + 8 + 24) * float(N)
+        as_bytes = lanes * as_frame + (lanes // 32) * 75.0e6
+        as_gbs = as_bytes / (as_ms * 1e-3) / 1e9
+        roofline["assembly"] = {"kernel": "pack_kernel + assemble_diag_kernel + assemble_offdiag_kernel", "achieved": as_gbs,
+                                "frac": as_gbs / peak, "ms_per_batch": as_ms, "frames_per_batch": nfr,
+                                "algorithmic_bytes_per_frame": as_frame, "share_of_step": as_ms * (-(-n // nfr)) / (ms_total / args.steps),
+                                "note": "timed alone with CUDA events, 5 launches back to back; instruction-bound (every block gathers its "
+                                        "contributing faces' geometry), not bandwidth-bound"}
+    except Exception as exc:
+        roofline["assembly"] = {"error": repr(exc)}
+
+    # ---- S5 wave speed (config 5) on the resident signal read as a phase map: the whole call
+    # (transpose in, stencil, transpose out) and the stencil kernel alone; algorithmic bytes 8 N in + 8 N out per frame
+    wave_speed = None
+    try:
+        from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5
+        op5 = s5._operator(coords, tris, areas, e)
+        ph = torch.remainder(3.0 * I_dev + math.pi, 2.0 * math.pi) - math.pi
+        need = int(_lib.load().mof_wave_work_doubles(N, T, 0, 1))
+        work = torch.empty((need,), dtype=torch.float64, device=dev)
+        w0, w1, w2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        _, wv = s5.wave_speed_device(op5, ph, 0, T, 0, T, 1.0 / SF, True, work=work)
+        n_w = 5
+        w0.record()
+        for _ in range(n_w):
+            _, wv = s5.wave_speed_device(op5, ph, 0, T, 0, T, 1.0 / SF, True, work=work)
+        w1.record()
+        ms5 = op5.struct()
+        for _ in range(n_w):
+            _lib.check(_lib.load().mof_wave_stencil(_ct.byref(ms5), T, 0, T, 1.0 / SF, 1, 0, 1, work.data_ptr(), stream))
+        w2.record()
+        torch.cuda.synchronize()
+        call_ms, sten_ms = w0.elapsed_time(w1) / n_w, w1.elapsed_time(w2) / n_w
+        lanes5 = -(-T // 32) * 32
+        call_gbs = 16.0 * N * T / (call_ms * 1e-3) / 1e9
+        sten_gbs = 16.0 * N * lanes5 / (sten_ms * 1e-3) / 1e9
+        wave_speed = {"frames_per_s": T / (call_ms * 1e-3), "frames": T, "ms": call_ms,
+                      "whole_call": {"achieved": call_gbs, "frac": call_gbs / peak,
+                                     "note": "wave_pack_kernel + wave_stencil_kernel + wave_unpack_kernel on 16 N algorithmic bytes per frame "
+                                             "(the two transposes move another 32 N)"},
+                      "stencil": {"achieved": sten_gbs, "frac": sten_gbs / peak, "ms": sten_ms,
+                                  "note": "wave_stencil_kernel alone, frame-minor in and out (8 N + 8 N bytes per frame)"},
+                      "finite_fraction": float(torch.isfinite(wv).double().mean())}
+        del ph, work, wv
+    except Exception as exc:
+        wave_speed = {"error": repr(exc)}
+
     # ---- detection (K4 + K5), reported separately from the solve: tangent -> xyz, vmax,
     # singular vertices / faces with ordered compaction, on the fields of the last step
     detection = None
@@ -577,7 +644,7 @@ def run_b200(args):
                        "l2": "no flush: the per-step working set (1.17 GB of matrix values per 32-frame group) is >> 126 MB L2",
                        "parallelism": f"frames sharded over {world} GPU(s), one process per GPU"},
             "clocks": clock_report, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "detection": detection, "interpolation": interpolation,
+            "detection": detection, "interpolation": interpolation, "wave_speed": wave_speed,
             "solver": {"converged": converged, "iterations_mean": float(np.mean(info.iterations)),
                        "iterations_max": int(np.max(info.iterations)), "relres_max": float(np.max(info.relres)),
                        "geometry_seconds": geom_s, "setup_seconds": time.time() - t0,

@@ -351,10 +351,23 @@ int mof_rbf_evaluate(int64_t n_vertices, int64_t n_centres, int64_t n_frames, co
  * grad_point (n_frames,N,3) = compute_grad_M_I (S5:136-171); wave (n_frames,N) = time
  * derivative / |projected gradient| (S5:121), signed and unscaled like the functions'
  * return value (the script divides by 1000 and takes abs afterwards, S5:312-313).
- * The derivative couples neighbouring frames: pass all frames of a trial in one call.
+ * The derivative couples neighbouring frames, so a call names the rows it was given and the rows it must
+ * produce: I holds n_rows consecutive frames of a trial of T_trial frames, the first being frame t_first;
+ * outputs are written for rows out0 .. out0+n_out-1 of the call only (grad_point (n_out,N,3), wave (n_out,N));
+ * the other rows are halo (one frame either side; two at a trial end in amplitude mode, where np.gradient's
+ * one-sided formula applies).  Whole trial on one GPU: n_rows = n_out = T_trial, out0 = t_first = 0.  Frames
+ * sharded over GPUs (config 5): every rank passes its range plus the halo -- no collective on the data path.
+ * work: device scratch of mof_wave_work_doubles(N, n_rows, grad_point != NULL, wave != NULL) doubles (the
+ * signal and the results in the frame-minor layout [group][internal vertex][32 frames]).
  * ------------------------------------------------------------------------- */
-int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_frames, const double* I, int64_t ld, double dt,
-                   int phase_mode, double* grad_point, double* wave, void* stream);
+int64_t mof_wave_work_doubles(int64_t n_vertices, int64_t n_rows, int want_grad, int want_wave);
+int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
+                   int64_t T_trial, const double* I, int64_t ld, double dt, int phase_mode, double* grad_point,
+                   double* wave, double* work, void* stream);
+/* The stencil kernel alone on a work buffer that a previous mof_wave_speed call with the same arguments has
+ * packed (roofline hook of bench.py, like mof_spmv_batch). */
+int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t t_first, int64_t T_trial, double dt,
+                     int phase_mode, int want_grad, int want_wave, double* work, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * On-disk formats either side of the path ("next" row 4 of SURVEY 8f), host only, multi-threaded.

@@ -10,9 +10,12 @@ of SURVEY.md section 8f): wave speed = |d/dt| / |surface gradient| of a phase (o
 ``surface`` is anything with the pyvista members the reference uses (``points``, ``faces``,
 ``compute_cell_sizes(...)['Area']``) -- a real ``pyvista.PolyData`` or ``synthetic.SurfaceMesh``.
 The per-vertex face lists come from the mesh pattern (ascending face index) instead of
-``surface.point_cell_ids``.  One fused CUDA kernel (csrc/wave.cu) does the per-face gradient, the
-area-weighted vertex average, the tangent projection, the basis coefficients, their norm, the
-(wrapped) time derivative and the division; no CPU fallback.
+``surface.point_cell_ids``.  csrc/wave.cu transposes the signal into the frame-minor layout, runs one
+stencil kernel (per-face gradient, area-weighted vertex average, tangent projection, basis coefficients,
+their norm, the (wrapped) time derivative and the division; one warp per vertex, lane = frame) and
+transposes the result back; no CPU fallback.  Under torchrun the frames are sharded over the GPUs with a
+time-derivative halo (``wave_speed_device`` / the public functions do it transparently), no collective on
+the data path.
 """
 import ctypes
 
@@ -49,21 +52,70 @@ def _operator(coordinates, triangles, areas, e=None):
     return op
 
 
-def _run(op, data, dt, phase_mode, want_grad, want_wave):
+def halo_rows(k0, k1, T, phase_mode):
+    """Rows [a, b) of a T-frame trial that a call producing frames [k0, k1) must be given: one frame either
+    side for the central difference, the three end frames where np.gradient's one-sided formula applies."""
+    a, b = max(k0 - 1, 0), min(k1 + 1, T)
+    if not phase_mode and k1 > k0:
+        if k0 == 0:
+            b = max(b, min(3, T))
+        if k1 == T:
+            a = min(a, max(T - 3, 0))
+    return a, b
+
+
+def wave_speed_device(op, d_rows, t_first, T_trial, out0, n_out, dt, phase_mode, want_grad=False, want_wave=True,
+                      work=None):
+    """mof_wave_speed on device-resident rows ``d_rows`` ((n_rows, N) float64, reference vertex order; row 0 is
+    frame ``t_first`` of a ``T_trial``-frame trial) -> (grad (n_out, N, 3) or None, wave (n_out, N) or None) for
+    rows out0 .. out0+n_out-1.  bench.py and the sharded path call this."""
     torch = _lib.require_cuda()
     lib = _lib.load()
+    n_rows, N = int(d_rows.shape[0]), int(d_rows.shape[1])
+    if N != op.n_vertices:
+        raise ValueError(f"data must have shape (T, {op.n_vertices}), got {tuple(d_rows.shape)}")
+    assert d_rows.stride(1) == 1
+    need = int(lib.mof_wave_work_doubles(N, n_rows, int(want_grad), int(want_wave)))
+    if work is None or work.numel() < need:
+        work = torch.empty((need,), dtype=torch.float64, device=op.device)
+    grad = torch.empty((n_out, N, 3), dtype=torch.float64, device=op.device) if want_grad else None
+    wave = torch.empty((n_out, N), dtype=torch.float64, device=op.device) if want_wave else None
+    ms = op.struct()
+    st = torch.cuda.current_stream(op.device).cuda_stream
+    _lib.check(lib.mof_wave_speed(ctypes.byref(ms), n_rows, int(out0), int(n_out), int(t_first), int(T_trial),
+                                  d_rows.data_ptr(), d_rows.stride(0), float(dt), 1 if phase_mode else 0,
+                                  grad.data_ptr() if want_grad else None, wave.data_ptr() if want_wave else None,
+                                  work.data_ptr(), st))
+    return grad, wave
+
+
+def _run(op, data, dt, phase_mode, want_grad, want_wave):
+    """All frames of a trial.  One GPU: one call.  Under torchrun: every rank computes a contiguous range of
+    frames from its rows plus the halo (halo_rows) and the ranges are gathered (S5:79-123 is a loop over
+    independent frames once the time derivative has its neighbours)."""
+    torch = _lib.require_cuda()
+    from . import distributed
     data = np.ascontiguousarray(np.asarray(data, dtype=np.float64))
     T, N = data.shape
     if N != op.n_vertices:
         raise ValueError(f"data must have shape (T, {op.n_vertices}), got {data.shape}")
-    d = torch.from_numpy(data).to(op.device)
-    grad = torch.empty((T, N, 3), dtype=torch.float64, device=op.device) if want_grad else None
-    wave = torch.empty((T, N), dtype=torch.float64, device=op.device) if want_wave else None
-    ms = op.struct()
-    st = torch.cuda.current_stream(op.device).cuda_stream
-    _lib.check(lib.mof_wave_speed(ctypes.byref(ms), T, d.data_ptr(), N, float(dt), 1 if phase_mode else 0,
-                                  grad.data_ptr() if want_grad else None, wave.data_ptr() if want_wave else None, st))
-    return (grad.cpu().numpy() if want_grad else None), (wave.cpu().numpy() if want_wave else None)
+    world, r = distributed.world_size(), distributed.rank()
+    if world == 1:
+        d = torch.from_numpy(data).to(op.device)
+        grad, wave = wave_speed_device(op, d, 0, T, 0, T, dt, phase_mode, want_grad, want_wave)
+        return (grad.cpu().numpy() if want_grad else None), (wave.cpu().numpy() if want_wave else None)
+    counts = distributed.shard_counts(T, world)
+    k0, k1 = distributed.shard_range(T, world, r)
+    a, b = halo_rows(k0, k1, T, phase_mode)
+    if k1 > k0:
+        d = torch.from_numpy(data[a:b]).to(op.device)
+        grad, wave = wave_speed_device(op, d, a, T, k0 - a, k1 - k0, dt, phase_mode, want_grad, want_wave)
+    else:
+        grad = torch.empty((0, N, 3), dtype=torch.float64, device=op.device) if want_grad else None
+        wave = torch.empty((0, N), dtype=torch.float64, device=op.device) if want_wave else None
+    out_g = distributed.gather_rows(grad.reshape(k1 - k0, 3 * N), counts).reshape(T, N, 3).cpu().numpy() if want_grad else None
+    out_w = distributed.gather_rows(wave, counts).cpu().numpy() if want_wave else None
+    return out_g, out_w
 
 
 def compute_grad_M_I(coordinates, triangles, potentials, surface, areas):

@@ -50,7 +50,49 @@ __global__ void __launch_bounds__(256) pack_kernel(int64_t N, int32_t n_frames, 
     }
 }
 
-__global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
+// K1 in two launches.  First the diagonal blocks (the row's incident faces: a1 + lambda a2 and the rhs f, cof:113-146),
+// from which everything per-vertex follows: block Jacobi -> D^-1; SSOR -> S = D^-1/2, the scaled rhs S f and the
+// scaled diagonal block S D S.  Then every off-diagonal block is assembled and written ONCE, already scaled
+// (Ah_ij = S_i A_ij S_j needs the neighbour's S_j, complete after the first launch).  Round 1 wrote the unscaled
+// matrix and then read-modified-wrote all of it in a separate scaling kernel (2 x 32 nb bytes per frame more).
+__global__ void __launch_bounds__(256) assemble_diag_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t g = blockIdx.y;
+    const int64_t N = M.n_vertices, nb = M.n_blocks;
+    const double* It_l = B.It + mof_ix_sca(N, g, 0) + lane;
+    const double* dIt_l = B.dIt + mof_ix_sca(N, g, 0) + lane;
+    const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int64_t v = row0 + rr;
+        if (v >= N) break;
+        const int32_t bd = M.diag[v];
+        double a[4], f[2], mi[3];
+        mof_assemble_block_body<true>(M, v, bd, It_l, dIt_l, lambda_, a, f);
+        if (!ssor) {
+            mof_inv2_body(a, mi);                              // block Jacobi: D^-1
+        } else {
+            mof_inv_sqrt2_body(a, mi);                         // SSOR: S = D^-1/2
+            double o[4];
+            mof_scale_block_body(mi, mi, a, o);                // S D S (identity up to rounding; the SpMV reads it)
+            for (int c = 0; c < 4; ++c) a[c] = o[c];
+            const double f0 = f[0], f1 = f[1];
+            f[0] = mi[0] * f0 + mi[1] * f1;                    // bh = S b
+            f[1] = mi[1] * f0 + mi[2] * f1;
+        }
+        B.rhs[mof_ix_vec(N, g, v, 0) + lane] = f[0];
+        B.rhs[mof_ix_vec(N, g, v, 1) + lane] = f[1];
+        B.minv[mof_ix_minv(N, g, v, 0) + lane] = mi[0];
+        B.minv[mof_ix_minv(N, g, v, 1) + lane] = mi[1];
+        B.minv[mof_ix_minv(N, g, v, 2) + lane] = mi[2];
+        double* out = B.vals + mof_ix_val(nb, g, bd, 0) + lane;
+        out[0] = a[0];
+        out[MOF_W] = a[1];
+        out[2 * MOF_W] = a[2];
+        out[3 * MOF_W] = a[3];
+    }
+}
+
+__global__ void __launch_bounds__(256) assemble_offdiag_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = blockIdx.y;
     const int64_t N = M.n_vertices, nb = M.n_blocks;
@@ -61,55 +103,25 @@ __global__ void __launch_bounds__(256) assemble_kernel(mof_mesh_dev M, mof_batch
         const int64_t v = row0 + rr;
         if (v >= N) break;
         const int32_t bs = M.rowptr[v], be = M.rowptr[v + 1], bd = M.diag[v];
+        double si[3] = {0.0, 0.0, 0.0};
+        if (ssor)
+            for (int c = 0; c < 3; ++c) si[c] = B.minv[mof_ix_minv(N, g, v, c) + lane];
         for (int32_t b = bs; b < be; ++b) {
+            if (b == bd) continue;
             double a[4], f[2];
-            if (b == bd) {
-                mof_assemble_block_body<true>(M, v, b, It_l, dIt_l, lambda_, a, f);
-                double mi[3];
-                if (!ssor) mof_inv2_body(a, mi);               // block Jacobi: D^-1
-                else       mof_inv_sqrt2_body(a, mi);          // SSOR: S = D^-1/2 (scale_kernel applies it)
-                B.rhs[mof_ix_vec(N, g, v, 0) + lane] = f[0];
-                B.rhs[mof_ix_vec(N, g, v, 1) + lane] = f[1];
-                B.minv[mof_ix_minv(N, g, v, 0) + lane] = mi[0];
-                B.minv[mof_ix_minv(N, g, v, 1) + lane] = mi[1];
-                B.minv[mof_ix_minv(N, g, v, 2) + lane] = mi[2];
-            } else {
-                mof_assemble_block_body<false>(M, v, b, It_l, dIt_l, lambda_, a, f);
+            mof_assemble_block_body<false>(M, v, b, It_l, dIt_l, lambda_, a, f);
+            if (ssor) {
+                const int64_t j = M.col[b];
+                double sj[3], o[4];
+                for (int c = 0; c < 3; ++c) sj[c] = B.minv[mof_ix_minv(N, g, j, c) + lane];
+                mof_scale_block_body(si, sj, a, o);
+                for (int c = 0; c < 4; ++c) a[c] = o[c];
             }
             double* out = B.vals + mof_ix_val(nb, g, b, 0) + lane;
-            out[0] = a[0];
-            out[MOF_W] = a[1];
-            out[2 * MOF_W] = a[2];
-            out[3 * MOF_W] = a[3];
-        }
-    }
-}
-
-// SSOR path: symmetric diagonal scaling Ah = S A S, bh = S b with S = D^-1/2 (in B.minv), in place.
-// After it the diagonal blocks are the identity, so the sweeps and the vector kernel need no
-// per-vertex matrix data at all (3 x 24 N bytes less per iteration).
-__global__ void __launch_bounds__(256) scale_kernel(mof_mesh_dev M, mof_batch_dev B) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t g = blockIdx.y;
-    const int64_t N = M.n_vertices, nb = M.n_blocks;
-    const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-        const int64_t v = row0 + rr;
-        if (v >= N) break;
-        double si[3], f0, f1;
-        for (int c = 0; c < 3; ++c) si[c] = B.minv[mof_ix_minv(N, g, v, c) + lane];
-        f0 = B.rhs[mof_ix_vec(N, g, v, 0) + lane];
-        f1 = B.rhs[mof_ix_vec(N, g, v, 1) + lane];
-        B.rhs[mof_ix_vec(N, g, v, 0) + lane] = si[0] * f0 + si[1] * f1;
-        B.rhs[mof_ix_vec(N, g, v, 1) + lane] = si[1] * f0 + si[2] * f1;
-        for (int32_t b = M.rowptr[v]; b < M.rowptr[v + 1]; ++b) {
-            const int64_t j = M.col[b];
-            double sj[3], a[4], o[4];
-            for (int c = 0; c < 3; ++c) sj[c] = B.minv[mof_ix_minv(N, g, j, c) + lane];
-            double* ap = B.vals + mof_ix_val(nb, g, b, 0) + lane;
-            for (int c = 0; c < 4; ++c) a[c] = ap[c * MOF_W];
-            mof_scale_block_body(si, sj, a, o);
-            for (int c = 0; c < 4; ++c) ap[c * MOF_W] = o[c];
+            __stcs(out, a[0]);
+            __stcs(out + MOF_W, a[1]);
+            __stcs(out + 2 * MOF_W, a[2]);
+            __stcs(out + 3 * MOF_W, a[3]);
         }
     }
 }
@@ -137,11 +149,9 @@ extern "C" int mof_assemble_batch(const mof_mesh_dev* mesh, const mof_batch_dev*
     MOF_REQUIRE(omega >= 0.0 && omega < 2.0, "omega must be 0 (block Jacobi) or in (0,2) (SSOR)");
     MOF_REQUIRE(batch->It && batch->dIt && batch->vals && batch->rhs && batch->minv, "batch buffers missing");
     dim3 grid((unsigned)mof_num_tiles(mesh->n_vertices), batch->n_groups);
-    assemble_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch, lambda_, omega > 0.0);
-    MOF_LAUNCH_CHECK("assemble_kernel");
-    if (omega > 0.0) {
-        scale_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch);
-        MOF_LAUNCH_CHECK("scale_kernel");
-    }
+    assemble_diag_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch, lambda_, omega > 0.0);
+    MOF_LAUNCH_CHECK("assemble_diag_kernel");
+    assemble_offdiag_kernel<<<grid, 256, 0, mof_stream(stream)>>>(*mesh, *batch, lambda_, omega > 0.0);
+    MOF_LAUNCH_CHECK("assemble_offdiag_kernel");
     return 0;
 }

@@ -256,7 +256,7 @@ class VelocitySolver:
                    allow_positive=True)
         path = (ctypes.c_int32 * 4)()
         lib.mof_pcg_last_path(path)
-        self.aux_launches += 3 + (1 if self.ssor else 0)
+        self.aux_launches += 4                    # pack, assemble (diagonal blocks, off-diagonal blocks), unpack
         assert V_out.stride(1) == 1
         _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
         return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames], path=tuple(path))

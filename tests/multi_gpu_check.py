@@ -66,6 +66,17 @@ def main():
     # results that stay on the device
     out, _ = mdist.compute_velocity_field_sharded(a2, T - 1, t_k, 0.01, I, I, gather="all", to_host=False)
     assert torch.equal(out, h)
+    # config 5: S5 wave speed with the frames sharded over the GPUs (time-derivative halo, no data-path collective
+    # besides the gather of the result): bit-identical to the whole trial on one GPU, both derivative modes
+    from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5
+    surf = synthetic.SurfaceMesh(coords, tris, normals, areas)
+    phases = synthetic.wrapped_phase(coords, t_k, seed=5, omega=300.0)
+    for data, fn, phase in ((phases, s5.wave_velocity_phase, True), (I, s5.wave_velocity_amplitude, False)):
+        w_sharded = fn(surf, data, 1 / 512.0, T, e)
+        op5 = s5._operator(coords, tris, areas, np.asarray(e, dtype=np.float64).reshape(-1, 2, 3))
+        d = torch.from_numpy(np.ascontiguousarray(data)).to(f"cuda:{local}")
+        _, w_one = s5.wave_speed_device(op5, d, 0, T, 0, T, 1 / 512.0, phase)
+        assert np.array_equal(w_sharded, w_one.cpu().numpy(), equal_nan=True), "sharded wave speed differs"
     if rank == 0:
         a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
         for k in (0, 17, 35, 69):

@@ -68,3 +68,72 @@ def test_wave_speed_matches_oracle_medium():
     w = s5.wave_velocity_phase(surf, phases, 1 / SF, T, e)
     wo = mof_oracle.wave_velocity(coords, tris, areas, phases, 1 / SF, e, phase=True)
     assert rel_l2(w, wo) <= 1e-12
+
+
+def test_halo_rows_cover_the_time_derivative():
+    """Host logic of the frame sharding (CPU): the rows a shard is given contain every frame its time
+    derivative touches (central difference; one-sided second-order ends in amplitude mode, S5:24)."""
+    from manifold_based_optical_flow_method_b200.S5_compute_wave_v import halo_rows
+    from manifold_based_optical_flow_method_b200.distributed import shard_range
+    for T in (1, 2, 3, 5, 33, 100):
+        for world in (1, 2, 4, 8):
+            for phase in (True, False):
+                if not phase and T < 3:
+                    continue
+                for r in range(world):
+                    k0, k1 = shard_range(T, world, r)
+                    a, b = halo_rows(k0, k1, T, phase)
+                    assert 0 <= a <= k0 and k1 <= b <= T
+                    for t in range(k0, k1):
+                        need = {t}
+                        if phase:
+                            need |= {t + 1} if t == 0 and T > 1 else ({t - 1} if t == T - 1 and T > 1 else {t - 1, t + 1} if T > 1 else set())
+                        else:
+                            need |= {1, 2} if t == 0 else ({T - 2, T - 3} if t == T - 1 else {t - 1, t + 1})
+                        assert all(a <= q < b for q in need), (T, world, r, phase, t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("phase", [True, False])
+def test_wave_speed_shards_equal_whole_trial(phase):
+    """Config 5 shards frames over GPUs: a shard computed from its rows plus the halo must be bit-identical to
+    the same frames of the whole-trial call (ragged shard sizes, group boundaries at 32 frames)."""
+    import torch
+    from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5
+    from manifold_based_optical_flow_method_b200.distributed import shard_range
+    coords, tris, normals, areas = synthetic.pial_like(3)
+    T, SF = 70, 512.0
+    t_k = synthetic.time_axis(T, SF)
+    data = synthetic.wrapped_phase(coords, t_k, seed=2, omega=300.0) if phase else synthetic.travelling_wave(coords, t_k, seed=2)
+    e = mof_oracle.orthonormal_basis(normals)
+    op = s5._operator(coords, tris, areas, e)
+    d = torch.from_numpy(np.ascontiguousarray(data)).to(op.device)
+    _, whole = s5.wave_speed_device(op, d, 0, T, 0, T, 1 / SF, phase)
+    wo = mof_oracle.wave_velocity(coords, tris, areas, data, 1 / SF, e, phase=phase)
+    assert rel_l2(whole.cpu().numpy(), wo) <= 1e-12
+    for world in (2, 3, 8):
+        for r in range(world):
+            k0, k1 = shard_range(T, world, r)
+            a, b = s5.halo_rows(k0, k1, T, phase)
+            _, part = s5.wave_speed_device(op, d[a:b], a, T, k0 - a, k1 - k0, 1 / SF, phase)
+            assert torch.equal(part, whole[k0:k1]), (world, r)
+
+
+@pytest.mark.gpu
+def test_wave_speed_full_size_config5():
+    """BASELINE.json configs[4] size: 163,842 vertices.  The oracle (numpy, vectorised over frames) handles a
+    few frames at this size in seconds; gradient and wave speed must match it."""
+    import torch
+    from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5
+    coords, tris, normals, areas = synthetic.pial_like(7)
+    T, SF = 6, 512.0
+    t_k = synthetic.time_axis(T, SF)
+    phases = synthetic.wrapped_phase(coords, t_k, seed=1, omega=500.0)
+    e = mof_oracle.orthonormal_basis(normals)
+    op = s5._operator(coords, tris, areas, e)
+    d = torch.from_numpy(np.ascontiguousarray(phases)).to(op.device)
+    grad, wave = s5.wave_speed_device(op, d, 0, T, 0, T, 1 / SF, True, want_grad=True)
+    wo = mof_oracle.wave_velocity(coords, tris, areas, phases, 1 / SF, e, phase=True)
+    go = mof_oracle.grad_M_I(coords, tris, phases, areas)
+    assert rel_l2(grad.cpu().numpy(), go) <= 1e-13
+    assert rel_l2(wave.cpu().numpy(), wo) <= 1e-12
