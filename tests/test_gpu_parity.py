@@ -216,6 +216,36 @@ def test_singular_vertices_and_face_skip(mods):
     assert vmax == float(g["v_length_max"])
 
 
+def test_interior_zero_next_to_an_edge_matches_reference(mods):
+    """fsp:126-131 at the edge of its domain: fields whose zero lies at barycentric (0.3, delta, 0.7 - delta) of one
+    face, goldens from the unmodified reference (tests/golden/make_golden_edge.py).  The reference decides with an
+    SVD least squares and hard thresholds, this library with the closed-form solution of the same system: for
+    |delta| >= 1e-12 the reported faces must be identical; below that (rounding decides in both) the zero must be
+    reported in at least one of the two faces sharing the edge and nothing else may change."""
+    _, fsp = mods
+    g = load_golden("edge_zero_ico2")
+    coords, tris, eps = g["coordinates"], g["triangles"], float(g["eps"])
+    pair = {int(g["face"]), 32}                              # the face and its neighbour across the edge (see the generator's log)
+    off_v = off_f = 0
+    for k, delta in enumerate(g["deltas"]):
+        nv, nf = (int(x) for x in g["counts"][k])
+        ref_faces = [int(x) for x in g["sing_face_idx"][off_f:off_f + nf]]
+        ref_lm = g["sing_face_lam_mu"][off_f:off_f + nf]
+        off_v, off_f = off_v + nv, off_f + nf
+        sv, si, vmax = fsp.find_singularity_points(coords, tris, g["V_now"][k], eps)
+        faces = [int(r[0]) for r in si]
+        assert len(sv) == nv and vmax == float(g["v_length_max"][k])
+        if abs(delta) >= 1e-12:
+            assert faces == ref_faces, (delta, faces, ref_faces)
+            assert np.allclose([r[3][:2] for r in si], ref_lm, rtol=0, atol=1e-10)
+        else:
+            assert [f for f in faces if f not in pair] == [f for f in ref_faces if f not in pair]
+            assert pair & set(faces), (delta, faces)
+        for r in si:                                         # whatever is reported is a valid barycentric triple
+            lam, mu = r[3][0], r[3][1]
+            assert lam >= 0 and mu >= 0 and lam + mu <= 1
+
+
 # ---------------------------------------------------------------------------------
 # oracle on seeded inputs (sizes the oracle finishes in seconds)
 # ---------------------------------------------------------------------------------
@@ -627,3 +657,59 @@ def test_persistent_level_kernel_bit_identical_to_per_level_launches(level, fram
     assert np.array_equal(out["1"][1], out["0"][1])
     assert np.array_equal(out["1"][0], out["0"][0])
     assert np.array_equal(out["1"][2], out["0"][2])
+
+
+def test_config1_exactly_as_configured():
+    """BASELINE.json configs[0]: icosphere level 5 (10,242 vertices), 64-frame travelling wave -> 63 solves, every
+    one against the reference algorithm's direct solve (oracle: P1 assembly + SuperLU) and detection on EVERY
+    frame against the oracle's lstsq decisions (exact index lists)."""
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof, find_singularity_point as fsp
+    coords, tris, normals, areas = synthetic.icosphere(5)
+    T = 64
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=0)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    info = cof.last_solve_info
+    assert len(V_k) == T - 1 and info.converged and info.relres.max() <= RES_TOL
+    assert info.path[0] == _lib.PATH_LEVEL_PERSISTENT
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    worst = 0.0
+    for k in range(T - 1):
+        Vo = mof_oracle.worker(k, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[k], I[k + 1])
+        worst = max(worst, rel_l2(V_k[k], Vo))
+    assert worst <= V_TOL, worst
+    Vx = fsp.process_V_k(V_k, e)
+    assert np.array_equal(Vx, mof_oracle.process_V_k(V_k, e))
+    s = fsp.detect_singularities(Vx, coords, tris, 1e-4)
+    for k in range(T - 1):
+        vio, fio, lmo, Po, vmaxo = mof_oracle.find_singularity_points(coords, tris, Vx[k], 1e-4)
+        vi, fi, lm, P, idx = s.frame(k)
+        assert np.array_equal(vi, vio) and np.array_equal(fi, fio) and s.v_length_max[k] == vmaxo, k
+        assert np.allclose(lm, lmo, rtol=0, atol=1e-10)
+
+
+def test_full_batch_every_group_against_oracle_system():
+    """A full 1,024-frame batch at config 2 size (32 groups of 32 lanes in one launch of the persistent kernel): one
+    lane of EVERY group, a different lane in each, is checked against the ORACLE's independently assembled system
+    (true residual), so lanes beyond the first group are covered at size."""
+    import torch
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    coords, tris, normals, areas = synthetic.pial_like(7)
+    T = 1025
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=0)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    I_dev = torch.from_numpy(I).to(a2.device)
+    V_dev, info = cof.solve_on_device(a2, I_dev, I_dev, t_k, 0.01, 0, T - 1)
+    assert info.converged and info.relres.max() <= RES_TOL and info.path[0] == _lib.PATH_LEVEL_PERSISTENT
+    assert info.iterations.max() <= 160                      # 143 mean / 149 max at omega = 1.9
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    for g in range(32):
+        k = 32 * g + (5 * g + 3) % 32
+        a1, f = mof_oracle.assemble_frame(gwo, eo, into, tris, areas, t_k[k + 1] - t_k[k], I[k], I[k + 1])
+        A = mof_oracle.system_matrix(a1, a2o, 0.01)
+        Vk = V_dev[k].cpu().numpy()
+        assert np.linalg.norm(A @ Vk - f) / np.linalg.norm(f) <= 1e-11, (g, k)
+    del V_dev, I_dev
+    torch.cuda.empty_cache()
