@@ -668,8 +668,13 @@ def test_config1_exactly_as_configured():
     T = 64
     t_k = synthetic.time_axis(T, 512.0)
     I = synthetic.travelling_wave(coords, t_k, seed=0)
-    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
-    V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    old = cof.settings["precond"]
+    cof.settings["precond"] = DEFAULT_PRECOND                # whatever the module fixture left active
+    try:
+        a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+        V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    finally:
+        cof.settings["precond"] = old
     info = cof.last_solve_info
     assert len(V_k) == T - 1 and info.converged and info.relres.max() <= RES_TOL
     assert info.path[0] == _lib.PATH_LEVEL_PERSISTENT
@@ -699,9 +704,14 @@ def test_full_batch_every_group_against_oracle_system():
     T = 1025
     t_k = synthetic.time_axis(T, 512.0)
     I = synthetic.travelling_wave(coords, t_k, seed=0)
-    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
-    I_dev = torch.from_numpy(I).to(a2.device)
-    V_dev, info = cof.solve_on_device(a2, I_dev, I_dev, t_k, 0.01, 0, T - 1)
+    old = cof.settings["precond"]
+    cof.settings["precond"] = DEFAULT_PRECOND
+    try:
+        a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+        I_dev = torch.from_numpy(I).to(a2.device)
+        V_dev, info = cof.solve_on_device(a2, I_dev, I_dev, t_k, 0.01, 0, T - 1)
+    finally:
+        cof.settings["precond"] = old
     assert info.converged and info.relres.max() <= RES_TOL and info.path[0] == _lib.PATH_LEVEL_PERSISTENT
     assert info.iterations.max() <= 160                      # 143 mean / 149 max at omega = 1.9
     a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
