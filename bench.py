@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--tune-omega", action="store_true",
                     help="probe omega in {1.7, 1.8, 1.9} on the first 32 frames during setup (default for --config c4)")
     ap.add_argument("--check-every", type=int, default=None, help="iterations per convergence poll (= per launch of the persistent kernel)")
+    ap.add_argument("--max-iter", type=int, default=None, help="experiments only: cap the PCG iterations and accept unconverged frames")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-transport", default="auto", choices=["auto", "shm", "nccl"],
                     help="N > 1: how the fields reach rank 0's host memory (shared host array / NCCL gather + drain)")
@@ -298,6 +299,9 @@ def run_b200(args):
     I_host[:] = I_np
     del I_np
     cof.settings["tol"] = args.tol
+    if args.max_iter:
+        cof.settings["max_iter"] = args.max_iter
+        cof.settings["allow_unconverged"] = True
     cof.settings["batch_groups"] = args.batch_groups
     if args.streams:
         cof.settings["streams"] = args.streams

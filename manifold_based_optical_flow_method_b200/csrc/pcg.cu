@@ -802,6 +802,9 @@ constexpr int kStageBytes = 6144;                                     // per war
                                                                       // phases 3 x 2048 (three vectors x four rows / three
                                                                       // slots of eight rows of p'Ap shares)
 constexpr int kSlotBytes = 2048;
+constexpr int kStages = 2;                                            // stages per warp in the sweeps: two items in flight behind
+                                                                      // the one being computed (DRAM latency under load is
+                                                                      // longer than one item's dependent chain)
 static_assert(kStageValBytes + 3 * kStageVecBytes <= kStageBytes, "stage too small");
 constexpr int kPersistMaxGroups = 1024;                               // active-group list kept in shared memory (uint16)
 constexpr int kDescInts = 8;                                          // per row and direction: bs, cnt, col[0..5]
@@ -886,7 +889,7 @@ struct LevelArgs {
 //   DIR 1 MODE 0: w = (Dt+L)^-1 (p - ((2-omega)/omega) t) ; dots[row] = p.(t + w)          (vin = B.p, vout = B.ap)
 //   DIR 1 MODE 1: vout = (Dt+L)^-1 vin
 // act == nullptr: all groups (A = n_groups).
-template <int DIR, int MODE, bool PROBE = false>
+template <int DIR, int MODE, int PROBE = 0>     // PROBE (development): 1 cycle counters, 2 no waiting (WRONG results; bandwidth bound of the schedule)
 __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const double* vin, double* vout, double* dots,
                                                   const uint16_t* act, int A, int32_t stamp, unsigned char* stage,
                                                   uint32_t bar, uint32_t& parity, uint64_t policy) {
@@ -905,9 +908,7 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
     const mof_batch_dev& B = a.B;
     const double omega = a.omega;
     constexpr int nvec = (DIR == 0) ? (MODE == 0 ? 3 : 2) : (MODE == 0 ? 2 : 1);
-    const uint32_t stage_s = smem_u32(stage);
-    const double* sv = reinterpret_cast<const double*>(stage) + lane;
-    const double* sx = reinterpret_cast<const double*>(stage + kStageValBytes) + lane;
+    const uint32_t stage_s0 = smem_u32(stage);
 
     // item J -> (row, group); row >= N: padding of the last block (skipped)
     auto item = [&](uint32_t j, uint32_t& irow, uint32_t& ig) {
@@ -916,49 +917,63 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
         irow = DIR ? q : nblk * kRowBlock - 1 - q;
         ig = act ? act[ia] : ia;
     };
-    // first real item of this warp
-    uint32_t row, g, gprev = 0xffffffffu;
-    for (;;) {
-        item(J, row, g);
-        if (row < N) break;
-        J += W;
-        if (J >= total) return;
-    }
-    auto issue = [&](uint32_t irow, uint32_t ig, int32_t d) {
+    // next real item at or after j (j >= total: none)
+    auto next_item = [&](uint32_t j, uint32_t& irow, uint32_t& ig) {
+        while (j < total) {
+            item(j, irow, ig);
+            if (irow < N) break;
+            j += W;
+        }
+        return j;
+    };
+    auto issue = [&](int slot, uint32_t irow, uint32_t ig, int32_t d) {
         const int32_t bs = __shfl_sync(kFull, d, 0), cnt = __shfl_sync(kFull, d, 1);
         if (lane == 0) {
+            const uint32_t stage_s = stage_s0 + slot * kStageBytes, b = bar + 8u * slot;
             const int nstage = cnt < kStageBlocks ? cnt : kStageBlocks;
             const size_t vo = ((size_t)ig * N + irow) * 2 * MOF_W;
-            mbar_expect_tx(bar, (uint32_t)(nstage * 4 * MOF_W * 8 + nvec * kStageVecBytes));
+            mbar_expect_tx(b, (uint32_t)(nstage * 4 * MOF_W * 8 + nvec * kStageVecBytes));
             if (nstage > 0)
-                bulk_g2s(stage_s, B.vals + ((size_t)ig * a.nb + bs) * 4 * MOF_W, (uint32_t)(nstage * 4 * MOF_W * 8), bar, policy);
+                bulk_g2s(stage_s, B.vals + ((size_t)ig * a.nb + bs) * 4 * MOF_W, (uint32_t)(nstage * 4 * MOF_W * 8), b, policy);
             if (DIR == 0) {
-                bulk_g2s(stage_s + kStageValBytes, B.p + vo, kStageVecBytes, bar, policy);
-                bulk_g2s(stage_s + kStageValBytes + kStageVecBytes, B.x + vo, kStageVecBytes, bar, policy);
-                if (MODE == 0) bulk_g2s(stage_s + kStageValBytes + 2 * kStageVecBytes, B.r + vo, kStageVecBytes, bar, policy);
+                bulk_g2s(stage_s + kStageValBytes, B.p + vo, kStageVecBytes, b, policy);
+                bulk_g2s(stage_s + kStageValBytes + kStageVecBytes, B.x + vo, kStageVecBytes, b, policy);
+                if (MODE == 0) bulk_g2s(stage_s + kStageValBytes + 2 * kStageVecBytes, B.r + vo, kStageVecBytes, b, policy);
             } else {
-                bulk_g2s(stage_s + kStageValBytes, vin + vo, kStageVecBytes, bar, policy);
-                if (MODE == 0) bulk_g2s(stage_s + kStageValBytes + kStageVecBytes, B.t + vo, kStageVecBytes, bar, policy);
+                bulk_g2s(stage_s + kStageValBytes, vin + vo, kStageVecBytes, b, policy);
+                if (MODE == 0) bulk_g2s(stage_s + kStageValBytes + kStageVecBytes, B.t + vo, kStageVecBytes, b, policy);
             }
         }
     };
+    // the warp's first kStages items go into flight; `cd` / `nd` are the descriptors of the current and the next item
+    uint32_t row = 0, g = 0, gprev = 0xffffffffu, rown = 0, gn = 0;
+    J = next_item(J, row, g);
+    if (J >= total) return;
     int32_t cd = __ldg(desc + (size_t)row * kDescInts + (lane & 7)), nd = 0;
-    issue(row, g, cd);
+    issue(0, row, g, cd);
+    uint32_t Jn = next_item(J + W, rown, gn);
+    if (Jn < total) {
+        nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
+        if (kStages > 1) issue(1, rown, gn, nd);
+    }
+    int slot = 0;
     // per-frame scalars of the item's group: re-read only when the group changes (with W a multiple of A, never)
     double s_alpha = 0.0, s_beta = 0.0, s_zsw = 0.0;
     int par = 0;
-    long long probe_prev = PROBE ? clock64() : 0, pacc[5] = {0, 0, 0, 0, 0};
+    long long probe_prev = PROBE == 1 ? clock64() : 0, pacc[5] = {0, 0, 0, 0, 0};
 
     for (;;) {
-        uint32_t Jn = J + W, rown = 0, gn = 0;
-        bool more = Jn < total;
-        while (more) {                                   // skip the padding rows of the last block
-            item(Jn, rown, gn);
-            if (rown < N) break;
-            Jn += W;
-            more = Jn < total;
+        const bool more = Jn < total;
+        // the item after the next: its descriptor is fetched now, its data requested when this item's stage is free
+        uint32_t rowf = 0, gf = 0, Jf = total;
+        int32_t fd = 0;
+        if (kStages > 1 && more) {
+            Jf = next_item(Jn + W, rowf, gf);
+            if (Jf < total) fd = __ldg(desc + (size_t)rowf * kDescInts + (lane & 7));
         }
-        if (more) nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
+        const uint32_t bslot = bar + 8u * slot;
+        const double* sv = reinterpret_cast<const double*>(stage + slot * kStageBytes) + lane;
+        const double* sx = reinterpret_cast<const double*>(stage + slot * kStageBytes + kStageValBytes) + lane;
         if (g != gprev) {                                // these loads overlap the gather below
             const int iters = __ldcg(state_ptr(B.state, g, MOF_I_ITERS) + lane);
             par = (MODE == 0 ? iters : iters + 1) & 1;
@@ -974,7 +989,7 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
         const int32_t bs = __shfl_sync(kFull, cd, 0), cnt = __shfl_sync(kFull, cd, 1);
         double* v_l = vout + ((size_t)g * N) * 2 * MOF_W + lane;          // the sweep's own output, gathered from finished rows
         long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
-        if (PROBE) tk0 = clock64();
+        if (PROBE == 1) tk0 = clock64();
         // MODE 0: the gathered entries carry their own validity bit (with_parity); MODE 1: ready stamps
         if (MODE == 1) {
             int32_t mycol = __shfl_sync(kFull, cd, 2 + (lane < kDescCols ? lane : 0));
@@ -1005,13 +1020,13 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
 #pragma unroll
                 for (int k = 0; k < kStageBlocks; ++k)
                     if (k < cnt) ok = ok && has_parity(gv[k][0], par) && has_parity(gv[k][1], par);
-                if (__all_sync(kFull, ok)) break;
+                if (PROBE == 2 || __all_sync(kFull, ok)) break;
             }
         }
-        if (PROBE) tk1 = clock64();
-        mbar_wait(bar, parity & 1u);
-        parity ^= 1u;
-        if (PROBE) tk2 = clock64();
+        if (PROBE == 1) tk1 = clock64();
+        mbar_wait(bslot, (parity >> slot) & 1u);
+        parity ^= 1u << slot;
+        if (PROBE == 1) tk2 = clock64();
         v_l += (size_t)row * 2 * MOF_W;                                   // -> this row's entry of the output
         double a0, a1, q0 = 0.0, q1 = 0.0;                                // q: what the row's share of p'Ap needs (forward, MODE 0)
         if (DIR == 0) {
@@ -1079,10 +1094,14 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             __syncwarp();
             if (lane == 0) st_relaxed(B.ready + (size_t)g * N + row, stamp);
         }
-        if (PROBE) tk3 = clock64();
-        if (more) issue(rown, gn, nd);                                   // the next item's static data
+        if (PROBE == 1) tk3 = clock64();
+        if (kStages > 1) {                                               // this stage is free: request the item after the next
+            if (Jf < total) issue(slot, rowf, gf, fd);
+        } else if (more) {
+            issue(0, rown, gn, nd);
+        }
         if (DIR == 1 && MODE == 0) __stcs(dots + ((size_t)g * N + row) * MOF_W + lane, q0);
-        if (PROBE) {
+        if (PROBE == 1) {
             pacc[0] += tk1 - tk0;                  // poll + gather
             pacc[1] += tk2 - tk1;                  // stage wait
             pacc[2] += tk3 - tk2;                  // arithmetic + result stores
@@ -1093,8 +1112,15 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
         }
         if (!more) break;
         J = Jn; row = rown; g = gn; cd = nd;
+        if (kStages > 1) {
+            Jn = Jf; rown = rowf; gn = gf; nd = fd;
+            slot ^= 1;
+        } else {
+            Jn = next_item(J + W, rown, gn);
+            if (Jn < total) nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
+        }
     }
-    if (PROBE && lane == 0)
+    if (PROBE == 1 && lane == 0)
         for (int k = 0; k < 5; ++k) atomicAdd(a.probe + DIR * 8 + k, (unsigned long long)pacc[k]);
 }
 
@@ -1283,7 +1309,7 @@ __device__ __forceinline__ void phase_barrier(cooperative_groups::grid_group& gr
 
 // n_iter PCG iterations (or fewer if every group converges earlier).  stamp0: value of the last stamp used
 // in B.ready; the sweeps of iteration i use stamp0 + 2 i + 1 and stamp0 + 2 i + 2.
-template <int MINB, bool PROBE>   // MINB: CTAs per SM the register budget is cut for (4: 64 registers, 3: 80)
+template <int MINB, int PROBE>   // MINB: CTAs per SM the register budget is cut for (4: 64 registers, 3: 80, 2: 128)
 __global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int n_iter, int32_t stamp0, int timing) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ PersistShared S;
@@ -1292,7 +1318,7 @@ __global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int 
     const mof_batch_dev& B = a.B;
     const int G = B.n_groups;
     persist_setup(S);
-    unsigned char* stage = dyn_smem + (size_t)warp * kStageBytes;
+    unsigned char* stage = dyn_smem + (size_t)warp * kStages * kStageBytes;
     const uint32_t bar = smem_u32(&S.bar[warp][0]);
     uint32_t parity = 0;                   // bit s: phase parity of this warp's mbarrier s (bit 0 is shared by all phases)
     const uint64_t policy = policy_evict_first();
@@ -1339,7 +1365,7 @@ __global__ void __launch_bounds__(256, 4) level_sweep_kernel(LevelArgs a, const 
     const int warp = threadIdx.x >> 5;
     persist_setup(S);
     uint32_t parity = 0;
-    level_sweep_phase<DIR, 1>(a, vin, vout, nullptr, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * kStageBytes,
+    level_sweep_phase<DIR, 1>(a, vin, vout, nullptr, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * kStages * kStageBytes,
                               smem_u32(&S.bar[warp][0]), parity, policy_evict_first());
 }
 
@@ -1641,7 +1667,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     g_last_path[3] = persist ? 0 : (!levels ? 0 : !mesh->level_desc ? 1 : !B.ready ? 2 : G > kPersistMaxGroups ? 3 : 4);
     int grid_iter = 0, grid_sweep = 0;
     const void* iter_fn = nullptr;
-    const size_t persist_smem = (size_t)kWarps * kStageBytes;
+    const size_t persist_smem = (size_t)kWarps * kStages * kStageBytes;
     LevelArgs largs{mesh->level_desc, mesh->col, B, N, nb, ntiles, omega, inv_omega, nullptr};
     unsigned long long* probe_buf = nullptr;
     struct ProbeGuard {
@@ -1657,9 +1683,13 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         const char* minb_env = getenv("MOF_LEVEL_MINB");             // tuning knob: register budget variant
         const char* probe_env = getenv("MOF_LEVEL_PROBE");           // development probe: per-item cycle breakdown on stderr
         const bool probe = probe_env && probe_env[0] == '1';
-        const bool minb3 = !(minb_env && minb_env[0] == '4');      // default: 3 CTAs per SM, 80 registers, no spills
-        iter_fn = probe ? (minb3 ? (const void*)level_iter_kernel<3, true> : (const void*)level_iter_kernel<4, true>)
-                        : (minb3 ? (const void*)level_iter_kernel<3, false> : (const void*)level_iter_kernel<4, false>);
+        const bool nowait = probe_env && probe_env[0] == '2';         // timing experiment only: the sweeps do not wait, results are wrong
+        const bool minb3 = minb_env && minb_env[0] == '3';
+        const bool minb4 = minb_env && minb_env[0] == '4';          // default: 2 CTAs per SM (two 6 KB stages per warp), <= 128 registers
+        iter_fn = nowait ? (const void*)level_iter_kernel<2, 2>
+                : probe ? (const void*)level_iter_kernel<2, 1>
+                : minb3 ? (const void*)level_iter_kernel<3, 0>
+                : minb4 ? (const void*)level_iter_kernel<4, 0> : (const void*)level_iter_kernel<2, 0>;
         if (probe) {
             const size_t pb = (16 + 2 * (size_t)N) * sizeof(unsigned long long);
             MOF_CUDA_TRY(cudaMalloc(&probe_buf, pb));
