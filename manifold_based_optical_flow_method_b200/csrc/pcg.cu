@@ -1222,35 +1222,45 @@ __device__ __noinline__ void level_update_phase(const LevelArgs& a, const uint16
         const int64_t n = N - row0;
         return (int)(n < 0 ? 0 : (n > kPiece ? kPiece : n));
     };
-    auto issue = [&](int64_t q, int h) {
+    // pieces of this CTA's items in order: piece i = half (i & 1) of the (i >> 1)-th item; piece i lives in stage
+    // i % kStages and piece i + kStages is requested as soon as piece i has been read
+    const int64_t q0 = blockIdx.x, gd = gridDim.x;
+    const int64_t n_items = q0 < items ? (items - q0 + gd - 1) / gd : 0;
+    const int64_t n_pieces = 2 * n_items;
+    auto issue_piece = [&](int64_t i) {
+        const int64_t q = q0 + (i >> 1) * gd;
+        const int h = (int)(i & 1), slot = (int)(i % kStages);
         const int n = rows_of(q, h);
         if (lane == 0 && n > 0) {
             const int64_t row0 = (q / A) * MOF_TILE_ROWS + warp * kRowsPerWarp + h * kPiece;
             const size_t off = ((size_t)act[q % A] * N + row0) * 2 * MOF_W;
             const uint32_t bytes = (uint32_t)(n * 2 * MOF_W * 8);
-            mbar_expect_tx(bar, 3 * bytes);
-            bulk_g2s(stage_s, B.ap + off, bytes, bar, policy);
-            bulk_g2s(stage_s + kSlotBytes, B.t + off, bytes, bar, policy);
-            bulk_g2s(stage_s + 2 * kSlotBytes, B.r + off, bytes, bar, policy);
+            const uint32_t b = bar + 8u * slot, dst = stage_s + slot * kStageBytes;
+            mbar_expect_tx(b, 3 * bytes);
+            bulk_g2s(dst, B.ap + off, bytes, b, policy);
+            bulk_g2s(dst + kSlotBytes, B.t + off, bytes, b, policy);
+            bulk_g2s(dst + 2 * kSlotBytes, B.r + off, bytes, b, policy);
         }
     };
-    const double* sw = reinterpret_cast<const double*>(stage) + lane;
-    const double* st = reinterpret_cast<const double*>(stage + kSlotBytes) + lane;
-    const double* sr = reinterpret_cast<const double*>(stage + 2 * kSlotBytes) + lane;
-    int64_t q = blockIdx.x;
-    if (q < items) issue(q, 0);
-    for (; q < items; q += gridDim.x) {
+    for (int64_t i = 0; i < kStages && i < n_pieces; ++i) issue_piece(i);
+    for (int64_t it = 0; it < n_items; ++it) {
+        const int64_t q = q0 + it * gd;
         const int tile = (int)(q / A);
         const int64_t g = act[q % A];
         const double alpha = __ldcg(scal_ptr(B.scal, g, MOF_S_ALPHA) + lane);
         double rr = 0.0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            const int64_t i = 2 * it + h;
+            const int slot = (int)(i % kStages);
             const int n = rows_of(q, h);
+            const double* sw = reinterpret_cast<const double*>(stage + slot * kStageBytes) + lane;
+            const double* st = sw + kSlotBytes / 8;
+            const double* sr = sw + 2 * kSlotBytes / 8;
             double rn[kPiece][2];
             if (n > 0) {
-                mbar_wait(bar, parity & 1u);
-                parity ^= 1u;
+                mbar_wait(bar + 8u * slot, (parity >> slot) & 1u);
+                parity ^= 1u << slot;
 #pragma unroll
                 for (int j = 0; j < kPiece; ++j)
                     if (j < n) {
@@ -1260,8 +1270,7 @@ __device__ __noinline__ void level_update_phase(const LevelArgs& a, const uint16
                     }
             }
             __syncwarp();                                                 // the stage has been read
-            if (h == 0) issue(q, 1);
-            else if (q + gridDim.x < items) issue(q + gridDim.x, 0);
+            if (i + kStages < n_pieces) issue_piece(i + kStages);
             if (n > 0) {
                 double* r_l = B.r + ((size_t)g * N + (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp + h * kPiece) * 2 * MOF_W + lane;
 #pragma unroll
