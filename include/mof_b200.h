@@ -217,11 +217,13 @@ int mof_spmv_batch(const mof_mesh_dev* mesh, const mof_batch_dev* batch, const d
  * max_restarts restarts from the true residual).
  * omega = 0: block-Jacobi PCG (SpMV + two vector kernels per iteration).
  * omega in (0,2): SSOR PCG in Eisenstat's form (needs batch->minv assembled with the same omega): per
- * iteration one backward and one forward block-triangular sweep plus one vector kernel.  With a mesh
- * built with reorder = 3 (mesh->n_levels > 0) the sweeps run level by level, one warp per row, and an
- * iteration is replayed as a CUDA graph (environment MOF_LEVEL_GRAPH=0: plain launches); with
- * reorder = 2 (mesh->n_colors > 0) they run colour by colour, one warp per patch.  ~3x (multicolour) to
- * ~8x (level-scheduled) fewer iterations than block Jacobi at the same bytes per iteration.  Synchronous: returns after the
+ * iteration one backward and one forward block-triangular sweep plus one vector pass.  With a mesh
+ * built with reorder = 3 (mesh->n_levels > 0), mesh->level_desc and batch->ready set, ONE persistent cooperative
+ * kernel runs check_every whole iterations per launch (row-level dataflow inside the sweeps, bulk-async prefetch;
+ * environment MOF_LEVEL_PERSIST=0, a missing descriptor / stamp buffer or a device without cooperative launch:
+ * one launch per dependency level, replayed as a CUDA graph -- same bits); with reorder = 2 (mesh->n_colors > 0)
+ * the sweeps run colour by colour, one warp per patch.  ~3x (multicolour) to ~8x (level-scheduled) fewer
+ * iterations than block Jacobi at the same bytes per iteration.  Synchronous: returns after the
  * stream has drained.  Host outputs (each MOF_GROUP*n_groups long, may be NULL):
  * iters, relres (true residual), status (MOF_STATUS_*).  Return value: 0 if every
  * valid frame converged (or had a zero rhs), else the largest status met. */
