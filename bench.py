@@ -269,11 +269,14 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa_node = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from manifold_based_optical_flow_method_b200 import _lib
     from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
     from manifold_based_optical_flow_method_b200 import distributed as mdist
+    if world > 1:
+        numa_node = mdist.bind_to_gpu_numa_node(local)      # before the pinned input buffer is allocated
 
     def barrier():
         if world > 1:
@@ -633,7 +636,7 @@ def run_b200(args):
                        "distributed.solve_shard_and_gather(numpy shard in; every rank drains its own fields over its own PCIe link "
                        "into its rows of a pooled, CUDA-registered shared host array that rank 0 returns as numpy; no data-path "
                        "collective)"),
-               "transport": None if world == 1 else transport_used}
+               "transport": None if world == 1 else transport_used, "numa_node_of_rank0": numa_node}
 
     if rank == 0:
         line = {

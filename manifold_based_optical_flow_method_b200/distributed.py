@@ -40,6 +40,42 @@ def rank():
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+_numa_bound = {}
+
+
+def bind_to_gpu_numa_node(device_index=None):
+    """Pin this process (its threads and, through first touch, the host buffers it allocates afterwards) to the
+    CPUs of the NUMA node its GPU hangs off, so that a rank's H2D / D2H traffic does not cross the socket
+    interconnect.  torchrun does not place ranks; with 8 ranks moving 31 GB per step through the host it matters.
+    Best effort: returns the node id, or None when the topology cannot be read (then nothing changes)."""
+    try:
+        import torch
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        if device_index in _numa_bound:
+            return _numa_bound[device_index]
+        props = torch.cuda.get_device_properties(device_index)
+        addr = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            raise OSError("no NUMA information")
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            raise OSError("node has no allowed CPU")
+        os.sched_setaffinity(0, allowed)
+        _numa_bound[device_index] = node
+        return node
+    except Exception:
+        _numa_bound[device_index] = None
+        return None
+
+
 def shard_range(n_frames, world, r):
     """Contiguous split: rank r gets frames [k0, k1); sizes differ by at most one and the
     first ``n_frames % world`` ranks take the extra frame."""
@@ -241,6 +277,8 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
     width = 2 * N
     if transport not in ("auto", "shm", "nccl"):
         raise ValueError("transport must be 'auto', 'shm' or 'nccl'")
+    if to_host and world > 1:
+        bind_to_gpu_numa_node(op.device.index)
     if to_host and world > 1 and gather in ("all", "root") and transport in ("shm", "auto"):
         if _result_pool.same_host():
             return _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, counts, gather, r, n_loc, width)
