@@ -395,13 +395,12 @@ def run_b200(args):
         # algorithmic bytes are (frame-iterations it performed) x bytes per frame-iteration.  The inputs are the
         # same every step, so the frame-iterations of the region are steps x sum(info.iterations).
         per_frame = {"sweep_back": 16.0 * (nb - N) + 96.0 * N,           # U blocks; read r, p, x; write p, t, x
-                     "sweep_fwd": 16.0 * (nb - N) + 48.0 * N + 8.0 * N,  # L blocks; read p, t; write w and the row's share of p'Ap
-                     "dot": 8.0 * N,                                     # read the shares back (fixed-order reduction)
+                     "sweep_fwd": 16.0 * (nb - N) + 48.0 * N,            # L blocks; read p, t; write w (p'Ap: exact fixed-point accumulators, no buffer)
                      "update": 64.0 * N}                                 # read w, t, r; write r
-        shared_per_group_iter = 2 * (32.0 * N + 4.0 * N)                 # row descriptors + ready stamps, both sweeps
+        shared_per_group_iter = 2 * 32.0 * N                             # row descriptors, both sweeps
         frame_iters = float(np.sum(info.iterations)) * args.steps
         group_iters = float(sum(int(np.max(info.iterations[g0:g0 + 32])) for g0 in range(0, n, 32))) * args.steps
-        dom_name = ("level_iter_kernel (persistent cooperative kernel: backward + forward level-scheduled SSOR sweeps, p'Ap, "
+        dom_name = ("level_iter_kernel (persistent cooperative kernel: backward + forward level-scheduled SSOR sweeps, alpha, "
                     f"r update; {op.pattern.n_levels} dependency levels per sweep, row-level dataflow)")
         dom_bytes = frame_iters * sum(per_frame.values()) + group_iters * shared_per_group_iter
         dom_ms = prof.ms_iter
@@ -409,10 +408,10 @@ def run_b200(args):
         ph = [float(x) * 1e-6 for x in prof.phase_ns]                     # ms, whole timed region
         phase_bytes = [frame_iters * per_frame["sweep_back"] + group_iters * shared_per_group_iter / 2,
                        frame_iters * per_frame["sweep_fwd"] + group_iters * shared_per_group_iter / 2,
-                       frame_iters * per_frame["dot"], frame_iters * per_frame["update"]]
-        others = {name: {"achieved": gbs(b, t), "ms_total": t, "time_share": t / max(sum(ph), 1e-9)}
-                  for name, b, t in zip(("phase backward sweep", "phase forward sweep", "phase p'Ap reduction", "phase r update"),
-                                        phase_bytes, ph)}
+                       0.0, frame_iters * per_frame["update"]]
+        others = {name: {"achieved": gbs(b, t) if b else None, "ms_total": t, "time_share": t / max(sum(ph), 1e-9)}
+                  for name, b, t in zip(("phase backward sweep", "phase forward sweep", "phase alpha (p'Ap accumulators -> alpha, grid barrier)",
+                                         "phase r update"), phase_bytes, ph)}
         ms_iter = prof.ms_iter
         try:
             with open(os.path.join(ROOT, "profiles", "level_traffic.json")) as fh:

@@ -39,7 +39,11 @@ static inline unsigned mof_cdiv(int64_t a, int64_t b) { return (unsigned)((a + b
 //   THR per-frame threshold on RR/BB, BETA_SAVED beta of a frozen frame for an exact resume
 enum { MOF_S_RZ = 0, MOF_S_PAP = 1, MOF_S_RR = 2, MOF_S_BB = 3, MOF_S_ALPHA = 4, MOF_S_BETA = 5,
        MOF_S_RRTRUE = 6, MOF_S_BBT = 7, MOF_S_THR = 8, MOF_S_ZS = 9, MOF_S_BETA_SAVED = 10, MOF_S_SPARE = 11,
-       MOF_S_COUNT = 12 };
+       // level path: exact fixed-point accumulator of p'Ap (128-bit two's complement in two 64-bit words), its
+       // binary scale (int64) and an overflow / non-finite flag (int64); the slots hold bit patterns, not doubles
+       MOF_S_FX_LO = 12, MOF_S_FX_HI = 13, MOF_S_FX_K = 14, MOF_S_FX_BAD = 15,
+       MOF_S_COUNT = 16 };
+static_assert(MOF_S_COUNT == MOF_SCAL_SLOTS, "scalar slots of the header and the kernels differ");
 // state[g][MOF_I_*][32], then group_done[G], ticket[G], groups_active[1]
 enum { MOF_I_ACTIVE = 0, MOF_I_ITERS = 1, MOF_I_STATUS = 2, MOF_I_SPARE = 3, MOF_I_COUNT = 4 };
 #define MOF_STATUS_PENDING (-1)

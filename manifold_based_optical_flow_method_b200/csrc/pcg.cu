@@ -30,9 +30,11 @@
 //   HBM bytes per frame-iteration: sweeps 2 x 16 (nb-N) + 144 N, update 64 N  (65.5 MB at ico7),
 //   ~3.1x fewer iterations than block Jacobi.
 // The same SSOR on the level-scheduled natural ordering (mesh built with reorder = 3; the default of
-// the Python layer): level_back_kernel<0> / level_fwd_kernel<0> per dependency level, one warp per row,
-// level_dot_kernel, update_kernel<true>; ~2.6x fewer iterations again (143 vs 372 at ico7), ~2050 small
-// launches per iteration replayed as a CUDA graph.
+// the Python layer), ~2.6x fewer iterations again (143 vs 372 at ico7): ONE persistent cooperative kernel
+// (level_iter_kernel) runs check_every whole iterations per launch -- row-level dataflow inside the sweeps,
+// bulk-async prefetch, p'Ap accumulated exactly in fixed point, the r update as a further phase; fallback
+// (bit-identical): level_back_kernel<0> / level_fwd_kernel<0> per dependency level, one warp per row,
+// level_alpha_kernel, update_kernel<true>, ~2050 small launches per iteration replayed as a CUDA graph.
 // A frame that meets its threshold is frozen with (alpha, beta, zs) = (0, 1, 0) and can resume
 // exactly; a group whose frames are all frozen makes its CTAs return at once.
 #include <cooperative_groups.h>
@@ -294,7 +296,7 @@ template <bool SSOR>
 __device__ __forceinline__ void update_finish(const mof_batch_dev& B, int ntiles, double inv_omega, int tile, int64_t g,
                                               double rz, double rr) {
     const int G = B.n_groups;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
     if (SSOR) rz = rr * inv_omega;                     // r'z with z = r / omega (linear, so per-lane partials add up)
     double val[2] = {rz, rr}, tot[2];
     if (!tile_reduce<2>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot))
@@ -410,6 +412,66 @@ __device__ __forceinline__ double ld_strong(const double* p) {
 }
 __device__ __forceinline__ void st_strong(double* p, double v) {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// Exact, order-free accumulation of p'Ap on the level path.  A row's share p_i.(t_i + w_i) is converted to a
+// 128-bit fixed-point integer (value x 2^k, floor) and integers are added -- associative, so warps may add the
+// shares of whatever rows they happen to own, in any order, and flush into one accumulator per frame with two
+// 64-bit atomics: the sum is independent of grid size, batch composition and GPU, like the fixed-order tile
+// reduction it replaces, but needs no per-row buffer (16 N bytes per frame-iteration less), no read-back pass
+// and no barrier of its own.  k = 90 - exponent(previous p'Ap, or r'z before the first iteration): shares up to
+// 2^37 times the reference fit, resolution 2^-90 of it (a double carries 2^-53).  A share that is not finite or
+// does not fit sets the frame's flag and the frame ends as a breakdown.
+struct Fx128 {
+    unsigned long long lo;
+    long long hi;
+};
+__device__ __forceinline__ bool fx_from_double(double v, int k, Fx128& out) {
+    const double t = scalbn(v, k - 64);                  // integer part = bits 64..127 of v 2^k
+    if (!(fabs(t) < 9.0e18)) { out.lo = 0; out.hi = 0; return false; }
+    const double fl = floor(t);
+    out.hi = (long long)fl;
+    out.lo = __double2ull_rz(scalbn(t - fl, 64));        // t - fl in [0, 1): exact, below 2^64
+    return true;
+}
+__device__ __forceinline__ void fx_add(Fx128& acc, const Fx128& x) {
+    acc.lo += x.lo;
+    acc.hi += x.hi + (acc.lo < x.lo ? 1 : 0);
+}
+__device__ __forceinline__ double fx_to_double(unsigned long long lo, long long hi, int k) {
+    const bool neg = hi < 0;
+    if (neg) { lo = ~lo + 1ull; hi = ~hi + (lo == 0ull ? 1 : 0); }
+    const double d = scalbn((double)(unsigned long long)hi, 64) + (double)lo;
+    return scalbn(neg ? -d : d, -k);
+}
+__device__ __forceinline__ unsigned long long* fx_word(double* scal, int64_t g, int which) {
+    return reinterpret_cast<unsigned long long*>(scal_ptr(scal, g, which));
+}
+// add a warp's partial sum (per lane) into the frame accumulators of group g
+__device__ __forceinline__ void fx_flush(double* scal, int64_t g, int lane, Fx128& acc, bool& bad) {
+    if (acc.lo | (unsigned long long)acc.hi) {
+        const unsigned long long old = atomicAdd(fx_word(scal, g, MOF_S_FX_LO) + lane, acc.lo);
+        const unsigned long long carry = (old + acc.lo) < acc.lo ? 1ull : 0ull;
+        atomicAdd(fx_word(scal, g, MOF_S_FX_HI) + lane, (unsigned long long)acc.hi + carry);
+    }
+    if (bad) atomicOr(fx_word(scal, g, MOF_S_FX_BAD) + lane, 1ull);
+    acc.lo = 0; acc.hi = 0; bad = false;
+}
+__device__ __forceinline__ int fx_scale_for(double ref) {          // k for the NEXT accumulation given a positive reference
+    return (ref > 0.0 && isfinite(ref)) ? 90 - ilogb(ref) : 0;
+}
+// p'Ap of group g from the accumulators -> alpha; accumulators cleared, scale set for the next iteration (warp 0 of one CTA)
+__device__ __forceinline__ void fx_finalize_alpha(double* scal, int32_t* state, int64_t g, int G, int lane) {
+    unsigned long long* lo = fx_word(scal, g, MOF_S_FX_LO) + lane;
+    unsigned long long* hi = fx_word(scal, g, MOF_S_FX_HI) + lane;
+    unsigned long long* kk = fx_word(scal, g, MOF_S_FX_K) + lane;
+    unsigned long long* bad = fx_word(scal, g, MOF_S_FX_BAD) + lane;
+    const int k = (int)(long long)__ldcg(kk);
+    double pap = fx_to_double(__ldcg(lo), (long long)__ldcg(hi), k);
+    if (__ldcg(bad)) pap = nan("");
+    *lo = 0ull; *hi = 0ull; *bad = 0ull;
+    if (pap > 0.0 && isfinite(pap)) *kk = (unsigned long long)(long long)fx_scale_for(pap);
+    finalize_alpha(pap, scal, state, g, G, lane);
 }
 
 // What a sweep knows about a row one step before it is processed: its block range, the first
@@ -700,11 +762,11 @@ __global__ void __launch_bounds__(256) level_back_kernel(const int32_t* __restri
     t_l[(2 * i + 1) * MOF_W] = with_parity(omega * a1, par);
 }
 
-// MODE 0 also leaves the row's share of p'(t+w) in dots[g][row][lane]; level_dot_kernel adds them up.
+// MODE 0 also adds the row's share of p'(t+w) to the frame's fixed-point accumulator; level_alpha_kernel turns it into alpha.
 template <int MODE>
 __global__ void __launch_bounds__(256) level_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                         const int32_t* __restrict__ diag, mof_batch_dev B, const double* pin,
-                                                        double* wout, double* __restrict__ dots, int64_t N, int64_t nb, int r_lo,
+                                                        double* wout, int64_t N, int64_t nb, int r_lo,
                                                         int r_hi, double omega) {
     const int64_t g = blockIdx.y;
     const int G = B.n_groups;
@@ -743,34 +805,20 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const int32_t* __restric
     }
     w_l[(2 * i) * MOF_W] = o0;
     w_l[(2 * i + 1) * MOF_W] = o1;
-    if (MODE == 0) dots[((size_t)g * N + i) * MOF_W + lane] = row_pdot(p0, p1, t0 + o0, t1 + o1);
-}
-
-// p'Ap = sum of the per-row shares (tile by tile, rows in order: deterministic), then alpha.
-__device__ __forceinline__ void level_dot_finish(const mof_batch_dev& B, int ntiles, int tile, int64_t g, double acc) {
-    const int G = B.n_groups;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double val[1] = {acc}, tot[1];
-    if (!tile_reduce<1>(val, B.partial + (size_t)g * ntiles * 2 * MOF_W, ntiles, tile, ticket_ptr(B.state, G) + g, tot)) return;
-    if (warp == 0) finalize_alpha(tot[0], B.scal, B.state, g, G, lane);
-}
-
-__device__ __forceinline__ void level_dot_body(const mof_batch_dev& B, const double* __restrict__ dots, int64_t N, int ntiles,
-                                               int tile, int64_t g) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row0 = (int64_t)tile * MOF_TILE_ROWS + warp * kRowsPerWarp;
-    double acc = 0.0;
-#pragma unroll
-    for (int q = 0; q < kRowsPerWarp; ++q) {
-        const int64_t v = row0 + q;
-        if (v < N) acc += __ldcs(dots + ((size_t)g * N + v) * MOF_W + lane);
+    if (MODE == 0) {                                 // the row's share of p'Ap, exact fixed-point accumulation
+        Fx128 x, acc = {0ull, 0ll};
+        const int k = (int)(long long)fx_word(B.scal, g, MOF_S_FX_K)[lane];
+        bool bad = !fx_from_double(row_pdot(p0, p1, t0 + o0, t1 + o1), k, x);
+        fx_add(acc, x);
+        fx_flush(B.scal, g, lane, acc, bad);
     }
-    level_dot_finish(B, ntiles, tile, g, acc);
 }
 
-__global__ void __launch_bounds__(256) level_dot_kernel(mof_batch_dev B, const double* __restrict__ dots, int64_t N, int ntiles) {
-    if (group_done_ptr(B.state, B.n_groups)[blockIdx.y]) return;
-    level_dot_body(B, dots, N, ntiles, blockIdx.x, blockIdx.y);
+// per-level launches: p'Ap of every group from its accumulators -> alpha (one warp per group)
+__global__ void __launch_bounds__(32) level_alpha_kernel(mof_batch_dev B) {
+    const int64_t g = blockIdx.x;
+    if (group_done_ptr(B.state, B.n_groups)[g]) return;
+    fx_finalize_alpha(B.scal, B.state, g, B.n_groups, threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------
@@ -886,11 +934,11 @@ struct LevelArgs {
 // One warp, one sweep.  DIR 0: backward (rows descending, upper blocks), DIR 1: forward.
 //   DIR 0 MODE 0: x += alpha p_old ; p <- zs r/omega + beta p_old ; t = (Dt+U)^-1 p        (vout = B.t)
 //   DIR 0 MODE 1: vout = (Dt+U)^-1 (x + alpha p)                                           (back-transform)
-//   DIR 1 MODE 0: w = (Dt+L)^-1 (p - ((2-omega)/omega) t) ; dots[row] = p.(t + w)          (vin = B.p, vout = B.ap)
+//   DIR 1 MODE 0: w = (Dt+L)^-1 (p - ((2-omega)/omega) t) ; p'Ap += p.(t + w)              (vin = B.p, vout = B.ap)
 //   DIR 1 MODE 1: vout = (Dt+L)^-1 vin
 // act == nullptr: all groups (A = n_groups).
 template <int DIR, int MODE, int PROBE = 0>     // PROBE (development): 1 cycle counters, 2 no waiting (WRONG results; bandwidth bound of the schedule)
-__device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const double* vin, double* vout, double* dots,
+__device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const double* vin, double* vout,
                                                   const uint16_t* act, int A, int32_t stamp, unsigned char* stage,
                                                   uint32_t bar, uint32_t& parity, uint64_t policy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -959,7 +1007,9 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
     int slot = 0;
     // per-frame scalars of the item's group: re-read only when the group changes (with W a multiple of A, never)
     double s_alpha = 0.0, s_beta = 0.0, s_zsw = 0.0;
-    int par = 0;
+    int par = 0, fxk = 0;                      // fxk: binary scale of the group's p'Ap accumulator (forward, MODE 0)
+    Fx128 fxacc = {0ull, 0ll};
+    bool fxbad = false;
     long long probe_prev = PROBE == 1 ? clock64() : 0, pacc[5] = {0, 0, 0, 0, 0};
 
     for (;;) {
@@ -975,6 +1025,10 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
         const double* sv = reinterpret_cast<const double*>(stage + slot * kStageBytes) + lane;
         const double* sx = reinterpret_cast<const double*>(stage + slot * kStageBytes + kStageValBytes) + lane;
         if (g != gprev) {                                // these loads overlap the gather below
+            if (DIR == 1 && MODE == 0) {
+                if (gprev != 0xffffffffu) fx_flush(B.scal, gprev, lane, fxacc, fxbad);
+                fxk = (int)(long long)__ldcg(fx_word(B.scal, g, MOF_S_FX_K) + lane);
+            }
             const int iters = __ldcg(state_ptr(B.state, g, MOF_I_ITERS) + lane);
             par = (MODE == 0 ? iters : iters + 1) & 1;
             if (DIR == 0) {
@@ -1083,10 +1137,12 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
         }
         st_strong(v_l, o0);
         st_strong(v_l + MOF_W, o1);
-        if (DIR == 1 && MODE == 0) {
+        if (DIR == 1 && MODE == 0) {                                    // the row's share of p'Ap
             q0 = sx[2 * MOF_W] + o0;
             q1 = sx[3 * MOF_W] + o1;
-            q0 = row_pdot(sx[0], sx[MOF_W], q0, q1);
+            Fx128 x;
+            if (!fx_from_double(row_pdot(sx[0], sx[MOF_W], q0, q1), fxk, x)) fxbad = true;
+            fx_add(fxacc, x);
         }
         __syncwarp();                                                    // every lane is done with the stage
         if (MODE == 1) {
@@ -1100,7 +1156,6 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
         } else if (more) {
             issue(0, rown, gn, nd);
         }
-        if (DIR == 1 && MODE == 0) __stcs(dots + ((size_t)g * N + row) * MOF_W + lane, q0);
         if (PROBE == 1) {
             pacc[0] += tk1 - tk0;                  // poll + gather
             pacc[1] += tk2 - tk1;                  // stage wait
@@ -1120,6 +1175,7 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             if (Jn < total) nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
         }
     }
+    if (DIR == 1 && MODE == 0) fx_flush(B.scal, g, lane, fxacc, fxbad);
     if (PROBE == 1 && lane == 0)
         for (int k = 0; k < 5; ++k) atomicAdd(a.probe + DIR * 8 + k, (unsigned long long)pacc[k]);
 }
@@ -1155,55 +1211,6 @@ __device__ __forceinline__ void persist_setup(PersistShared& S) {
     if (threadIdx.x < kWarps * 3) mbar_init(smem_u32(&S.bar[threadIdx.x / 3][threadIdx.x % 3]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-}
-
-// p'Ap = sum of the per-row shares the forward sweep left in `dots` -> alpha.  level_dot_kernel's arithmetic (a
-// warp adds its eight rows in order, tile_reduce does the rest); a warp's rows are one contiguous 2 KB piece,
-// fetched by one bulk copy per item, two items ahead (three slots).
-__device__ __noinline__ void level_dot_phase(const LevelArgs& a, const double* dots, const uint16_t* act, int A,
-                                                unsigned char* stage, uint32_t bar0, uint32_t& parity3, uint64_t policy,
-                                                double (*red)[1][MOF_W]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t N = a.N;
-    const int64_t items = (int64_t)a.ntiles * A;
-    const uint32_t stage_s = smem_u32(stage);
-    auto rows_of = [&](int64_t q) {
-        const int64_t row0 = (q / A) * MOF_TILE_ROWS + warp * kRowsPerWarp;
-        const int64_t n = N - row0;
-        return (int)(n < 0 ? 0 : (n > kRowsPerWarp ? kRowsPerWarp : n));
-    };
-    auto issue = [&](int64_t q, int slot) {
-        const int n = rows_of(q);
-        if (lane == 0 && n > 0) {
-            const int64_t row0 = (q / A) * MOF_TILE_ROWS + warp * kRowsPerWarp;
-            const uint32_t b = bar0 + 8u * slot;
-            mbar_expect_tx(b, (uint32_t)(n * MOF_W * 8));
-            bulk_g2s(stage_s + slot * kSlotBytes, dots + ((size_t)act[q % A] * N + row0) * MOF_W, (uint32_t)(n * MOF_W * 8), b, policy);
-        }
-    };
-    int64_t q = blockIdx.x;
-    if (q < items) issue(q, 0);
-    if (q + gridDim.x < items) issue(q + gridDim.x, 1);
-    int slot = 0;
-    for (; q < items; q += gridDim.x) {
-        const int64_t q2 = q + 2 * (int64_t)gridDim.x;
-        if (q2 < items) issue(q2, slot == 0 ? 2 : slot - 1);
-        const int n = rows_of(q);
-        double acc = 0.0;
-        if (n > 0) {
-            mbar_wait(bar0 + 8u * slot, (parity3 >> slot) & 1u);
-            parity3 ^= 1u << slot;
-            const double* sd = reinterpret_cast<const double*>(stage + slot * kSlotBytes) + lane;
-#pragma unroll
-            for (int j = 0; j < kRowsPerWarp; ++j)
-                if (j < n) acc += sd[j * MOF_W];
-        }
-        {
-            double val[1] = {acc};
-            tile_partial<1>(val, a.B.partial + (size_t)act[q % A] * a.ntiles * 2 * MOF_W, (int)(q / A), red);
-        }
-        slot = slot == 2 ? 0 : slot + 1;
-    }
 }
 
 // r -= alpha (t + w) ; r'r -> beta and the convergence test.  update_body<true>'s arithmetic; the three vectors
@@ -1299,13 +1306,14 @@ __device__ __noinline__ void level_group_phase(const LevelArgs& a, const uint16_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = blockIdx.x; q < A; q += gridDim.x) {
         const int64_t g = act[q];
-        double tot[STEP + 1];
-        reduce_all_tiles<STEP + 1>(B.partial + (size_t)g * a.ntiles * 2 * MOF_W, a.ntiles, tot, red);
-        if (warp == 0) {
-            if constexpr (STEP == 0) finalize_alpha(tot[0], B.scal, B.state, g, B.n_groups, lane);
-            else update_scalar_step(B, g, tot);
+        if constexpr (STEP == 0) {
+            if (warp == 0) fx_finalize_alpha(B.scal, B.state, g, B.n_groups, lane);
+        } else {
+            double tot[STEP + 1];
+            reduce_all_tiles<STEP + 1>(B.partial + (size_t)g * a.ntiles * 2 * MOF_W, a.ntiles, tot, red);
+            if (warp == 0) update_scalar_step(B, g, tot);
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -1331,7 +1339,6 @@ __global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int 
     const uint32_t bar = smem_u32(&S.bar[warp][0]);
     uint32_t parity = 0;                   // bit s: phase parity of this warp's mbarrier s (bit 0 is shared by all phases)
     const uint64_t policy = policy_evict_first();
-    double* dots = B.z;
     const bool clock = timing && blockIdx.x == 0 && threadIdx.x == 0;
     if (clock) {
         S.tprev = global_ns();
@@ -1343,15 +1350,13 @@ __global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int 
     for (int it = 0; it < n_iter; ++it) {
         const int A = build_active_list(group_done_ptr(B.state, G), G, S.act, &S.count);
         if (A == 0) break;
-        level_sweep_phase<0, 0, PROBE>(a, nullptr, B.t, nullptr, S.act, A, stamp0 + 2 * it + 1, stage, bar, parity, policy);
+        level_sweep_phase<0, 0, PROBE>(a, nullptr, B.t, S.act, A, stamp0 + 2 * it + 1, stage, bar, parity, policy);
         phase_barrier(grid);
         lap(0);
-        level_sweep_phase<1, 0, PROBE>(a, B.p, B.ap, dots, S.act, A, stamp0 + 2 * it + 2, stage, bar, parity, policy);
+        level_sweep_phase<1, 0, PROBE>(a, B.p, B.ap, S.act, A, stamp0 + 2 * it + 2, stage, bar, parity, policy);
         phase_barrier(grid);
         lap(1);
-        level_dot_phase(a, dots, S.act, A, stage, bar, parity, policy, reinterpret_cast<double(*)[1][MOF_W]>(S.red));
-        phase_barrier(grid);
-        level_group_phase<0>(a, S.act, A, reinterpret_cast<double(*)[1][MOF_W]>(S.red));
+        level_group_phase<0>(a, S.act, A, reinterpret_cast<double(*)[1][MOF_W]>(S.red));    // p'Ap accumulators -> alpha
         phase_barrier(grid);
         lap(2);
         level_update_phase(a, S.act, A, stage, bar, parity, policy, S.red);
@@ -1374,7 +1379,7 @@ __global__ void __launch_bounds__(256, 4) level_sweep_kernel(LevelArgs a, const 
     const int warp = threadIdx.x >> 5;
     persist_setup(S);
     uint32_t parity = 0;
-    level_sweep_phase<DIR, 1>(a, vin, vout, nullptr, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * kStages * kStageBytes,
+    level_sweep_phase<DIR, 1>(a, vin, vout, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * kStages * kStageBytes,
                               smem_u32(&S.bar[warp][0]), parity, policy_evict_first());
 }
 
@@ -1476,6 +1481,12 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
         scal_ptr(B.scal, g, MOF_S_BETA)[lane] = 0.0;      // first p-update: p = z
         scal_ptr(B.scal, g, MOF_S_ZS)[lane] = 1.0;
         scal_ptr(B.scal, g, MOF_S_BETA_SAVED)[lane] = 0.0;
+        if (mode == MODE_START_SSOR) {                       // level path: p'Ap accumulator, scaled by r'z for the first iteration
+            fx_word(B.scal, g, MOF_S_FX_LO)[lane] = 0ull;
+            fx_word(B.scal, g, MOF_S_FX_HI)[lane] = 0ull;
+            fx_word(B.scal, g, MOF_S_FX_BAD)[lane] = 0ull;
+            fx_word(B.scal, g, MOF_S_FX_K)[lane] = (unsigned long long)(long long)fx_scale_for(tot[0]);
+        }
         state_ptr(B.state, g, MOF_I_ITERS)[lane] = 0;
         if (!valid || tot[1] == 0.0) { act = 0; status[lane] = MOF_STATUS_ZERO_RHS; }
         else if (!isfinite(tot[1]) || !isfinite(tot[0])) { act = 0; status[lane] = MOF_STATUS_BREAKDOWN; }
@@ -1667,7 +1678,6 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     int32_t* d_active_groups = B.state + (size_t)G * MOF_I_COUNT * MOF_W + 2 * (size_t)G;
     int64_t launches = 0;
 
-    double* dots = B.z;                  // SSOR never stores z: its buffer carries the per-row shares of p'Ap
 
     // Persistent level kernels (default of the level path): cooperative launches sized to the device.
     const char* persist_env = getenv("MOF_LEVEL_PERSIST");
@@ -1780,12 +1790,12 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                 const int r0 = lp[l], r1 = lp[l + 1];
                 if (r1 <= r0) continue;
                 dim3 gs(mof_cdiv(r1 - r0, kWarps), G);
-                if (mode == 0) level_fwd_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
-                else           level_fwd_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, dots, N, nb, r0, r1, omega);
+                if (mode == 0) level_fwd_kernel<0><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, N, nb, r0, r1, omega);
+                else           level_fwd_kernel<1><<<gs, 256, 0, st>>>(mesh->rowptr, mesh->col, mesh->diag, B, pin, wout, N, nb, r0, r1, omega);
                 ++launches;
             }
             if (mode == 0) {
-                level_dot_kernel<<<grid, 256, 0, st>>>(B, dots, N, ntiles);
+                level_alpha_kernel<<<G, 32, 0, st>>>(B);
                 ++launches;
             }
             return;
