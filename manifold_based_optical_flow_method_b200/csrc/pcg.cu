@@ -937,7 +937,7 @@ struct LevelArgs {
 //   DIR 1 MODE 0: w = (Dt+L)^-1 (p - ((2-omega)/omega) t) ; p'Ap += p.(t + w)              (vin = B.p, vout = B.ap)
 //   DIR 1 MODE 1: vout = (Dt+L)^-1 vin
 // act == nullptr: all groups (A = n_groups).
-template <int DIR, int MODE, int PROBE = 0>     // PROBE (development): 1 cycle counters, 2 no waiting (WRONG results; bandwidth bound of the schedule)
+template <int DIR, int MODE, int PROBE = 0>     // PROBE = 1 (MOF_LEVEL_PROBE=1): cycle counters per item segment, same results
 __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const double* vin, double* vout,
                                                   const uint16_t* act, int A, int32_t stamp, unsigned char* stage,
                                                   uint32_t bar, uint32_t& parity, uint64_t policy) {
@@ -1074,7 +1074,7 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
 #pragma unroll
                 for (int k = 0; k < kStageBlocks; ++k)
                     if (k < cnt) ok = ok && has_parity(gv[k][0], par) && has_parity(gv[k][1], par);
-                if (PROBE == 2 || __all_sync(kFull, ok)) break;
+                if (__all_sync(kFull, ok)) break;
             }
         }
         if (PROBE == 1) tk1 = clock64();
@@ -1326,8 +1326,8 @@ __device__ __forceinline__ void phase_barrier(cooperative_groups::grid_group& gr
 
 // n_iter PCG iterations (or fewer if every group converges earlier).  stamp0: value of the last stamp used
 // in B.ready; the sweeps of iteration i use stamp0 + 2 i + 1 and stamp0 + 2 i + 2.
-template <int MINB, int PROBE>   // MINB: CTAs per SM the register budget is cut for (4: 64 registers, 3: 80, 2: 128)
-__global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int n_iter, int32_t stamp0, int timing) {
+template <int PROBE>              // two CTAs of eight warps per SM (two 6 KB stages per warp), <= 128 registers
+__global__ void __launch_bounds__(256, 2) level_iter_kernel(LevelArgs a, int n_iter, int32_t stamp0, int timing) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ PersistShared S;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
@@ -1373,7 +1373,7 @@ __global__ void __launch_bounds__(256, MINB) level_iter_kernel(LevelArgs a, int 
 
 // A single sweep of all groups (start: r = (Dt+L)^-1 b ; end: xs = (Dt+U)^-1 (xhat + alpha p)).
 template <int DIR>
-__global__ void __launch_bounds__(256, 4) level_sweep_kernel(LevelArgs a, const double* vin, double* vout, int32_t stamp) {
+__global__ void __launch_bounds__(256, 2) level_sweep_kernel(LevelArgs a, const double* vin, double* vout, int32_t stamp) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ PersistShared S;
     const int warp = threadIdx.x >> 5;
@@ -1699,16 +1699,9 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         MOF_CUDA_TRY(cudaGetDevice(&dev));
         MOF_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         MOF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const char* minb_env = getenv("MOF_LEVEL_MINB");             // tuning knob: register budget variant
         const char* probe_env = getenv("MOF_LEVEL_PROBE");           // development probe: per-item cycle breakdown on stderr
         const bool probe = probe_env && probe_env[0] == '1';
-        const bool nowait = probe_env && probe_env[0] == '2';         // timing experiment only: the sweeps do not wait, results are wrong
-        const bool minb3 = minb_env && minb_env[0] == '3';
-        const bool minb4 = minb_env && minb_env[0] == '4';          // default: 2 CTAs per SM (two 6 KB stages per warp), <= 128 registers
-        iter_fn = nowait ? (const void*)level_iter_kernel<2, 2>
-                : probe ? (const void*)level_iter_kernel<2, 1>
-                : minb3 ? (const void*)level_iter_kernel<3, 0>
-                : minb4 ? (const void*)level_iter_kernel<4, 0> : (const void*)level_iter_kernel<2, 0>;
+        iter_fn = probe ? (const void*)level_iter_kernel<1> : (const void*)level_iter_kernel<0>;
         if (probe) {
             const size_t pb = (16 + 2 * (size_t)N) * sizeof(unsigned long long);
             MOF_CUDA_TRY(cudaMalloc(&probe_buf, pb));

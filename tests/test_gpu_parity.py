@@ -723,3 +723,34 @@ def test_full_batch_every_group_against_oracle_system():
         assert np.linalg.norm(A @ Vk - f) / np.linalg.norm(f) <= 1e-11, (g, k)
     del V_dev, I_dev
     torch.cuda.empty_cache()
+
+
+def test_level_probe_mode_changes_nothing(tmp_path):
+    """MOF_LEVEL_PROBE=1 selects the instrumented build of the persistent kernel (cycle counters per item segment on
+    stderr, per-row finish times to MOF_LEVEL_PROBE_FILE): a development aid reachable from the environment, so it is
+    run here -- same bits as the plain kernel, and the timeline file has one stamp per row and sweep direction."""
+    import os
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    coords, tris, normals, areas = synthetic.pial_like(4)
+    T = 40
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=7)
+    old = cof.settings["precond"]
+    cof.settings["precond"] = DEFAULT_PRECOND
+    path = str(tmp_path / "rows.bin")
+    out = {}
+    try:
+        a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+        for probe in ("0", "1"):
+            os.environ["MOF_LEVEL_PROBE"] = probe
+            os.environ["MOF_LEVEL_PROBE_FILE"] = path
+            V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+            assert cof.last_solve_info.path[0] == _lib.PATH_LEVEL_PERSISTENT
+            out[probe] = (np.array(V_k), cof.last_solve_info.iterations.copy())
+    finally:
+        os.environ.pop("MOF_LEVEL_PROBE", None)
+        os.environ.pop("MOF_LEVEL_PROBE_FILE", None)
+        cof.settings["precond"] = old
+    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+    stamps = np.fromfile(path, dtype=np.uint64)
+    assert stamps.shape == (2 * len(coords),) and np.all(stamps > 0)
