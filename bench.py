@@ -588,6 +588,26 @@ def run_b200(args):
                          "tflops_fp64": 2.0 * T * N * m_el / (rbf_ms * 1e-3) / 1e12,
                          "note": "mof_rbf_fit (matrix, LU, T solves) + mof_rbf_evaluate (GEMM-shaped, kernel matrix on the "
                                  "fly), host electrode data in, (T, N) signal left in HBM; flops count the 2*T*N*m of the product only"}
+        # what the chip's fp64 pipe gives a library GEMM of the same shape class (cuBLAS DGEMM through torch), measured here:
+        # the honest denominator for a contraction that runs on the fp64 CUDA cores (no DMMA / tcgen05 path for fp64)
+        try:
+            ga = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+            gb = torch.randn((4096, 4096), dtype=torch.float64, device=dev)
+            torch.matmul(ga, gb)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(5):
+                torch.matmul(ga, gb)
+            g1.record()
+            torch.cuda.synchronize()
+            dgemm_tf = 5 * 2.0 * 4096 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
+            interpolation["dgemm_tflops_measured"] = dgemm_tf
+            interpolation["frac_of_measured_dgemm"] = interpolation["tflops_fp64"] / dgemm_tf
+            interpolation["note"] += ("; fp64 roofline: cuBLAS DGEMM 4096^3 measured in this run (dgemm_tflops_measured); the evaluate "
+                                      "kernel also spends two fp64 square roots per kernel-matrix entry that the flop count ignores")
+            del ga, gb
+        except Exception as exc:
+            interpolation["dgemm_error"] = repr(exc)
         if cpu is not None:
             from scipy.interpolate import Rbf
             tc = time.time()

@@ -754,3 +754,37 @@ def test_level_probe_mode_changes_nothing(tmp_path):
     assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
     stamps = np.fromfile(path, dtype=np.uint64)
     assert stamps.shape == (2 * len(coords),) and np.all(stamps > 0)
+
+
+@pytest.mark.parametrize("signal", ["wave", "phase"])
+def test_threshold_calibration_saves_a_verification_round(signal):
+    """After the first check interval the SSOR paths measure every frame's true / recurrence residual ratio once and
+    set its threshold from it (init_kernel MODE_CALIBRATE); MOF_CALIBRATE=0 is round 1's behaviour (freeze on the
+    recurrence residual, verify, rescale, resume).  Both must meet the true-residual tolerance and agree to the parity
+    tolerance; with the calibration no frame may need more kernel launches than without."""
+    import os
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    coords, tris, normals, areas = synthetic.icosphere(5)
+    T = 65
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=1) if signal == "wave" else synthetic.wrapped_phase(coords, t_k, seed=1)
+    old = cof.settings["precond"]
+    cof.settings["precond"] = DEFAULT_PRECOND
+    out = {}
+    try:
+        a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+        s = cof._solver(a2)
+        for cal in ("1", "0"):
+            os.environ["MOF_CALIBRATE"] = cal
+            s.profile = _lib.PcgProfile()
+            V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+            info = cof.last_solve_info
+            assert info.converged and info.relres.max() <= RES_TOL
+            out[cal] = (np.array(V_k), int(s.profile.launches_total), float(info.iterations.mean()))
+            s.profile = None
+    finally:
+        os.environ.pop("MOF_CALIBRATE", None)
+        cof.settings["precond"] = old
+    assert max(rel_l2(out["1"][0][k], out["0"][0][k]) for k in range(T - 1)) <= 1e-9
+    assert out["1"][1] <= out["0"][1] + 3, (out["1"][1:], out["0"][1:])      # + the three kernels of the calibration itself
+    assert out["1"][2] <= out["0"][2] * 1.05
