@@ -84,11 +84,31 @@ __global__ void __launch_bounds__(256) wave_unpack_kernel(int64_t N, int64_t out
 // needs, so the gathers of a vertex are all independent instead of a centry -> tri -> value chain per face.
 constexpr int kRingFaces = 8;
 
-__global__ void wave_ring_kernel(mof_mesh_dev M, int32_t* __restrict__ ring) {
+// ... and the vertex constants the per-frame arithmetic would otherwise recompute in every lane: 1 / area sum of the
+// ring (S5:169), the plane normal e1 x e2 and 1 / |n|^2 (S5:177-179), 1 / |e1|^2, 1 / |e2|^2 (S5:189-190).  fp64
+// divisions cost ~25 instructions each; as reciprocals computed once per vertex they are a multiplication per frame
+// (one rounding more than the reference's division, 1 ulp, inside the 1e-12 parity tolerance).
+constexpr int kVertexConsts = 8;      // inv_area_sum, n[3], inv_nn, inv_e1e1, inv_e2e2, pad
+
+__global__ void wave_ring_kernel(mof_mesh_dev M, int32_t* __restrict__ ring, double* __restrict__ vc) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= M.n_vertices) return;
     const int32_t bd = M.diag[v];
     const int32_t q0 = M.cptr[bd], q1 = M.cptr[bd + 1];
+    {
+        double asum = 0.0;
+        for (int32_t q = q0; q < q1; ++q) asum += M.areas[M.centry[q] >> 4];      // same order as the reference's sum
+        const double* e1 = M.e + 6 * v;
+        const double* e2 = e1 + 3;
+        const double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+        double* c = vc + (size_t)v * kVertexConsts;
+        c[0] = 1.0 / asum;
+        c[1] = nx; c[2] = ny; c[3] = nz;
+        c[4] = 1.0 / (nx * nx + ny * ny + nz * nz);
+        c[5] = 1.0 / (e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+        c[6] = 1.0 / (e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+        c[7] = 0.0;
+    }
     int32_t* r = ring + (size_t)v * kRingFaces * 4;
     for (int k = 0; k < kRingFaces; ++k) {
         const int32_t q = q0 + k;
@@ -102,7 +122,8 @@ __global__ void wave_ring_kernel(mof_mesh_dev M, int32_t* __restrict__ ring) {
 }
 
 // One warp per internal vertex, lane = frame (row 32 g + lane of the call).
-__global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const int32_t* __restrict__ ring, int64_t n_rows,
+__global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const int32_t* __restrict__ ring,
+                                                           const double* __restrict__ vc, int64_t n_rows,
                                                            int64_t t_first, int64_t T_trial, const double* __restrict__ It,
                                                            double dt, int phase_mode, double* __restrict__ Gt,
                                                            double* __restrict__ Wt) {
@@ -113,8 +134,9 @@ __global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const
     if (v >= N) return;
     const double* It_l = It + mof_ix_sca(N, g, 0) + lane;
     // area-weighted mean of the face gradients, faces ascending (S5:161-169)
-    double gx = 0.0, gy = 0.0, gz = 0.0, area_sum = 0.0;
+    double gx = 0.0, gy = 0.0, gz = 0.0;
     const int32_t rec = ring[(size_t)v * kRingFaces * 4 + lane];
+    const double* kc = vc + (size_t)v * kVertexConsts;
     auto add_face = [&](int64_t f, int64_t t0, int64_t t1, int64_t t2) {
         const double* gw = M.grad_w + 9 * f;
         const double I0 = It_l[(size_t)t0 * MOF_W], I1 = It_l[(size_t)t1 * MOF_W], I2 = It_l[(size_t)t2 * MOF_W];
@@ -122,7 +144,6 @@ __global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const
         gx += (I0 * gw[0] + I1 * gw[3] + I2 * gw[6]) * A;                   // S5:154-158,165
         gy += (I0 * gw[1] + I1 * gw[4] + I2 * gw[7]) * A;
         gz += (I0 * gw[2] + I1 * gw[5] + I2 * gw[8]) * A;
-        area_sum += A;
     };
     bool overflow = false;
 #pragma unroll
@@ -140,7 +161,7 @@ __global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const
             add_face(f, M.tri[3 * f], M.tri[3 * f + 1], M.tri[3 * f + 2]);
         }
     }
-    gx /= area_sum; gy /= area_sum; gz /= area_sum;                         // S5:169
+    gx *= kc[0]; gy *= kc[0]; gz *= kc[0];                                     // S5:169
     if (Gt) {
         double* gp = Gt + ((size_t)(g * N + v) * 3) * MOF_W + lane;
         gp[0] = gx; gp[MOF_W] = gy; gp[2 * MOF_W] = gz;
@@ -149,12 +170,12 @@ __global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const
     const double* e1 = M.e + 6 * v;
     const double* e2 = e1 + 3;
     // project_vector_to_plane (S5:173-180)
-    const double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
-    const double s = (gx * nx + gy * ny + gz * nz) / (nx * nx + ny * ny + nz * nz);
+    const double nx = kc[1], ny = kc[2], nz = kc[3];
+    const double s = (gx * nx + gy * ny + gz * nz) * kc[4];
     const double px = gx - s * nx, py = gy - s * ny, pz = gz - s * nz;
     // express_vector_on_basis (S5:182-191) and its norm (S5:117)
-    const double al = (px * e1[0] + py * e1[1] + pz * e1[2]) / (e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
-    const double be = (px * e2[0] + py * e2[1] + pz * e2[2]) / (e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+    const double al = (px * e1[0] + py * e1[1] + pz * e1[2]) * kc[5];
+    const double be = (px * e2[0] + py * e2[1] + pz * e2[2]) * kc[6];
     const double dis = sqrt(al * al + be * be);
     // time derivative: the neighbours in time are the adjacent lanes; the lanes at the ends of the group fetch
     // theirs from the next / previous group
@@ -187,7 +208,7 @@ __global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const
 extern "C" int64_t mof_wave_work_doubles(int64_t n_vertices, int64_t n_rows, int want_grad, int want_wave) {
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
     // signal + results in the frame-minor layout, then the ring records (kRingFaces x 4 int32 per vertex)
-    return G * n_vertices * MOF_W * (1 + (want_grad ? 3 : 0) + (want_wave ? 1 : 0)) + n_vertices * (kRingFaces * 4 / 2);
+    return G * n_vertices * MOF_W * (1 + (want_grad ? 3 : 0) + (want_wave ? 1 : 0)) + n_vertices * (kRingFaces * 4 / 2 + kVertexConsts);
 }
 
 extern "C" int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
@@ -218,11 +239,12 @@ extern "C" int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t 
     double* Wt = wave ? It + (size_t)G * N * MOF_W * (grad_point ? 4 : 1) : nullptr;
     dim3 tgrid(mof_cdiv(N, 32), (unsigned)G), tblock(32, 8);
     int32_t* ring = reinterpret_cast<int32_t*>(It + (size_t)G * N * MOF_W * (1 + (grad_point ? 3 : 0) + (wave ? 1 : 0)));
-    wave_ring_kernel<<<mof_cdiv(N, 256), 256, 0, st>>>(*mesh, ring);
+    double* vc = reinterpret_cast<double*>(ring + (size_t)N * kRingFaces * 4);
+    wave_ring_kernel<<<mof_cdiv(N, 256), 256, 0, st>>>(*mesh, ring, vc);
     MOF_LAUNCH_CHECK("wave_ring_kernel");
     wave_pack_kernel<<<tgrid, tblock, 0, st>>>(N, n_rows, mesh->perm, I, ld, It);
     MOF_LAUNCH_CHECK("wave_pack_kernel");
-    wave_stencil_kernel<<<dim3(mof_cdiv(N, 8), (unsigned)G), 256, 0, st>>>(*mesh, ring, n_rows, t_first, T_trial, It, dt, phase_mode, Gt, Wt);
+    wave_stencil_kernel<<<dim3(mof_cdiv(N, 8), (unsigned)G), 256, 0, st>>>(*mesh, ring, vc, n_rows, t_first, T_trial, It, dt, phase_mode, Gt, Wt);
     MOF_LAUNCH_CHECK("wave_stencil_kernel");
     if (grad_point) {
         wave_unpack_kernel<3><<<tgrid, tblock, 0, st>>>(N, out0, n_out, mesh->perm, Gt, grad_point);
@@ -246,7 +268,8 @@ extern "C" int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_
     double* Gt = want_grad ? It + (size_t)G * N * MOF_W : nullptr;
     double* Wt = want_wave ? It + (size_t)G * N * MOF_W * (want_grad ? 4 : 1) : nullptr;
     const int32_t* ring = reinterpret_cast<const int32_t*>(It + (size_t)G * N * MOF_W * (1 + (want_grad ? 3 : 0) + (want_wave ? 1 : 0)));
-    wave_stencil_kernel<<<dim3(mof_cdiv(N, 8), (unsigned)G), 256, 0, mof_stream(stream)>>>(*mesh, ring, n_rows, t_first, T_trial, It, dt,
+    const double* vc = reinterpret_cast<const double*>(ring + (size_t)N * kRingFaces * 4);
+    wave_stencil_kernel<<<dim3(mof_cdiv(N, 8), (unsigned)G), 256, 0, mof_stream(stream)>>>(*mesh, ring, vc, n_rows, t_first, T_trial, It, dt,
                                                                                           phase_mode, Gt, Wt);
     MOF_LAUNCH_CHECK("wave_stencil_kernel");
     return 0;
