@@ -47,6 +47,7 @@ settings = {
     "allow_unconverged": False,
     "pinned_results": True,        # host results land in pinned memory by direct DMA (False: pageable numpy via staging)
     "device": None,                # None = current CUDA device
+    "numa_bind": True,             # multi-GPU host delivery: pin each rank to the CPUs of its GPU's NUMA node (best effort)
 }
 
 last_solve_info = None             # SolveInfo of the most recent compute_velocity_field / worker call

@@ -277,7 +277,7 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
     width = 2 * N
     if transport not in ("auto", "shm", "nccl"):
         raise ValueError("transport must be 'auto', 'shm' or 'nccl'")
-    if to_host and world > 1:
+    if to_host and world > 1 and cof.settings.get("numa_bind", True):
         bind_to_gpu_numa_node(op.device.index)
     if to_host and world > 1 and gather in ("all", "root") and transport in ("shm", "auto"):
         if _result_pool.same_host():

@@ -788,3 +788,30 @@ def test_threshold_calibration_saves_a_verification_round(signal):
     assert max(rel_l2(out["1"][0][k], out["0"][0][k]) for k in range(T - 1)) <= 1e-9
     assert out["1"][1] <= out["0"][1] + 3, (out["1"][1:], out["0"][1:])      # + the three kernels of the calibration itself
     assert out["1"][2] <= out["0"][2] * 1.05
+
+
+@pytest.mark.parametrize("valence,want", [(20, "persistent"), (40, "launches")])
+def test_high_valence_rows_in_the_level_path(valence, want):
+    """A vertex with many neighbours: up to 32 blocks on one side of the diagonal the persistent kernel handles the
+    row (four blocks staged by the bulk copy, the next two from the row descriptor, the rest through the column
+    array); beyond that mof_level_desc_build declines and the solver falls back to one launch per level.  Either way
+    the fields match the oracle and the path taken is the one expected (no silent fallback, no silent misuse)."""
+    from manifold_based_optical_flow_method_b200 import compute_optical_flow as cof
+    coords, tris, normals, areas = synthetic.fan_mesh(valence, 3)
+    T = 5
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=1)
+    old = cof.settings["precond"]
+    cof.settings["precond"] = DEFAULT_PRECOND
+    try:
+        a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+        V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+    finally:
+        cof.settings["precond"] = old
+    info = cof.last_solve_info
+    assert (a2.d_level_desc is not None) == (want == "persistent")
+    assert info.path[0] == (_lib.PATH_LEVEL_PERSISTENT if want == "persistent" else _lib.PATH_LEVEL_LAUNCHES), info.path
+    a2o, gwo, eo, into = mof_oracle.geometrical_quantities(coords, normals, tris, areas)
+    for k in range(T - 1):
+        Vo = mof_oracle.worker(k, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[k], I[k + 1])
+        assert rel_l2(V_k[k], Vo) <= V_TOL
