@@ -43,7 +43,7 @@ extern "C" {
 #define MOF_GROUP 32          /* frames per group (= one warp, lane = frame)      */
 #define MOF_TILE_ROWS 64      /* block rows per CTA tile in the SpMV/PCG kernels  */
 #define MOF_MAX_COLORS 16     /* patch colours of the block-multicolour ordering   */
-#define MOF_SCAL_SLOTS 16      /* per-frame scalar slots in mof_batch_dev.scal      */
+#define MOF_SCAL_SLOTS 20      /* per-frame scalar slots in mof_batch_dev.scal      */
 
 /* numerical status per frame, written by mof_pcg_solve_batch */
 #define MOF_STATUS_CONVERGED 0

@@ -15,7 +15,7 @@ GROUP = 32           # MOF_GROUP
 TILE_ROWS = 64       # MOF_TILE_ROWS
 DETECT_CHUNK = 1024  # MOF_DETECT_CHUNK
 MAX_COLORS = 16      # MOF_MAX_COLORS
-SCAL_SLOTS = 16      # MOF_SCAL_SLOTS
+SCAL_SLOTS = 20      # MOF_SCAL_SLOTS
 
 PATH_JACOBI, PATH_MULTICOLOUR, PATH_LEVEL_LAUNCHES, PATH_LEVEL_PERSISTENT = 0, 1, 2, 3
 STATUS_CONVERGED, STATUS_MAXITER, STATUS_BREAKDOWN, STATUS_ZERO_RHS = 0, 1, 2, 3

@@ -42,7 +42,9 @@ enum { MOF_S_RZ = 0, MOF_S_PAP = 1, MOF_S_RR = 2, MOF_S_BB = 3, MOF_S_ALPHA = 4,
        // level path: exact fixed-point accumulator of p'Ap (128-bit two's complement in two 64-bit words), its
        // binary scale (int64) and an overflow / non-finite flag (int64); the slots hold bit patterns, not doubles
        MOF_S_FX_LO = 12, MOF_S_FX_HI = 13, MOF_S_FX_K = 14, MOF_S_FX_BAD = 15,
-       MOF_S_COUNT = 16 };
+       // the same accumulator serves r'r in the update phase (the phases alternate); its own binary scale:
+       MOF_S_FX_K_RR = 16, MOF_S_SPARE2 = 17, MOF_S_SPARE3 = 18, MOF_S_SPARE4 = 19,
+       MOF_S_COUNT = 20 };
 static_assert(MOF_S_COUNT == MOF_SCAL_SLOTS, "scalar slots of the header and the kernels differ");
 // state[g][MOF_I_*][32], then group_done[G], ticket[G], groups_active[1]
 enum { MOF_I_ACTIVE = 0, MOF_I_ITERS = 1, MOF_I_STATUS = 2, MOF_I_SPARE = 3, MOF_I_COUNT = 4 };

@@ -98,27 +98,6 @@ __device__ __forceinline__ void reduce_all_tiles(const double* __restrict__ part
     }
 }
 
-// First half of tile_reduce for the persistent kernel: the CTA's partial of tile `tile` goes to `partial_g`;
-// the cross-tile sum happens after a grid barrier (group_reduce), so no fence and no ticket per tile.
-template <int NV>
-__device__ __forceinline__ void tile_partial(const double (&val)[NV], double* __restrict__ partial_g, int tile,
-                                             double (*red)[NV][MOF_W]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) red[warp][k][lane] = val[k];
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double s = red[0][k][lane];
-#pragma unroll
-            for (int w = 1; w < kWarps; ++w) s += red[w][k][lane];
-            partial_g[((size_t)tile * 2 + k) * MOF_W + lane] = s;
-        }
-    }
-    __syncthreads();
-}
-
 // Deterministic CTA + cross-tile reduction of NV per-lane values.  Returns true (for every
 // thread of the CTA) in the last CTA of group g; there `tot` holds the totals in warp 0.
 template <int NV>
@@ -472,6 +451,53 @@ __device__ __forceinline__ void fx_finalize_alpha(double* scal, int32_t* state, 
     *lo = 0ull; *hi = 0ull; *bad = 0ull;
     if (pap > 0.0 && isfinite(pap)) *kk = (unsigned long long)(long long)fx_scale_for(pap);
     finalize_alpha(pap, scal, state, g, G, lane);
+}
+
+// r'r of group g from the accumulators -> r'z = r'r / omega, beta and the convergence test; accumulators cleared,
+// scale set for the next iteration (warp 0 of one CTA).
+__device__ __forceinline__ void fx_finalize_beta(const mof_batch_dev& B, int64_t g, int lane, double inv_omega) {
+    unsigned long long* lo = fx_word(B.scal, g, MOF_S_FX_LO) + lane;
+    unsigned long long* hi = fx_word(B.scal, g, MOF_S_FX_HI) + lane;
+    unsigned long long* kk = fx_word(B.scal, g, MOF_S_FX_K_RR) + lane;
+    unsigned long long* bad = fx_word(B.scal, g, MOF_S_FX_BAD) + lane;
+    const int k = (int)(long long)__ldcg(kk);
+    double rr = fx_to_double(__ldcg(lo), (long long)__ldcg(hi), k);
+    if (__ldcg(bad)) rr = nan("");
+    *lo = 0ull; *hi = 0ull; *bad = 0ull;
+    if (rr > 0.0 && isfinite(rr)) *kk = (unsigned long long)(long long)fx_scale_for(rr);
+    const double tot[2] = {rr * inv_omega, rr};          // r'z with z = r / omega
+    update_scalar_step(B, g, tot);
+}
+
+// Level path, per-level launches: the SSOR update with r'r accumulated in fixed point like the persistent kernel
+// (a warp's eight rows are summed in order in fp64, that partial goes into the accumulator), then level_beta_kernel.
+__global__ void __launch_bounds__(256) level_update_kernel(mof_batch_dev B, int64_t N) {
+    const int64_t g = blockIdx.y;
+    if (group_done_ptr(B.state, B.n_groups)[g]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * MOF_TILE_ROWS + warp * kRowsPerWarp;
+    if (row0 >= N) return;
+    const double alpha = scal_ptr(B.scal, g, MOF_S_ALPHA)[lane];
+    double rr = 0.0;
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int64_t v = row0 + q;
+        if (v >= N) break;
+        const size_t i0 = mof_ix_vec(N, g, v, 0) + lane, i1 = i0 + MOF_W;
+        const double a0 = __ldcs(B.ap + i0) + __ldcs(B.t + i0), a1 = __ldcs(B.ap + i1) + __ldcs(B.t + i1);
+        const double r0 = fma(-alpha, a0, B.r[i0]), r1 = fma(-alpha, a1, B.r[i1]);
+        B.r[i0] = r0; B.r[i1] = r1;
+        rr = fma(r0, r0, rr); rr = fma(r1, r1, rr);
+    }
+    Fx128 x, acc = {0ull, 0ll};
+    bool bad = !fx_from_double(rr, (int)(long long)fx_word(B.scal, g, MOF_S_FX_K_RR)[lane], x);
+    fx_add(acc, x);
+    fx_flush(B.scal, g, lane, acc, bad);
+}
+
+__global__ void __launch_bounds__(32) level_beta_kernel(mof_batch_dev B, double inv_omega) {
+    const int64_t g = blockIdx.x;
+    if (group_done_ptr(B.state, B.n_groups)[g]) return;
+    fx_finalize_beta(B, g, threadIdx.x, inv_omega);
 }
 
 // What a sweep knows about a row one step before it is processed: its block range, the first
@@ -1204,7 +1230,6 @@ struct PersistShared {
     uint16_t act[kPersistMaxGroups];
     int count;
     unsigned long long tprev, tacc[4];     // phase clock of CTA 0 (profile)
-    double red[kWarps][2][MOF_W];          // cross-warp scratch of the reductions
 };
 
 __device__ __forceinline__ void persist_setup(PersistShared& S) {
@@ -1217,7 +1242,7 @@ __device__ __forceinline__ void persist_setup(PersistShared& S) {
 // of a warp's rows come in by bulk copies, four rows (3 x 2 KB) at a time, the next piece requested as soon as
 // the stage has been read.
 __device__ __noinline__ void level_update_phase(const LevelArgs& a, const uint16_t* act, int A, unsigned char* stage,
-                                                   uint32_t bar, uint32_t& parity, uint64_t policy, double (*red)[2][MOF_W]) {
+                                                   uint32_t bar, uint32_t& parity, uint64_t policy) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const mof_batch_dev& B = a.B;
     const int64_t N = a.N;
@@ -1250,6 +1275,10 @@ __device__ __noinline__ void level_update_phase(const LevelArgs& a, const uint16
         }
     };
     for (int64_t i = 0; i < kStages && i < n_pieces; ++i) issue_piece(i);
+    Fx128 fxacc = {0ull, 0ll};
+    bool fxbad = false;
+    int fxk = 0;
+    int64_t gacc = -1;
     for (int64_t it = 0; it < n_items; ++it) {
         const int64_t q = q0 + it * gd;
         const int tile = (int)(q / A);
@@ -1290,30 +1319,30 @@ __device__ __noinline__ void level_update_phase(const LevelArgs& a, const uint16
                     }
             }
         }
-        {
-            double val[2] = {rr * a.inv_omega, rr};                      // r'z with z = r / omega, r'r
-            tile_partial<2>(val, B.partial + (size_t)g * a.ntiles * 2 * MOF_W, tile, red);
+        // the warp's partial of r'r (its eight rows, in order) goes into the group's fixed-point accumulator
+        if (g != gacc) {
+            if (gacc >= 0) fx_flush(B.scal, gacc, lane, fxacc, fxbad);
+            gacc = g;
+            fxk = (int)(long long)__ldcg(fx_word(B.scal, g, MOF_S_FX_K_RR) + lane);
         }
+        Fx128 x;
+        if (!fx_from_double(rr, fxk, x)) fxbad = true;
+        fx_add(fxacc, x);
     }
+    if (gacc >= 0) fx_flush(B.scal, gacc, lane, fxacc, fxbad);
 }
 
-// Second half of the two reductions, after a grid barrier: one CTA per group adds the tile partials in
-// tile_reduce's order and takes the scalar step (STEP 0: alpha from p'Ap, STEP 1: beta and convergence).
+// After a grid barrier: one warp per group turns the fixed-point accumulator into the scalar step
+// (STEP 0: p'Ap -> alpha; STEP 1: r'r -> beta and the convergence test).
 template <int STEP>
-__device__ __noinline__ void level_group_phase(const LevelArgs& a, const uint16_t* act, int A,
-                                                  double (*red)[STEP + 1][MOF_W]) {
+__device__ __noinline__ void level_group_phase(const LevelArgs& a, const uint16_t* act, int A) {
     const mof_batch_dev& B = a.B;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp != 0) return;
     for (int q = blockIdx.x; q < A; q += gridDim.x) {
         const int64_t g = act[q];
-        if constexpr (STEP == 0) {
-            if (warp == 0) fx_finalize_alpha(B.scal, B.state, g, B.n_groups, lane);
-        } else {
-            double tot[STEP + 1];
-            reduce_all_tiles<STEP + 1>(B.partial + (size_t)g * a.ntiles * 2 * MOF_W, a.ntiles, tot, red);
-            if (warp == 0) update_scalar_step(B, g, tot);
-            __syncthreads();
-        }
+        if constexpr (STEP == 0) fx_finalize_alpha(B.scal, B.state, g, B.n_groups, lane);
+        else fx_finalize_beta(B, g, lane, a.inv_omega);
     }
 }
 
@@ -1356,12 +1385,12 @@ __global__ void __launch_bounds__(256, 2) level_iter_kernel(LevelArgs a, int n_i
         level_sweep_phase<1, 0, PROBE>(a, B.p, B.ap, S.act, A, stamp0 + 2 * it + 2, stage, bar, parity, policy);
         phase_barrier(grid);
         lap(1);
-        level_group_phase<0>(a, S.act, A, reinterpret_cast<double(*)[1][MOF_W]>(S.red));    // p'Ap accumulators -> alpha
+        level_group_phase<0>(a, S.act, A);                               // p'Ap accumulator -> alpha
         phase_barrier(grid);
         lap(2);
-        level_update_phase(a, S.act, A, stage, bar, parity, policy, S.red);
+        level_update_phase(a, S.act, A, stage, bar, parity, policy);
         phase_barrier(grid);
-        level_group_phase<1>(a, S.act, A, S.red);
+        level_group_phase<1>(a, S.act, A);                               // r'r accumulator -> beta, convergence
         phase_barrier(grid);
         lap(3);
     }
@@ -1503,6 +1532,7 @@ __global__ void __launch_bounds__(256) init_kernel(mof_batch_dev B, int64_t N, i
             fx_word(B.scal, g, MOF_S_FX_HI)[lane] = 0ull;
             fx_word(B.scal, g, MOF_S_FX_BAD)[lane] = 0ull;
             fx_word(B.scal, g, MOF_S_FX_K)[lane] = (unsigned long long)(long long)fx_scale_for(tot[0]);
+            fx_word(B.scal, g, MOF_S_FX_K_RR)[lane] = (unsigned long long)(long long)fx_scale_for(tot[1]);
         }
         state_ptr(B.state, g, MOF_I_ITERS)[lane] = 0;
         if (!valid || tot[1] == 0.0) { act = 0; status[lane] = MOF_STATUS_ZERO_RHS; }
@@ -1878,7 +1908,9 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         MOF_CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
         sweep_back(0, B.t, cap);
         sweep_fwd(0, B.p, B.ap, cap);
-        update_kernel<true><<<grid, 256, 0, cap>>>(B, N, ntiles, inv_omega);
+        level_update_kernel<<<grid, 256, 0, cap>>>(B, N);
+        level_beta_kernel<<<G, 32, 0, cap>>>(B, inv_omega);
+        ++launches;
         const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
         launches_per_graph = launches - before + 1;
         launches = before;
@@ -1917,8 +1949,14 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
                     if (sample) cudaEventRecord(ev[1], st);
                     sweep_fwd(0, B.p, B.ap, st);                    // w ; alpha
                     if (sample) cudaEventRecord(ev[2], st);
-                    update_kernel<true><<<grid, 256, 0, st>>>(B, N, ntiles, inv_omega);
-                    launches += 1;
+                    if (levels) {
+                        level_update_kernel<<<grid, 256, 0, st>>>(B, N);
+                        level_beta_kernel<<<G, 32, 0, st>>>(B, inv_omega);
+                        launches += 2;
+                    } else {
+                        update_kernel<true><<<grid, 256, 0, st>>>(B, N, ntiles, inv_omega);
+                        launches += 1;
+                    }
                 }
                 if (sample) cudaEventRecord(ev[3], st);
             }
