@@ -118,7 +118,9 @@ typedef struct {
      * level_ptr is the ONE HOST POINTER of this struct: n_levels+1 row offsets read by the host side of
      * mof_pcg_solve_batch only (launch ranges of the per-level fallback path); kernels never dereference it. */
     int32_t n_levels;
-    int32_t reserved_;
+    int32_t level_stage_blocks;   /* persistent kernel: 3 = stage three matrix blocks per row in shared memory and keep three
+                                     stages per warp (meshes where nearly every row has <= 3 blocks on either side of its
+                                     diagonal); anything else = four blocks, two stages */
     const int32_t* level_ptr;
     /* device, [2][N][8] int32, filled by mof_level_desc_build (may be NULL: the solver then falls back to one
      * launch per dependency level): per row {first block, block count, first six columns} of the strictly

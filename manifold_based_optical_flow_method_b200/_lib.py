@@ -48,7 +48,7 @@ class MeshDev(Structure):
         ("cptr", c_void_p), ("centry", c_void_p), ("tri", c_void_p),
         ("e", c_void_p), ("grad_w", c_void_p), ("integral", c_void_p), ("areas", c_void_p), ("a2v", c_void_p),
         ("n_colors", c_int32), ("color_tile_ptr", c_int32 * (MAX_COLORS + 1)),
-        ("n_levels", c_int32), ("reserved_", c_int32), ("level_ptr", c_void_p),     # level_ptr: HOST int32[n_levels+1]
+        ("n_levels", c_int32), ("level_stage_blocks", c_int32), ("level_ptr", c_void_p),     # level_ptr: HOST int32[n_levels+1]
         ("level_desc", c_void_p),                                                   # device int32 [2][N][8] or NULL
     ]
 

@@ -869,17 +869,22 @@ __global__ void __launch_bounds__(32) level_alpha_kernel(mof_batch_dev B) {
 // device.  Per-row arithmetic and the order of every reduction are those of the per-level kernels: results
 // are bit-identical to them and independent of grid size, batch composition and GPU.
 // ---------------------------------------------------------------------------------
-constexpr int kStageBlocks = 4;                                       // matrix blocks of a row staged in shared memory
-constexpr int kStageValBytes = kStageBlocks * 4 * MOF_W * 8;          // 4096
 constexpr int kStageVecBytes = 2 * MOF_W * 8;                         // one row of one vector: 512
-constexpr int kStageBytes = 6144;                                     // per warp: sweeps use 4096 + 3 x 512, the vector
-                                                                      // phases 3 x 2048 (three vectors x four rows / three
-                                                                      // slots of eight rows of p'Ap shares)
-constexpr int kSlotBytes = 2048;
-constexpr int kStages = 2;                                            // stages per warp in the sweeps: two items in flight behind
-                                                                      // the one being computed (DRAM latency under load is
-                                                                      // longer than one item's dependent chain)
-static_assert(kStageValBytes + 3 * kStageVecBytes <= kStageBytes, "stage too small");
+constexpr int kSlotBytes = 2048;                                      // r update: three vectors x four rows = 3 x 2048 per piece
+constexpr int kPieceBytes = 3 * kSlotBytes;
+// Stage configuration of the sweeps: SB matrix blocks of a row are staged in shared memory (further blocks of a
+// longer row come through ordinary loads), NS stages per warp = NS - 1 items in flight behind the one being
+// computed.  A sweep's rate follows its items in flight (DRAM latency under load is several times one item's
+// dependent chain), and shared memory bounds them: <4, 2> (5.5 KB stages) suits meshes where many rows have four
+// blocks on one side of the diagonal, <3, 3> (4.5 KB stages, 216 KB per SM) the regular ones (ico7: 99.6 % of the
+// rows have three); the host picks by mesh->level_stage_blocks.
+template <int SB, int NS>
+struct StageCfg {
+    static constexpr int kBlocks = SB, kStages = NS;
+    static constexpr int kValBytes = SB * 4 * MOF_W * 8;
+    static constexpr int kBytes = kValBytes + 3 * kStageVecBytes;
+    static constexpr int kWarpBytes = NS * kBytes > 2 * kPieceBytes ? NS * kBytes : 2 * kPieceBytes;   // the r update rides two 6 KB pieces
+};
 constexpr int kPersistMaxGroups = 1024;                               // active-group list kept in shared memory (uint16)
 constexpr int kDescInts = 8;                                          // per row and direction: bs, cnt, col[0..5]
 constexpr int kDescCols = kDescInts - 2;
@@ -963,7 +968,7 @@ struct LevelArgs {
 //   DIR 1 MODE 0: w = (Dt+L)^-1 (p - ((2-omega)/omega) t) ; p'Ap += p.(t + w)              (vin = B.p, vout = B.ap)
 //   DIR 1 MODE 1: vout = (Dt+L)^-1 vin
 // act == nullptr: all groups (A = n_groups).
-template <int DIR, int MODE, int PROBE = 0>     // PROBE = 1 (MOF_LEVEL_PROBE=1): cycle counters per item segment, same results
+template <int DIR, int MODE, class CFG, int PROBE = 0>     // PROBE = 1 (MOF_LEVEL_PROBE=1): cycle counters per item segment, same results
 __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const double* vin, double* vout,
                                                   const uint16_t* act, int A, int32_t stamp, unsigned char* stage,
                                                   uint32_t bar, uint32_t& parity, uint64_t policy) {
@@ -982,6 +987,7 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
     const mof_batch_dev& B = a.B;
     const double omega = a.omega;
     constexpr int nvec = (DIR == 0) ? (MODE == 0 ? 3 : 2) : (MODE == 0 ? 2 : 1);
+    constexpr int kStageBlocks = CFG::kBlocks, kStages = CFG::kStages, kStageBytes = CFG::kBytes, kStageValBytes = CFG::kValBytes;
     const uint32_t stage_s0 = smem_u32(stage);
 
     // item J -> (row, group); row >= N: padding of the last block (skipped)
@@ -1019,18 +1025,25 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             }
         }
     };
-    // the warp's first kStages items go into flight; `cd` / `nd` are the descriptors of the current and the next item
-    uint32_t row = 0, g = 0, gprev = 0xffffffffu, rown = 0, gn = 0;
-    J = next_item(J, row, g);
-    if (J >= total) return;
-    int32_t cd = __ldg(desc + (size_t)row * kDescInts + (lane & 7)), nd = 0;
-    issue(0, row, g, cd);
-    uint32_t Jn = next_item(J + W, rown, gn);
-    if (Jn < total) {
-        nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
-        if (kStages > 1) issue(1, rown, gn, nd);
+    // the warp's first kStages items go into flight: cur (being computed next), nx1 and -- with three stages -- nx2
+    struct Item { uint32_t J, row, g; int32_t d; };
+    auto fetch = [&](uint32_t j) {
+        Item it{j, 0u, 0u, 0};
+        it.J = next_item(j, it.row, it.g);
+        if (it.J < total) it.d = __ldg(desc + (size_t)it.row * kDescInts + (lane & 7));
+        return it;
+    };
+    Item cur = fetch(J);
+    if (cur.J >= total) return;
+    issue(0, cur.row, cur.g, cur.d);
+    Item nx1 = fetch(cur.J + W), nx2{total, 0u, 0u, 0};
+    if (nx1.J < total) issue(1, nx1.row, nx1.g, nx1.d);
+    if (kStages > 2 && nx1.J < total) {
+        nx2 = fetch(nx1.J + W);
+        if (nx2.J < total) issue(2, nx2.row, nx2.g, nx2.d);
     }
     int slot = 0;
+    uint32_t gprev = 0xffffffffu;
     // per-frame scalars of the item's group: re-read only when the group changes (with W a multiple of A, never)
     double s_alpha = 0.0, s_beta = 0.0, s_zsw = 0.0;
     int par = 0, fxk = 0;                      // fxk: binary scale of the group's p'Ap accumulator (forward, MODE 0)
@@ -1039,13 +1052,14 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
     long long probe_prev = PROBE == 1 ? clock64() : 0, pacc[5] = {0, 0, 0, 0, 0};
 
     for (;;) {
-        const bool more = Jn < total;
-        // the item after the next: its descriptor is fetched now, its data requested when this item's stage is free
-        uint32_t rowf = 0, gf = 0, Jf = total;
-        int32_t fd = 0;
-        if (kStages > 1 && more) {
-            Jf = next_item(Jn + W, rowf, gf);
-            if (Jf < total) fd = __ldg(desc + (size_t)rowf * kDescInts + (lane & 7));
+        const uint32_t row = cur.row, g = cur.g;
+        const int32_t cd = cur.d;
+        const bool more = nx1.J < total;
+        // the item behind the ones in flight: its descriptor is fetched now, its data requested when this item's stage is free
+        Item far{total, 0u, 0u, 0};
+        {
+            const uint32_t last = kStages > 2 ? nx2.J : nx1.J;
+            if (last < total) far = fetch(last + W);
         }
         const uint32_t bslot = bar + 8u * slot;
         const double* sv = reinterpret_cast<const double*>(stage + slot * kStageBytes) + lane;
@@ -1177,11 +1191,7 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             if (lane == 0) st_relaxed(B.ready + (size_t)g * N + row, stamp);
         }
         if (PROBE == 1) tk3 = clock64();
-        if (kStages > 1) {                                               // this stage is free: request the item after the next
-            if (Jf < total) issue(slot, rowf, gf, fd);
-        } else if (more) {
-            issue(0, rown, gn, nd);
-        }
+        if (far.J < total) issue(slot, far.row, far.g, far.d);          // this stage is free again
         if (PROBE == 1) {
             pacc[0] += tk1 - tk0;                  // poll + gather
             pacc[1] += tk2 - tk1;                  // stage wait
@@ -1192,16 +1202,11 @@ __device__ __forceinline__ void level_sweep_phase(const LevelArgs& a, const doub
             if (lane == 0 && act && g == act[0]) a.probe[16 + (size_t)DIR * N + row] = global_ns();
         }
         if (!more) break;
-        J = Jn; row = rown; g = gn; cd = nd;
-        if (kStages > 1) {
-            Jn = Jf; rown = rowf; gn = gf; nd = fd;
-            slot ^= 1;
-        } else {
-            Jn = next_item(J + W, rown, gn);
-            if (Jn < total) nd = __ldg(desc + (size_t)rown * kDescInts + (lane & 7));
-        }
+        cur = nx1;
+        if (kStages > 2) { nx1 = nx2; nx2 = far; } else { nx1 = far; }
+        slot = slot + 1 == kStages ? 0 : slot + 1;
     }
-    if (DIR == 1 && MODE == 0) fx_flush(B.scal, g, lane, fxacc, fxbad);
+    if (DIR == 1 && MODE == 0 && gprev != 0xffffffffu) fx_flush(B.scal, gprev, lane, fxacc, fxbad);
     if (PROBE == 1 && lane == 0)
         for (int k = 0; k < 5; ++k) atomicAdd(a.probe + DIR * 8 + k, (unsigned long long)pacc[k]);
 }
@@ -1254,8 +1259,9 @@ __device__ __noinline__ void level_update_phase(const LevelArgs& a, const uint16
         const int64_t n = N - row0;
         return (int)(n < 0 ? 0 : (n > kPiece ? kPiece : n));
     };
-    // pieces of this CTA's items in order: piece i = half (i & 1) of the (i >> 1)-th item; piece i lives in stage
-    // i % kStages and piece i + kStages is requested as soon as piece i has been read
+    // pieces of this CTA's items in order: piece i = half (i & 1) of the (i >> 1)-th item; piece i lives in slot
+    // i % 2 of the warp's shared memory and piece i + 2 is requested as soon as piece i has been read
+    constexpr int kStages = 2, kStageBytes = kPieceBytes;
     const int64_t q0 = blockIdx.x, gd = gridDim.x;
     const int64_t n_items = q0 < items ? (items - q0 + gd - 1) / gd : 0;
     const int64_t n_pieces = 2 * n_items;
@@ -1355,7 +1361,7 @@ __device__ __forceinline__ void phase_barrier(cooperative_groups::grid_group& gr
 
 // n_iter PCG iterations (or fewer if every group converges earlier).  stamp0: value of the last stamp used
 // in B.ready; the sweeps of iteration i use stamp0 + 2 i + 1 and stamp0 + 2 i + 2.
-template <int PROBE>              // two CTAs of eight warps per SM (two 6 KB stages per warp), <= 128 registers
+template <int PROBE, class CFG>   // two CTAs of eight warps per SM, <= 128 registers; CFG: stage configuration of the sweeps
 __global__ void __launch_bounds__(256, 2) level_iter_kernel(LevelArgs a, int n_iter, int32_t stamp0, int timing) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ PersistShared S;
@@ -1364,7 +1370,7 @@ __global__ void __launch_bounds__(256, 2) level_iter_kernel(LevelArgs a, int n_i
     const mof_batch_dev& B = a.B;
     const int G = B.n_groups;
     persist_setup(S);
-    unsigned char* stage = dyn_smem + (size_t)warp * kStages * kStageBytes;
+    unsigned char* stage = dyn_smem + (size_t)warp * CFG::kWarpBytes;
     const uint32_t bar = smem_u32(&S.bar[warp][0]);
     uint32_t parity = 0;                   // bit s: phase parity of this warp's mbarrier s (bit 0 is shared by all phases)
     const uint64_t policy = policy_evict_first();
@@ -1379,10 +1385,10 @@ __global__ void __launch_bounds__(256, 2) level_iter_kernel(LevelArgs a, int n_i
     for (int it = 0; it < n_iter; ++it) {
         const int A = build_active_list(group_done_ptr(B.state, G), G, S.act, &S.count);
         if (A == 0) break;
-        level_sweep_phase<0, 0, PROBE>(a, nullptr, B.t, S.act, A, stamp0 + 2 * it + 1, stage, bar, parity, policy);
+        level_sweep_phase<0, 0, CFG, PROBE>(a, nullptr, B.t, S.act, A, stamp0 + 2 * it + 1, stage, bar, parity, policy);
         phase_barrier(grid);
         lap(0);
-        level_sweep_phase<1, 0, PROBE>(a, B.p, B.ap, S.act, A, stamp0 + 2 * it + 2, stage, bar, parity, policy);
+        level_sweep_phase<1, 0, CFG, PROBE>(a, B.p, B.ap, S.act, A, stamp0 + 2 * it + 2, stage, bar, parity, policy);
         phase_barrier(grid);
         lap(1);
         level_group_phase<0>(a, S.act, A);                               // p'Ap accumulator -> alpha
@@ -1401,14 +1407,14 @@ __global__ void __launch_bounds__(256, 2) level_iter_kernel(LevelArgs a, int n_i
 }
 
 // A single sweep of all groups (start: r = (Dt+L)^-1 b ; end: xs = (Dt+U)^-1 (xhat + alpha p)).
-template <int DIR>
+template <int DIR, class CFG>
 __global__ void __launch_bounds__(256, 2) level_sweep_kernel(LevelArgs a, const double* vin, double* vout, int32_t stamp) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ PersistShared S;
     const int warp = threadIdx.x >> 5;
     persist_setup(S);
     uint32_t parity = 0;
-    level_sweep_phase<DIR, 1>(a, vin, vout, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * kStages * kStageBytes,
+    level_sweep_phase<DIR, 1, CFG>(a, vin, vout, nullptr, a.B.n_groups, stamp, dyn_smem + (size_t)warp * CFG::kWarpBytes,
                               smem_u32(&S.bar[warp][0]), parity, policy_evict_first());
 }
 
@@ -1733,7 +1739,12 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     g_last_path[3] = persist ? 0 : (!levels ? 0 : !mesh->level_desc ? 1 : !B.ready ? 2 : G > kPersistMaxGroups ? 3 : 4);
     int grid_iter = 0, grid_sweep = 0;
     const void* iter_fn = nullptr;
-    const size_t persist_smem = (size_t)kWarps * kStages * kStageBytes;
+    using CfgWide = StageCfg<4, 2>;       // four blocks per row staged, two stages per warp
+    using CfgDeep = StageCfg<3, 3>;       // three blocks staged, three stages per warp (regular meshes)
+    const bool deep = mesh->level_stage_blocks == 3;
+    const size_t persist_smem = (size_t)kWarps * (deep ? CfgDeep::kWarpBytes : CfgWide::kWarpBytes);
+    const void* sweep_fn[2] = {deep ? (const void*)level_sweep_kernel<0, CfgDeep> : (const void*)level_sweep_kernel<0, CfgWide>,
+                               deep ? (const void*)level_sweep_kernel<1, CfgDeep> : (const void*)level_sweep_kernel<1, CfgWide>};
     LevelArgs largs{mesh->level_desc, mesh->col, B, N, nb, ntiles, omega, inv_omega, nullptr};
     unsigned long long* probe_buf = nullptr;
     struct ProbeGuard {
@@ -1748,7 +1759,8 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
         MOF_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const char* probe_env = getenv("MOF_LEVEL_PROBE");           // development probe: per-item cycle breakdown on stderr
         const bool probe = probe_env && probe_env[0] == '1';
-        iter_fn = probe ? (const void*)level_iter_kernel<1> : (const void*)level_iter_kernel<0>;
+        iter_fn = deep ? (probe ? (const void*)level_iter_kernel<1, CfgDeep> : (const void*)level_iter_kernel<0, CfgDeep>)
+                       : (probe ? (const void*)level_iter_kernel<1, CfgWide> : (const void*)level_iter_kernel<0, CfgWide>);
         if (probe) {
             const size_t pb = (16 + 2 * (size_t)N) * sizeof(unsigned long long);
             MOF_CUDA_TRY(cudaMalloc(&probe_buf, pb));
@@ -1756,15 +1768,15 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
             largs.probe = probe_buf;
         }
         MOF_CUDA_TRY(cudaFuncSetAttribute(iter_fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(sweep_fn[0], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(sweep_fn[1], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         // static + dynamic shared memory exceeds 48 KB: opt in
         MOF_CUDA_TRY(cudaFuncSetAttribute(iter_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
-        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
-        MOF_CUDA_TRY(cudaFuncSetAttribute(level_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(sweep_fn[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
+        MOF_CUDA_TRY(cudaFuncSetAttribute(sweep_fn[1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)persist_smem));
         MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_iter, iter_fn, 256, persist_smem));
-        MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, level_sweep_kernel<0>, 256, persist_smem));
-        MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, level_sweep_kernel<1>, 256, persist_smem));
+        MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, sweep_fn[0], 256, persist_smem));
+        MOF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, sweep_fn[1], 256, persist_smem));
         const int occ_s = occ_b < occ_f ? occ_b : occ_f;
         if (!coop || occ_iter < 1 || occ_s < 1) {
             persist = false;             // no co-residency guarantee: per-level launches
@@ -1787,7 +1799,7 @@ extern "C" int mof_pcg_solve_batch(const mof_mesh_dev* mesh, const mof_batch_dev
     auto persist_sweep = [&](int dir, const double* vin, double* vout, cudaStream_t st) -> cudaError_t {
         ++stamp;
         void* args[] = {(void*)&largs, (void*)&vin, (void*)&vout, (void*)&stamp};
-        return cudaLaunchCooperativeKernel(dir ? (const void*)level_sweep_kernel<1> : (const void*)level_sweep_kernel<0>,
+        return cudaLaunchCooperativeKernel(sweep_fn[dir ? 1 : 0],
                                            dim3(grid_sweep), dim3(256), args, persist_smem, st);
     };
     cudaError_t persist_err = cudaSuccess;

@@ -141,6 +141,14 @@ class MeshOperator:
             return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
         self.d_level_desc = None
+        # stage configuration of the persistent level kernel: four matrix blocks per row staged, two stages per warp.
+        # The alternative (three blocks, three stages: one more item in flight per warp) measured 0.4 % slower at ico7
+        # -- the sweeps sit at the memory system's rate for their access mix, not at a lack of items in flight -- and
+        # stays selectable for the tests that run both (MOF_LEVEL_STAGE_BLOCKS=3).
+        self.level_stage_blocks = 4
+        import os
+        if os.environ.get("MOF_LEVEL_STAGE_BLOCKS") in ("3", "4"):      # tests exercise both configurations on one mesh
+            self.level_stage_blocks = int(os.environ["MOF_LEVEL_STAGE_BLOCKS"])
         with torch.cuda.device(dev):
             self.d_perm, self.d_rowptr, self.d_col, self.d_diag = up(P.perm), up(P.rowptr), up(P.col), up(P.diag)
             self.d_cptr, self.d_centry, self.d_tri = up(P.cptr), up(P.centry), up(P.tri)
@@ -180,7 +188,7 @@ class MeshOperator:
             self.d_e.data_ptr(), self.d_grad_w.data_ptr(), self.d_integral.data_ptr(), self.d_areas.data_ptr(),
             self.d_a2v.data_ptr(), P.n_colors,
             (ctypes.c_int32 * (_lib.MAX_COLORS + 1))(*([int(x) for x in P.color_tile_ptr] + [0] * (_lib.MAX_COLORS - P.n_colors))),
-            P.n_levels, 0, P.level_ptr.ctypes.data if P.n_levels else None,
+            P.n_levels, self.level_stage_blocks, P.level_ptr.ctypes.data if P.n_levels else None,
             self.d_level_desc.data_ptr() if self.d_level_desc is not None else None)
 
     # -- reference-compatible views ----------------------------------------------------

@@ -626,8 +626,9 @@ def test_full_size_level_scheduled_path():
     assert itb < 0.6 * ita, (ita, itb)
 
 
+@pytest.mark.parametrize("stage_blocks", ["3", "4"])
 @pytest.mark.parametrize("level,frames", [(3, 5), (5, 70), (6, 33)])
-def test_persistent_level_kernel_bit_identical_to_per_level_launches(level, frames):
+def test_persistent_level_kernel_bit_identical_to_per_level_launches(level, frames, stage_blocks):
     """The persistent cooperative kernel (row-level dataflow, bulk-async prefetch) and the one-launch-per-level
     path run the same per-row arithmetic and the same reduction order: fields, iteration counts and residuals
     must be identical bit for bit (cof:147 replacement, default path vs its fallback)."""
@@ -640,9 +641,10 @@ def test_persistent_level_kernel_bit_identical_to_per_level_launches(level, fram
     old = cof.settings["precond"]
     cof.settings["precond"] = "ssor_level"
     out = {}
+    os.environ["MOF_LEVEL_STAGE_BLOCKS"] = stage_blocks        # both stage configurations of the sweeps (<3,3> and <4,2>)
     try:
         a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
-        assert a2.d_level_desc is not None
+        assert a2.d_level_desc is not None and a2.level_stage_blocks == int(stage_blocks)
         for persist in ("1", "0"):
             os.environ["MOF_LEVEL_PERSIST"] = persist
             V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
@@ -653,6 +655,7 @@ def test_persistent_level_kernel_bit_identical_to_per_level_launches(level, fram
             assert info.path[0] == want, info.path          # no silent fallback
     finally:
         os.environ.pop("MOF_LEVEL_PERSIST", None)
+        os.environ.pop("MOF_LEVEL_STAGE_BLOCKS", None)
         cof.settings["precond"] = old
     assert np.array_equal(out["1"][1], out["0"][1])
     assert np.array_equal(out["1"][0], out["0"][0])
