@@ -853,21 +853,24 @@ __global__ void __launch_bounds__(32) level_alpha_kernel(mof_batch_dev B) {
 // The per-level launches above cost a kernel boundary (a GPU-wide barrier plus a launch gap) per
 // dependency level, 2 x 1024 per iteration at ico7, and leave every row's loads exposed behind it.  Here
 // ONE cooperative launch runs `n_iter` whole PCG iterations.  Inside a sweep there is no barrier at all:
-// the rows of all active groups form one static work list in dependency order (forward: item J = row * A
-// + a, backward: rows descending; A = groups still iterating), warp w of the grid owns items w, w + W, ...
-// and a row waits only for the rows it actually reads, through one int32 `ready` stamp per (group, row):
-//   consumer: ld.acquire.gpu of the stamps of its <= 6 neighbours, then the gather of their t / w (L2),
-//   producer: stores, __threadfence, stamp.
+// the rows of all active groups form one static work list in dependency order (blocks of eight rows, group by
+// group inside a block; backward: rows descending; A = groups still iterating), warp w of the grid owns items
+// w, w + W, ... and a row waits only for the rows it actually reads:
+//   * iteration sweeps: the gathered t / w entries carry a validity bit (with_parity): ONE 8-byte
+//     ld.relaxed.gpu is both the "is it ready" poll and the gather; the writer needs neither fence nor flag;
+//   * the three other sweeps of a solve (start transform, back-transforms): an int32 `ready` stamp per
+//     (group, row) -- consumer ld.acquire.gpu, producer stores, fence, stamp.
 // Every item depends on items earlier in the list only, each warp walks its items in list order and all
 // CTAs are co-resident (cooperative launch), so the earliest unfinished item can always run: no deadlock.
 // Everything of a row that does not depend on the sweep (its matrix blocks -- contiguous in the level-major
-// numbering -- and its own entries of p, r, x / p, t) is fetched one item ahead by 1-D bulk async copies
-// (cp.async.bulk -> UBLKCP, completion on an mbarrier) into the warp's shared-memory stage while the warp is
-// still inside the previous item's dependent chain, so that chain is poll -> gather -> FMAs -> store.
-// The four phases of an iteration (backward sweep, forward sweep, p'Ap -> alpha, r update -> beta and the
-// convergence test) are separated by grid barriers; alpha, beta and the group_done flags never leave the
-// device.  Per-row arithmetic and the order of every reduction are those of the per-level kernels: results
-// are bit-identical to them and independent of grid size, batch composition and GPU.
+// numbering -- and its own entries of p, r, x / p, t) is fetched ahead by 1-D bulk async copies (cp.async.bulk
+// -> UBLKCP, completion on an mbarrier) into a ring of shared-memory stages per warp (StageCfg), so the
+// dependent chain of a row is gather -> FMAs -> store.
+// The phases of an iteration (backward sweep, forward sweep, alpha, r update, beta and the convergence test)
+// are separated by five grid barriers; p'Ap and r'r are accumulated exactly in 128-bit fixed point (Fx128), so
+// no reduction has an order; alpha, beta and the group_done flags never leave the device.  Per-row arithmetic
+// is that of the per-level kernels: results are bit-identical to them and independent of grid size, batch
+// composition and GPU.
 // ---------------------------------------------------------------------------------
 constexpr int kStageVecBytes = 2 * MOF_W * 8;                         // one row of one vector: 512
 constexpr int kSlotBytes = 2048;                                      // r update: three vectors x four rows = 3 x 2048 per piece
