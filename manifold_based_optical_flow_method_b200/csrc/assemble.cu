@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) pack_kernel(int64_t N, int32_t n_frames, 
 // scaled diagonal block S D S.  Then every off-diagonal block is assembled and written ONCE, already scaled
 // (Ah_ij = S_i A_ij S_j needs the neighbour's S_j, complete after the first launch).  Round 1 wrote the unscaled
 // matrix and then read-modified-wrote all of it in a separate scaling kernel (2 x 32 nb bytes per frame more).
-__global__ void __launch_bounds__(256) assemble_diag_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
+// Both launches are latency-bound on their index chains (contributor list -> face -> vertex values), so occupancy
+// decides: capped at 64 registers (4 CTAs = 32 warps per SM, 40 bytes of spills) they take 35.4 ms per 999-frame batch,
+// uncapped (74 registers, 3 CTAs) 41.6 ms, at 48 registers 43.7 ms.
+__global__ void __launch_bounds__(256, 4) assemble_diag_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = blockIdx.y;
     const int64_t N = M.n_vertices, nb = M.n_blocks;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) assemble_diag_kernel(mof_mesh_dev M, mof_
     }
 }
 
-__global__ void __launch_bounds__(256) assemble_offdiag_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
+__global__ void __launch_bounds__(256, 4) assemble_offdiag_kernel(mof_mesh_dev M, mof_batch_dev B, double lambda_, bool ssor) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t g = blockIdx.y;
     const int64_t N = M.n_vertices, nb = M.n_blocks;
