@@ -47,6 +47,7 @@ settings = {
     "allow_unconverged": False,
     "pinned_results": True,        # host results land in pinned memory by direct DMA (False: pageable numpy via staging)
     "device": None,                # None = current CUDA device
+    "streamed_upload": True,       # host signal copied in chunks on a side stream, K1 runs chunk by chunk as rows arrive
     "numa_bind": True,             # multi-GPU host delivery: pin each rank to the CPUs of its GPU's NUMA node (best effort)
 }
 
@@ -102,6 +103,32 @@ def _check_converged(info, first_frame=0):
         raise UnconvergedError(info, [int(b) + first_frame for b in bad])
 
 
+def _upload_for_solve(op, I_k, I_k_2, n, first=0):
+    """_upload_signals for a solve that follows at once -> (I_dev, I2_dev, upload).  With settings["streamed_upload"]
+    and both signals being the same contiguous float64 host array (what S3 passes, S3:115-116) the copy is issued
+    in chunks on a side stream and ``upload`` is the ``SignalUpload`` in flight: the solver assembles every chunk of
+    frames as its rows arrive.  Otherwise a blocking upload and ``upload`` = None."""
+    torch = _lib.require_cuda()
+    N = op.n_vertices
+    if settings["streamed_upload"] and I_k_2 is I_k and not isinstance(I_k, (list, tuple)) and n > 0:
+        src = None
+        if torch.is_tensor(I_k):
+            if I_k.device.type == "cpu" and I_k.dtype == torch.float64 and I_k.ndim == 2 and I_k.shape[1] == N \
+                    and I_k.shape[0] >= first + n + 1 and I_k[first:first + n + 1].is_contiguous():
+                src = I_k[first:first + n + 1]
+        else:
+            a = np.asarray(I_k)
+            if a.ndim == 2 and a.shape[1] == N and a.shape[0] >= first + n + 1 and a.dtype == np.float64 \
+                    and a[first:first + n + 1].flags.c_contiguous:
+                src = torch.from_numpy(a[first:first + n + 1])
+        if src is not None:
+            from .solver import SignalUpload
+            up = SignalUpload(torch, op.device, src, n + 1, N)
+            return up.tensor, up.tensor, up
+    I_dev, I2_dev = _upload_signals(op, I_k, I_k_2, n, first)
+    return I_dev, I2_dev, None
+
+
 def _upload_signals(op, I_k, I_k_2, n, first=0):
     """Rows first .. first+n of the (T,N) signals -> device float64 tensors whose row 0 is
     frame ``first``.  Frame k reads I_k[k] and I_k_2[k+1] (:174-175)."""
@@ -128,17 +155,21 @@ def _upload_signals(op, I_k, I_k_2, n, first=0):
     return rows(I_k, first, first + n, "I_k"), rows(I_k_2, first, first + n + 1, "I_k_2")
 
 
-def solve_on_device(op, I_dev, I2_dev, t_k, lambda_, k0, k1, V_dev=None, on_batch=None):
+def solve_on_device(op, I_dev, I2_dev, t_k, lambda_, k0, k1, V_dev=None, on_batch=None, upload=None):
     """Frames k0..k1-1 from device-resident signals (rows are absolute frame indices).
     -> (V_dev (k1-k0, 2N) device tensor, SolveInfo).  Used by bench.py (inputs resident in
-    HBM) and by distributed.py."""
+    HBM) and by distributed.py.  upload: the SignalUpload still filling I_dev (k0 must be 0), see _upload_signals."""
     torch = _lib.require_cuda()
     s = _solver(op)
     dt = torch.from_numpy(frame_dt(t_k, k0, k1)).to(op.device)
+    if upload is not None and k0 == 0:
+        return s.solve_frames(I_dev, I2_dev, dt, lambda_, V_dev, on_batch=on_batch, upload=upload)
+    if upload is not None:
+        upload.wait_rows(torch, op.device, k1 + 1)
     return s.solve_frames(I_dev[k0:k1 + 1], I2_dev[k0:k1 + 1], dt, lambda_, V_dev, on_batch=on_batch)
 
 
-def solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n):
+def solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n, upload=None):
     """solve_on_device for frames 0..n-1 with the results drained to a host array batch by
     batch, overlapped with the solve of the next batch.  -> (V (n, 2N) numpy, SolveInfo)"""
     s = _solver(op)
@@ -151,7 +182,7 @@ def solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n):
     else:
         V = np.empty((n, 2 * op.n_vertices), dtype=np.float64)
         on_batch = lambda k0, k1, Vd: drain.submit(Vd, V[k0:k1])
-    _, info = solve_on_device(op, I_dev, I2_dev, t_k, lambda_, 0, n, on_batch=on_batch)
+    _, info = solve_on_device(op, I_dev, I2_dev, t_k, lambda_, 0, n, on_batch=on_batch, upload=upload)
     drain.finish()
     return V, info
 
@@ -204,8 +235,8 @@ def compute_velocity_field(processes_num, time_steps, a2, grad_w, e, integral_wi
     if distributed.world_size() > 1:
         V, info = distributed.compute_velocity_field_sharded(op, n, t_k, lambda_, I_k, I_k_2)
     else:
-        I_dev, I2_dev = _upload_signals(op, I_k, I_k_2, n)
-        V, info = solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n)
+        I_dev, I2_dev, upload = _upload_for_solve(op, I_k, I_k_2, n)
+        V, info = solve_to_host(op, I_dev, I2_dev, t_k, lambda_, n, upload=upload)
     execution_time = time.time() - start_time
     info.seconds = execution_time
     last_solve_info = info

@@ -329,8 +329,8 @@ def solve_shard_and_gather(op, I_shard, I2_shard, t_k_shard, lambda_, counts, ga
         on_batch = None
 
     if n_loc > 0:
-        I_dev, I2_dev = cof._upload_signals(op, I_shard, I2_shard, n_loc)
-        V_loc, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc, on_batch=on_batch)
+        I_dev, I2_dev, upload = cof._upload_for_solve(op, I_shard, I2_shard, n_loc)
+        V_loc, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc, on_batch=on_batch, upload=upload)
         rep = np.stack([info.iterations.astype(np.float64), info.relres, info.status.astype(np.float64)], axis=1)
     else:
         V_loc = torch.empty((0, width), dtype=torch.float64, device=op.device)
@@ -370,14 +370,14 @@ def _solve_shard_to_shared_host(op, I_shard, I2_shard, t_k_shard, lambda_, count
     if n_loc > 0:
         solver = cof._solver(op)
         drain = solver.drain(width)
-        I_dev, I2_dev = cof._upload_signals(op, I_shard, I2_shard, n_loc)
+        I_dev, I2_dev, upload = cof._upload_for_solve(op, I_shard, I2_shard, n_loc)
         if entry["pinned"]:
             mine_t = entry["mine_t"]
             on_batch = lambda k0, k1, Vd: drain.submit_pinned(Vd, mine_t[k0:k1])
         else:                                            # registration refused: staged copies into the same rows
             mine = entry["mine"]
             on_batch = lambda k0, k1, Vd: drain.submit(Vd, mine[k0:k1])
-        _, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc, on_batch=on_batch)
+        _, info = cof.solve_on_device(op, I_dev, I2_dev, list(t_k_shard), lambda_, 0, n_loc, on_batch=on_batch, upload=upload)
         drain.finish()
         rep = np.stack([info.iterations.astype(np.float64), info.relres, info.status.astype(np.float64)], axis=1)
     else:

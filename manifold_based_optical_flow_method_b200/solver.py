@@ -98,6 +98,42 @@ class FrameBatch:
         return 8 * GROUP * (4 * n_blocks + n_vertices * (2 + 2 * 7 + 3)) + 4 * n_vertices
 
 
+class SignalUpload:
+    """A (rows, N) device tensor that is still being filled from host memory: chunks of rows are copied on a side
+    stream, in order, and ``arrivals`` lists (rows_complete, event) pairs -- rows [0, rows_complete) are on the device
+    once the event has fired.  VelocitySolver.solve_frames packs and assembles every 32-frame group chunk as soon as
+    its rows are there, so the host-to-device copy of a signal hides behind K1 instead of preceding it."""
+
+    CHUNK_GROUPS = 4                     # 128 frames (~170 MB at 164k vertices) per copy
+
+    def __init__(self, torch, device, src, n_rows, n_cols):
+        self.tensor = torch.empty((int(n_rows), int(n_cols)), dtype=torch.float64, device=device)
+        self.arrivals = []
+        self.stream = torch.cuda.Stream(device=device)
+        self.stream.wait_stream(torch.cuda.current_stream(device))
+        step = self.CHUNK_GROUPS * GROUP
+        with torch.cuda.stream(self.stream):
+            r0 = 0
+            while r0 < n_rows:
+                # frames [f0, f1) read rows [f0, f1]: a chunk of frames ends one row later than it starts the next one
+                r1 = min(int(n_rows), (r0 // step + 1) * step + 1) if r0 == 0 else min(int(n_rows), r0 + step)
+                self.tensor[r0:r1].copy_(src[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.arrivals.append((r1, ev))
+                r0 = r1
+        self.tensor.record_stream(self.stream)
+
+    def wait_rows(self, torch, device, rows):
+        """Make the current stream wait until rows [0, rows) have arrived."""
+        for have, ev in self.arrivals:
+            if have >= rows:
+                torch.cuda.current_stream(device).wait_event(ev)
+                return
+        if self.arrivals:
+            torch.cuda.current_stream(device).wait_event(self.arrivals[-1][1])
+
+
 class VelocitySolver:
     """Solves batches of frames on one GPU.  Buffers are allocated once and reused."""
 
@@ -235,8 +271,33 @@ class VelocitySolver:
         _lib.check(lib.mof_assemble_batch(ctypes.byref(ms), ctypes.byref(bs), float(lambda_), self.omega, st))
         return ms, bs
 
-    def solve_batch(self, I_now, I_next, dt, lambda_, V_out, batch=None, profile=None):
-        """One batch: frames = rows of I_now.  V_out: device (n_frames, 2N) view.  -> SolveInfo"""
+    def assemble_streamed(self, batch, upload, row0, dt, lambda_, n_frames):
+        """pack + K1 chunk by chunk while ``upload`` (a SignalUpload whose row ``row0`` is frame 0 of this batch, the same
+        tensor serving as I_now and, one row later, as I_next) is still arriving.  Same kernels on the same data as
+        ``assemble``: every chunk is a view of the batch (the buffers are group-major) whose launches wait for its rows."""
+        torch, lib, op = self.torch, self.lib, self.op
+        st = torch.cuda.current_stream(op.device).cuda_stream
+        ms = op.struct()
+        I = upload.tensor
+        N, nb, W = op.n_vertices, op.n_blocks, GROUP
+        step = SignalUpload.CHUNK_GROUPS * GROUP
+        for f0 in range(0, n_frames, step):
+            f1 = min(n_frames, f0 + step)
+            upload.wait_rows(torch, op.device, row0 + f1 + 1)
+            g0, gc = f0 // GROUP, -(-(f1 - f0) // GROUP)
+            b = batch
+            view = _lib.BatchDev(
+                gc, f1 - f0, b.It.data_ptr() + 8 * g0 * N * W, b.dIt.data_ptr() + 8 * g0 * N * W,
+                b.vals.data_ptr() + 8 * g0 * nb * 4 * W, b.rhs.data_ptr() + 8 * g0 * N * 2 * W,
+                b.minv.data_ptr() + 8 * g0 * N * 3 * W, None, None, None, None, None, None, None, None, None, None)
+            _lib.check(lib.mof_pack_frames(ctypes.byref(ms), ctypes.byref(view), I[row0 + f0].data_ptr(), I[row0 + f0 + 1].data_ptr(),
+                                           I.stride(0), dt[f0:].data_ptr(), st))
+            _lib.check(lib.mof_assemble_batch(ctypes.byref(ms), ctypes.byref(view), float(lambda_), self.omega, st))
+        return ms, batch.struct(n_frames, (int(n_frames) + GROUP - 1) // GROUP)
+
+    def solve_batch(self, I_now, I_next, dt, lambda_, V_out, batch=None, profile=None, upload=None, upload_row0=0):
+        """One batch: frames = rows of I_now.  V_out: device (n_frames, 2N) view.  -> SolveInfo.
+        upload: a SignalUpload still in flight whose tensor I_now / I_next are views of (then K1 runs chunk by chunk)."""
         torch, lib, op = self.torch, self.lib, self.op
         n_frames = int(I_now.shape[0])
         G = (n_frames + GROUP - 1) // GROUP
@@ -245,7 +306,10 @@ class VelocitySolver:
         if profile is None:
             profile = self.profile
         st = torch.cuda.current_stream(op.device).cuda_stream
-        ms, bs = self.assemble(batch, I_now, I_next, dt, lambda_, n_frames)
+        if upload is not None:
+            ms, bs = self.assemble_streamed(batch, upload, upload_row0, dt, lambda_, n_frames)
+        else:
+            ms, bs = self.assemble(batch, I_now, I_next, dt, lambda_, n_frames)
         iters = np.zeros(G * GROUP, np.int32)
         relres = np.zeros(G * GROUP, np.float64)
         status = np.zeros(G * GROUP, np.int32)
@@ -261,7 +325,7 @@ class VelocitySolver:
         _lib.check(lib.mof_unpack_solution(ctypes.byref(ms), ctypes.byref(bs), V_out.data_ptr(), V_out.stride(0), st))
         return SolveInfo(iters[:n_frames], relres[:n_frames], status[:n_frames], path=tuple(path))
 
-    def solve_frames(self, I_dev, I2_dev, dt_dev, lambda_, V_dev=None, on_batch=None):
+    def solve_frames(self, I_dev, I2_dev, dt_dev, lambda_, V_dev=None, on_batch=None, upload=None):
         """All frames k = 0 .. n-1 with (I_dev[k], I2_dev[k+1]) (compute_optical_flow.py:174-175).
         I_dev, I2_dev: device (>= n+1, N) float64 (may be the same tensor); dt_dev: device (n,).
         on_batch(k0, k1, V_dev[k0:k1]) is called after each batch has been queued on the stream
@@ -276,10 +340,14 @@ class VelocitySolver:
         per = max(1, min(self.batch_groups // lanes, -(-groups // lanes))) if lanes > 1 else self.batch_groups
         step = per * GROUP
         ranges = [(k0, min(n, k0 + step)) for k0 in range(0, n, step)]
+        if upload is not None and not (I_dev is I2_dev and (lanes == 1 or len(ranges) == 1)):
+            upload.wait_rows(torch, op.device, n + 1)              # concurrent lanes / two signals: wait for the whole copy
+            upload = None
         if lanes == 1 or len(ranges) == 1:
             infos = []
             for k0, k1 in ranges:
-                infos.append(self.solve_batch(I_dev[k0:k1], I2_dev[k0 + 1:k1 + 1], dt_dev[k0:k1], lambda_, V_dev[k0:k1]))
+                infos.append(self.solve_batch(I_dev[k0:k1], I2_dev[k0 + 1:k1 + 1], dt_dev[k0:k1], lambda_, V_dev[k0:k1],
+                                              upload=upload, upload_row0=k0))
                 if on_batch is not None:
                     on_batch(k0, k1, V_dev[k0:k1])
         else:

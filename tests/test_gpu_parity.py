@@ -818,3 +818,26 @@ def test_high_valence_rows_in_the_level_path(valence, want):
     for k in range(T - 1):
         Vo = mof_oracle.worker(k, a2o, gwo, eo, into, tris, t_k, areas, 0.01, I[k], I[k + 1])
         assert rel_l2(V_k[k], Vo) <= V_TOL
+
+
+@pytest.mark.parametrize("n_frames", [5, 129, 300])
+def test_streamed_upload_is_bit_identical(n_frames, mods):
+    """settings['streamed_upload']: the host signal arrives in chunks on a side stream and pack + K1 run chunk by chunk as
+    the rows land (the copy hides behind the assembly).  Same kernels on the same data: fields identical bit for bit to the
+    blocking upload, for a single ragged group, a chunk boundary and several chunks."""
+    cof, _ = mods
+    coords, tris, normals, areas = synthetic.icosphere(3)
+    T = n_frames + 1
+    t_k = synthetic.time_axis(T, 512.0)
+    I = synthetic.travelling_wave(coords, t_k, seed=11)
+    a2, gw, e, integ, _ = cof.compute_geometrical_quantities(coords, normals, tris, areas)
+    out = {}
+    old = cof.settings["streamed_upload"]
+    try:
+        for mode in (True, False):
+            cof.settings["streamed_upload"] = mode
+            V_k, _ = cof.compute_velocity_field(1, T, a2, gw, e, integ, tris, t_k, areas, 0.01, I, I)
+            out[mode] = np.array(V_k)
+    finally:
+        cof.settings["streamed_upload"] = old
+    assert np.array_equal(out[True], out[False])
