@@ -108,6 +108,7 @@ class SignalUpload:
 
     def __init__(self, torch, device, src, n_rows, n_cols):
         self.tensor = torch.empty((int(n_rows), int(n_cols)), dtype=torch.float64, device=device)
+        self.src = src                       # the host rows must outlive the copies in flight
         self.arrivals = []
         self.stream = torch.cuda.Stream(device=device)
         self.stream.wait_stream(torch.cuda.current_stream(device))
