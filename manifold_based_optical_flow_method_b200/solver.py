@@ -98,6 +98,17 @@ class FrameBatch:
         return 8 * GROUP * (4 * n_blocks + n_vertices * (2 + 2 * 7 + 3)) + 4 * n_vertices
 
 
+def upload_chunks(n_rows, step):
+    """Row ranges [r0, r1) in which a signal of ``n_rows`` rows is copied so that the frames [c*step, (c+1)*step) of
+    chunk c are complete when copy c is (frame k reads rows k and k+1): the first copy carries one row more."""
+    out, r0 = [], 0
+    while r0 < n_rows:
+        r1 = min(int(n_rows), step + 1 if r0 == 0 else r0 + step)
+        out.append((r0, r1))
+        r0 = r1
+    return out
+
+
 class SignalUpload:
     """A (rows, N) device tensor that is still being filled from host memory: chunks of rows are copied on a side
     stream, in order, and ``arrivals`` lists (rows_complete, event) pairs -- rows [0, rows_complete) are on the device
@@ -114,15 +125,11 @@ class SignalUpload:
         self.stream.wait_stream(torch.cuda.current_stream(device))
         step = self.CHUNK_GROUPS * GROUP
         with torch.cuda.stream(self.stream):
-            r0 = 0
-            while r0 < n_rows:
-                # frames [f0, f1) read rows [f0, f1]: a chunk of frames ends one row later than it starts the next one
-                r1 = min(int(n_rows), (r0 // step + 1) * step + 1) if r0 == 0 else min(int(n_rows), r0 + step)
+            for r0, r1 in upload_chunks(n_rows, step):
                 self.tensor[r0:r1].copy_(src[r0:r1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
                 self.arrivals.append((r1, ev))
-                r0 = r1
         self.tensor.record_stream(self.stream)
 
     def wait_rows(self, torch, device, rows):

@@ -482,3 +482,18 @@ def test_level_sweeps_do_not_depend_on_the_order_inside_a_level():
                           beta.ctypes.data, zs.ctypes.data, omega, 0)
     hc.hc_sweep_rows_fwd(ref, G, vals.ctypes.data, p.ctypes.data, t.ctypes.data, w.ctypes.data, 0, N, omega, 0, None)
     assert all(np.array_equal(a, b) for a, b in zip((p, t, w), base))
+
+
+def test_upload_chunks_cover_every_frame():
+    """Streamed upload (solver.SignalUpload): copy c must bring every row that the frames of chunk c read (rows k and
+    k + 1 of frame k), rows are copied once and in order."""
+    from manifold_based_optical_flow_method_b200.solver import upload_chunks
+    for step in (32, 128):
+        for n_rows in (1, 2, step, step + 1, step + 2, 3 * step, 3 * step + 1, 1000):
+            ch = upload_chunks(n_rows, step)
+            assert ch[0][0] == 0 and ch[-1][1] == n_rows
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and all(r1 > r0 for r0, r1 in ch)
+            n_frames = n_rows - 1
+            for c, f0 in enumerate(range(0, n_frames, step)):
+                f1 = min(n_frames, f0 + step)
+                assert ch[min(c, len(ch) - 1)][1] >= f1 + 1, (step, n_rows, c)
