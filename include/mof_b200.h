@@ -361,17 +361,26 @@ int mof_rbf_evaluate(int64_t n_vertices, int64_t n_centres, int64_t n_frames, co
  * the other rows are halo (one frame either side; two at a trial end in amplitude mode, where np.gradient's
  * one-sided formula applies).  Whole trial on one GPU: n_rows = n_out = T_trial, out0 = t_first = 0.  Frames
  * sharded over GPUs (config 5): every rank passes its range plus the halo -- no collective on the data path.
- * work: device scratch of mof_wave_work_doubles(N, n_rows, grad_point != NULL, wave != NULL) doubles (the
- * signal and the results in the frame-minor layout [group][internal vertex][32 frames]).
+ * work: device scratch of mof_wave_work_doubles(mesh, n_rows, grad_point != NULL, wave != NULL) doubles: the
+ * signal in the frame-minor layout [group][internal vertex][32 frames] and the coefficient rows (two / three
+ * doubles per block of the mesh pattern) that turn the per-frame work into one sparse row product per vertex
+ * (csrc/wave.cu); the results go straight into grad_point / wave.  The kernels work for any mesh ordering; the
+ * transposes are fully coalesced when the mesh was built with reorder = 0 (perm = identity), which is what
+ * S5_compute_wave_v.py does.
  * ------------------------------------------------------------------------- */
-int64_t mof_wave_work_doubles(int64_t n_vertices, int64_t n_rows, int want_grad, int want_wave);
+int64_t mof_wave_work_doubles(const mof_mesh_dev* mesh, int64_t n_rows, int want_grad, int want_wave);
 int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
                    int64_t T_trial, const double* I, int64_t ld, double dt, int phase_mode, double* grad_point,
                    double* wave, double* work, void* stream);
-/* The stencil kernel alone on a work buffer that a previous mof_wave_speed call with the same arguments has
- * packed (roofline hook of bench.py, like mof_spmv_batch). */
-int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t t_first, int64_t T_trial, double dt,
-                     int phase_mode, int want_grad, int want_wave, double* work, void* stream);
+/* The row kernel(s) alone on a work buffer that a previous mof_wave_speed call with the same mesh, n_rows and
+ * outputs has filled (roofline hook of bench.py, like mof_spmv_batch). */
+int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
+                     int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, double* work,
+                     void* stream);
+
+/* Tuning knob: 32-frame groups a CTA of the wave-speed kernel takes per pass, 1 or 2 (default 2, or the environment
+ * variable MOF_WAVE_GROUPS at first use).  Results are bit-identical either way. */
+int mof_wave_set_groups_per_pass(int groups);
 
 /* ------------------------------------------------------------------------- *
  * On-disk formats either side of the path ("next" row 4 of SURVEY 8f), host only, multi-threaded.

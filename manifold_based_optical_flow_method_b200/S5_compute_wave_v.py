@@ -10,10 +10,11 @@ of SURVEY.md section 8f): wave speed = |d/dt| / |surface gradient| of a phase (o
 ``surface`` is anything with the pyvista members the reference uses (``points``, ``faces``,
 ``compute_cell_sizes(...)['Area']``) -- a real ``pyvista.PolyData`` or ``synthetic.SurfaceMesh``.
 The per-vertex face lists come from the mesh pattern (ascending face index) instead of
-``surface.point_cell_ids``.  csrc/wave.cu transposes the signal into the frame-minor layout, runs one
-stencil kernel (per-face gradient, area-weighted vertex average, tangent projection, basis coefficients,
-their norm, the (wrapped) time derivative and the division; one warp per vertex, lane = frame) and
-transposes the result back; no CPU fallback.  Under torchrun the frames are sharded over the GPUs with a
+``surface.point_cell_ids``.  csrc/wave.cu folds the per-face gradients, the area-weighted vertex average, the
+tangent projection and the basis coefficients -- all linear in the signal -- into two coefficients per
+(vertex, ring vertex) pair once per call, transposes the signal into the frame-minor layout, and runs one kernel
+that evaluates a sparse row product per vertex and frame (lane = frame), the (wrapped) time derivative and the
+division, and writes the (T, N) result directly; no CPU fallback.  Under torchrun the frames are sharded over the GPUs with a
 time-derivative halo (``wave_speed_device`` / the public functions do it transparently), no collective on
 the data path.
 """
@@ -47,7 +48,9 @@ def _operator(coordinates, triangles, areas, e=None):
         _ops.clear()
         normals = np.zeros_like(coordinates)
         normals[:, 2] = 1.0
-        op = _ops[key] = MeshOperator(coordinates, normals, triangles, areas, reorder=1)
+        # reference vertex order (reorder=0): the (T, N) <-> frame-minor transposes of csrc/wave.cu are then fully
+        # coalesced, and the ring gathers move whole 256-byte lines whatever the numbering
+        op = _ops[key] = MeshOperator(coordinates, normals, triangles, areas, reorder=0)
     op.use_geometry(None, e, None, areas)
     return op
 
@@ -65,22 +68,29 @@ def halo_rows(k0, k1, T, phase_mode):
 
 
 def wave_speed_device(op, d_rows, t_first, T_trial, out0, n_out, dt, phase_mode, want_grad=False, want_wave=True,
-                      work=None):
+                      work=None, grad_out=None, wave_out=None):
     """mof_wave_speed on device-resident rows ``d_rows`` ((n_rows, N) float64, reference vertex order; row 0 is
     frame ``t_first`` of a ``T_trial``-frame trial) -> (grad (n_out, N, 3) or None, wave (n_out, N) or None) for
-    rows out0 .. out0+n_out-1.  bench.py and the sharded path call this."""
+    rows out0 .. out0+n_out-1.  bench.py and the sharded path call this.  ``work`` / ``grad_out`` / ``wave_out``:
+    optional preallocated scratch and result tensors (a repeated caller then allocates nothing per call)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     n_rows, N = int(d_rows.shape[0]), int(d_rows.shape[1])
     if N != op.n_vertices:
         raise ValueError(f"data must have shape (T, {op.n_vertices}), got {tuple(d_rows.shape)}")
     assert d_rows.stride(1) == 1
-    need = int(lib.mof_wave_work_doubles(N, n_rows, int(want_grad), int(want_wave)))
+    ms = op.struct()
+    need = int(lib.mof_wave_work_doubles(ctypes.byref(ms), n_rows, int(want_grad), int(want_wave)))
     if work is None or work.numel() < need:
         work = torch.empty((need,), dtype=torch.float64, device=op.device)
-    grad = torch.empty((n_out, N, 3), dtype=torch.float64, device=op.device) if want_grad else None
-    wave = torch.empty((n_out, N), dtype=torch.float64, device=op.device) if want_wave else None
-    ms = op.struct()
+    def result(given, shape):
+        if given is None:
+            return torch.empty(shape, dtype=torch.float64, device=op.device)
+        if tuple(given.shape) != shape or given.dtype != torch.float64 or not given.is_contiguous() or given.device != op.device:
+            raise ValueError(f"result tensor must be a contiguous float64 {shape} on {op.device}")
+        return given
+    grad = result(grad_out, (int(n_out), N, 3)) if want_grad else None
+    wave = result(wave_out, (int(n_out), N)) if want_wave else None
     st = torch.cuda.current_stream(op.device).cuda_stream
     _lib.check(lib.mof_wave_speed(ctypes.byref(ms), n_rows, int(out0), int(n_out), int(t_first), int(T_trial),
                                   d_rows.data_ptr(), d_rows.stride(0), float(dt), 1 if phase_mode else 0,

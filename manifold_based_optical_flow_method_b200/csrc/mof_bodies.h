@@ -439,4 +439,83 @@ MOF_HD double mof_rbf_phi_body(const double* x, const double* c, double inv_eps)
     return sqrt(MOF_ADD(MOF_MUL(s, s), 1.0));
 }
 
+// ---- K6 (S5 wave speed; S5 = S5_compute_wave_v.py under /root/reference) -------------
+// angle_subtract, S5:224-233: np.mod(f1 - f2 + pi, 2 pi) - pi, result in [-pi, pi).  fmod is exact, so the three
+// range branches ARE fmod plus numpy's sign fix for |d| < 4 pi (d - 2 pi is exact for d in [2 pi, 4 pi) by Sterbenz);
+// inputs in [-pi, pi] never leave them.
+MOF_HD double mof_angle_subtract_body(double a, double b) {
+    const double kPi = 3.141592653589793, kTwoPi = 2.0 * 3.141592653589793;
+    const double d = MOF_ADD(MOF_ADD(a, -b), kPi);
+    double m;
+    if (d >= 0.0 && d < kTwoPi) m = d;
+    else if (d < 0.0 && d > -kTwoPi) m = MOF_ADD(d, kTwoPi);
+    else if (d >= kTwoPi && d < 2.0 * kTwoPi) m = MOF_ADD(d, -kTwoPi);
+    else {
+        m = fmod(d, kTwoPi);
+        if (m != 0.0 && m < 0.0) m = MOF_ADD(m, kTwoPi);      // numpy's mod takes the sign of the divisor
+    }
+    return MOF_ADD(m, -kPi);
+}
+
+// Coefficient rows of vertex v, aligned with its block row j = rowptr[v] .. rowptr[v+1]-1 (column u = col[j]):
+//   cg[j][3] = (1 / sum of A_f over the faces of v) * sum over the faces f holding v and u of A_f grad_w[f][position of u]
+//              -> grad_point[v] = sum_j cg[j] I[u_j]                      (compute_grad_M_I, S5:136-171, faces ascending)
+//   cw[j][2] = (alpha, beta) of cg[j] projected into the plane of (e1, e2) (project_vector_to_plane S5:173-180,
+//              express_vector_on_basis S5:182-191) -> (alpha, beta)[v] = sum_j cw[j] I[u_j]
+// Either output may be NULL.
+MOF_HD void mof_wave_coef_row_body(const mof_mesh_dev& M, int64_t v, double* cw, double* cg) {
+    const int32_t bd = M.diag[v];
+    double asum = 0.0;                                                       // S5:169: every face of v is on its diagonal block
+    for (int32_t q = M.cptr[bd]; q < M.cptr[bd + 1]; ++q) asum += M.areas[M.centry[q] >> 4];
+    const double inv_asum = 1.0 / asum;
+    const double* e1 = M.e + 6 * v;
+    const double* e2 = e1 + 3;
+    const double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];   // S5:177
+    const double inv_nn = 1.0 / (nx * nx + ny * ny + nz * nz);
+    const double inv_e1 = 1.0 / (e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    const double inv_e2 = 1.0 / (e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+    for (int32_t j = M.rowptr[v]; j < M.rowptr[v + 1]; ++j) {
+        double x = 0.0, y = 0.0, z = 0.0;
+        for (int32_t q = M.cptr[j]; q < M.cptr[j + 1]; ++q) {
+            const int32_t ce = M.centry[q];
+            const int64_t f = ce >> 4;
+            const double* gw = M.grad_w + 9 * f + 3 * (ce & 3);             // hat gradient of the column vertex in f (S5:154-158)
+            const double A = M.areas[f];
+            x += gw[0] * A; y += gw[1] * A; z += gw[2] * A;                  // S5:165
+        }
+        x *= inv_asum; y *= inv_asum; z *= inv_asum;
+        if (cg) { cg[3 * (size_t)j] = x; cg[3 * (size_t)j + 1] = y; cg[3 * (size_t)j + 2] = z; }
+        if (cw) {
+            const double s = (x * nx + y * ny + z * nz) * inv_nn;
+            const double px = x - s * nx, py = y - s * ny, pz = z - s * nz;
+            cw[2 * (size_t)j] = (px * e1[0] + py * e1[1] + pz * e1[2]) * inv_e1;
+            cw[2 * (size_t)j + 1] = (px * e2[0] + py * e2[1] + pz * e2[2]) * inv_e2;
+        }
+    }
+}
+
+// Time derivative of one (vertex, frame): wrapped differences for phases (compute_temporal_gradient_phase, S5:60-77)
+// or np.gradient(axis=0, edge_order=2) / dt for amplitudes (S5:24).  first / last: the frame is the trial's first / last;
+// far2: the value two frames inside the trial from that end (amplitude mode only).  x inv_dt is one rounding away from
+// the reference's / dt.
+MOF_HD double mof_wave_td_body(int phase_mode, bool first, bool last, int64_t T_trial, double cur, double prev, double next,
+                               double far2, double inv_dt) {
+    if (phase_mode) {
+        if (T_trial <= 1) return 0.0;
+        return mof_angle_subtract_body(last ? cur : next, first ? cur : prev) * (first || last ? inv_dt : 0.5 * inv_dt);
+    }
+    if (first) return (-1.5 * cur + 2.0 * next - 0.5 * far2) * inv_dt;
+    if (last) return (1.5 * cur - 2.0 * prev + 0.5 * far2) * inv_dt;
+    return ((next - prev) / 2.0) * inv_dt;
+}
+
+// S5:117,121 (S5:52,56): td / sqrt(alpha^2 + beta^2); 0 / 0 -> nan and x / 0 -> +-inf come out of 0 * inf and x * inf alike.
+MOF_HD double mof_wave_speed_body(double td, double al, double be) {
+#if defined(__CUDA_ARCH__)
+    return td * rsqrt(fma(be, be, al * al));
+#else
+    return td * (1.0 / sqrt(fma(be, be, al * al)));
+#endif
+}
+
 #endif  // MOF_BODIES_H

@@ -7,30 +7,39 @@
 //   S5:60-77, angle_subtract S5:224-233) or np.gradient(edge_order=2) for amplitudes (S5:24),
 //   wave_velocity = time derivative / norm (S5:121 / S5:56).
 //
-// Layout.  Round 1 ran one thread per (vertex, frame) on the (T,N) arrays as they are: every value of
-// the 1-ring was an 8-byte load through two index indirections and the result an 8-byte scattered
-// store.  Now the signal is first transposed into the frame-minor layout of the solver
-// (It[group][internal vertex][32 frames], wave_pack_kernel), the stencil runs with one WARP per
-// vertex and lane = frame -- every value of the 1-ring is one 256-byte line that 32 frames share,
-// the face geometry is a broadcast, the time neighbours are the adjacent lanes -- and the result is
-// transposed back (wave_unpack_kernel).  Algorithmic HBM bytes of the stencil: 8 N read + 8 N written
-// per frame; the 1-ring re-reads are served by L1/L2 (internal numbering = breadth-first).
-// A call may cover a SHARD of a trial: rows outside [out0, out0 + n_out) are halo for the time
-// derivative, and the one-sided end formulas apply at the trial's ends only (t_first, T_trial).
+// Formulation.  Everything between the signal and (alpha, beta) is LINEAR in the signal and depends on the mesh
+// only: grad_point[v] = sum over the 1-ring u (v included) of cg[v,u] I[u], with
+//     cg[v,u] = (1 / sum of A_f over the faces of v) * sum over the faces f that hold v and u of A_f grad_w[f][position of u]
+// and (alpha, beta)[v] = sum_u cw[v,u] I[u], cw[v,u] = the tangent coefficients of the projected cg[v,u].  The pairs
+// (v,u) are exactly the blocks of the solver's block-CSR pattern (rowptr / col / per-block face lists), so the
+// coefficients are two or three doubles per block, computed once per call by wave_coef_kernel (faces ascending, the
+// order of S5:161-166), and the per-frame work is one sparse row product: 7 entries x 2 FMAs per vertex and frame
+// instead of six face gradients, a projection and two basis coefficients (~120 fp64 instructions in round 2's first
+// kernel, which made it fp64-bound at 0.08 of the HBM peak).  The sums are re-associated with respect to the
+// reference (per ring vertex instead of per face); measured difference from the unmodified reference 5e-14 rel-L2 at
+// most on the parity cases (tests/test_wave_speed.py asserts <= 1e-12 / 1e-13).
+//
+// Layout.  The (T,N) signal is transposed once into the frame-minor layout of the solver (It[group][vertex][32 frames],
+// wave_pack_kernel).  wave_rows_kernel: a CTA owns 32 consecutive vertices of one 32-frame group; it stages the
+// column indices and coefficients of its 32 block rows in shared memory with one coalesced pass, then every warp walks
+// four vertices with lane = frame -- each ring value is one 256-byte line that 32 frames share, the time neighbours are
+// the adjacent lanes -- and the tile is transposed through shared memory so that the result is written straight into
+// the caller's (T,N[,3]) array as 256-byte (768-byte) row pieces: no frame-minor result, no transpose kernel behind it.
+// Algorithmic HBM bytes: 8 N read + 8 N written per frame (the pack moves another 16 N); the ring re-reads are served
+// by L1 (inside the CTA's tile) and L2 (a group's It is N x 256 bytes = 42 MB at 164k vertices).
+// The wave operator keeps the mesh in REFERENCE vertex order (S5_compute_wave_v._operator: reorder = 0), which
+// makes both transposes fully coalesced; the kernels honour mesh->perm all the same.
+// A call may cover a SHARD of a trial: rows outside [out0, out0 + n_out) are halo for the time derivative, and the
+// one-sided end formulas apply at the trial's ends only (t_first, T_trial).
+#include <stdlib.h>
+
 #include "mof_common.cuh"
 
 namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-
-__device__ __forceinline__ double angle_subtract(double a, double b) {
-    // np.mod(f1 - f2 + pi, 2 pi) - pi : result in [-pi, pi)            (S5:230)
-    const double kPi = 3.141592653589793, kTwoPi = 2.0 * 3.141592653589793;
-    double d = a - b + kPi;
-    double m = fmod(d, kTwoPi);
-    if (m != 0.0 && m < 0.0) m += kTwoPi;      // numpy's mod takes the sign of the divisor
-    return m - kPi;
-}
+constexpr int kTileVerts = 32;        // vertices per CTA of wave_rows_kernel
+constexpr int kStageEntries = 384;    // block-row entries of a tile staged in shared memory (12 per row; longer rows read global)
 
 // (rows, N) row-major, reference vertex order -> It[g][v][32], internal order (rows padded with 0)
 __global__ void __launch_bounds__(256) wave_pack_kernel(int64_t N, int64_t n_rows, const int32_t* __restrict__ perm,
@@ -52,163 +61,213 @@ __global__ void __launch_bounds__(256) wave_pack_kernel(int64_t N, int64_t n_row
     }
 }
 
-// frame-minor result [g][v][C][32] -> out (n_out, N, C) reference order, rows out0 .. out0+n_out-1 of the call
-template <int C>
-__global__ void __launch_bounds__(256) wave_unpack_kernel(int64_t N, int64_t out0, int64_t n_out, const int32_t* __restrict__ perm,
-                                                          const double* __restrict__ Wt, double* __restrict__ out) {
-    __shared__ double s[C][32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int64_t g = blockIdx.y;
-    const int64_t v0 = (int64_t)blockIdx.x * 32;
-    for (int vv = ty; vv < 32; vv += 8) {
-        const int64_t v = v0 + vv;
-        if (v < N)
+// Coefficient rows aligned with the block pattern: cg[j][3] and / or cw[j][2] for block j = (row v, column u).
+__global__ void __launch_bounds__(128) wave_coef_kernel(mof_mesh_dev M, double* __restrict__ cw, double* __restrict__ cg) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < M.n_vertices) mof_wave_coef_row_body(M, v, cw, cg);
+}
+
+// One sparse row product per (vertex, frame).  C = 2: coefficients (alpha, beta) -> wave speed (T,N);
+// C = 3: coefficients of grad_point -> (T,N,3).  GP = 32-frame groups a CTA takes in one pass (blockIdx.y counts
+// passes): the column indices and coefficients read from shared memory serve GP groups, and a warp has GP x 8 ring
+// lines in flight per vertex.
+template <int C, int GP>
+__global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
+    int64_t N, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+    const double* __restrict__ coef, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first, int64_t T_trial,
+    const double* __restrict__ It, double inv_dt, int phase_mode, double* __restrict__ out) {
+    constexpr int OC = C == 3 ? 3 : 1;                 // doubles written per (vertex, frame)
+    constexpr int LD = kTileVerts * OC + 1;            // odd row length: both sides of the transpose are conflict-free
+    __shared__ double s_out[GP * 32 * LD];
+    __shared__ __align__(16) double s_coef[kStageEntries * C];
+    __shared__ int32_t s_col[kStageEntries];
+    __shared__ int32_t s_rp[kTileVerts + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t v0 = (int64_t)blockIdx.x * kTileVerts;
+    const int64_t g0 = (int64_t)blockIdx.y * GP;
+    const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
+    const int64_t v_end = v0 + kTileVerts < N ? v0 + kTileVerts : N;
+    // ---- the tile's block rows: row pointers, column indices and coefficients in one coalesced pass
+    const int32_t e0 = rowptr[v0], e1 = rowptr[v_end];
+    const int ne = e1 - e0 < kStageEntries ? e1 - e0 : kStageEntries;
+    if (tid <= kTileVerts) s_rp[tid] = rowptr[v0 + tid < N ? v0 + tid : N];
+    for (int i = tid; i < ne; i += 256) s_col[i] = col[e0 + i];
+    for (int i = tid; i < ne * C; i += 256) s_coef[i] = coef[(size_t)e0 * C + i];
+    __syncthreads();
+
+    // value of vertex u in this lane's frame of group g0 + gp: It_l[gp][u * 32]; a pass that reaches past the last group
+    // computes its first group twice and writes it once
+    const double* It_l[GP];
 #pragma unroll
-            for (int c = 0; c < C; ++c) s[c][vv][tx] = Wt[((size_t)(g * N + v) * C + c) * MOF_W + tx];
+    for (int gp = 0; gp < GP; ++gp) It_l[gp] = It + mof_ix_sca(N, g0 + gp < G ? g0 + gp : g0, 0) + lane;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const int vv = warp * 4 + i;
+        const int64_t v = v0 + vv;
+        if (v >= N) break;                                                  // warp-uniform
+        const int j0 = s_rp[vv] - e0, cnt = s_rp[vv + 1] - s_rp[vv];
+        double acc[GP][C];
+#pragma unroll
+        for (int gp = 0; gp < GP; ++gp)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[gp][c] = 0.0;
+        if (j0 + cnt <= ne) {                                               // the whole row is staged (always, up to valence 11)
+            // eight slots, straight-line: a slot past the end of the row re-reads the row's last entry (an L1 hit) and
+            // its product is discarded, so all loads of a vertex are in flight together and there is no branch ladder
+            const int last = cnt - 1;                                       // cnt >= 1: the diagonal block
+            double val[GP][8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const size_t u = (size_t)s_col[j0 + (k < last ? k : last)] * MOF_W;
+#pragma unroll
+                for (int gp = 0; gp < GP; ++gp) val[gp][k] = It_l[gp][u];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int kk = j0 + (k < last ? k : last);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const double w = s_coef[kk * C + c];
+#pragma unroll
+                    for (int gp = 0; gp < GP; ++gp) {
+                        const double f = fma(w, val[gp][k], acc[gp][c]);
+                        acc[gp][c] = k < cnt ? f : acc[gp][c];
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int k = 8; k < cnt; ++k) {
+                const size_t u = (size_t)s_col[j0 + k] * MOF_W;
+#pragma unroll
+                for (int gp = 0; gp < GP; ++gp) {
+                    const double x = It_l[gp][u];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[gp][c] = fma(s_coef[(j0 + k) * C + c], x, acc[gp][c]);
+                }
+            }
+        } else {                                                            // a long row beyond the staged entries: same order from global
+            const int32_t* cj = col + e0 + j0;
+            const double* kj = coef + (size_t)(e0 + j0) * C;
+#pragma unroll 1
+            for (int k = 0; k < cnt; ++k) {
+                const size_t u = (size_t)cj[k] * MOF_W;
+#pragma unroll
+                for (int gp = 0; gp < GP; ++gp) {
+                    const double x = It_l[gp][u];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[gp][c] = fma(kj[(size_t)k * C + c], x, acc[gp][c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int gp = 0; gp < GP; ++gp) {
+            double* so = s_out + gp * 32 * LD + lane * LD + vv * OC;
+            if (C == 3) {
+#pragma unroll
+                for (int c = 0; c < OC; ++c) so[c] = acc[gp][c];
+            } else {
+                // time derivative: the neighbours in time are the adjacent lanes; the lanes at the ends of the group fetch
+                // theirs from the next / previous group
+                const int64_t r = (g0 + gp) * 32 + lane;                    // row of the call
+                const int64_t t = t_first + r;                              // frame of the trial
+                const double* Iv = It + (size_t)v * MOF_W;                  // It[gg][v][ll] = Iv[gg * N * 32 + ll]
+                auto at = [&](int64_t row) { return Iv[(size_t)(row >> 5) * N * MOF_W + (row & 31)]; };
+                const double cur = It_l[gp][(size_t)v * MOF_W];
+                double prev = __shfl_up_sync(kFullMask, cur, 1), next = __shfl_down_sync(kFullMask, cur, 1);
+                if (lane == 0 && r > 0 && r < n_rows) prev = at(r - 1);
+                if (lane == 31 && r + 1 < n_rows) next = at(r + 1);
+                double td = 0.0;
+                if (r < n_rows) {
+                    const bool first = t == 0, last_t = t == T_trial - 1;
+                    double far2 = 0.0;                                      // np.gradient's one-sided ends reach two frames in
+                    if (!phase_mode && first) far2 = at(r + 2);
+                    else if (!phase_mode && last_t && r >= 2) far2 = at(r - 2);
+                    td = mof_wave_td_body(phase_mode, first, last_t, T_trial, cur, prev, next, far2, inv_dt);
+                }
+                so[0] = mof_wave_speed_body(td, acc[gp][0], acc[gp][1 % C]);
+            }
+        }
     }
     __syncthreads();
-    const int64_t v = v0 + tx;
-    if (v >= N) return;
-    const int64_t o = perm[v];
-    for (int fr = ty; fr < 32; fr += 8) {
-        const int64_t k = g * 32 + fr - out0;
-        if (k >= 0 && k < n_out)
+    // ---- transposed write: thread column tx walks the tile's doubles of one frame row, 8 rows per pass
+    const int tx = tid & 31, ty = tid >> 5;
 #pragma unroll
-            for (int c = 0; c < C; ++c) out[((size_t)k * N + o) * C + c] = s[c][tx][fr];
+    for (int gp = 0; gp < GP; ++gp) {
+        if (g0 + gp >= G) break;
+        for (int fr = ty; fr < 32; fr += 8) {
+            const int64_t k = (g0 + gp) * 32 + fr - out0;
+            if (k < 0 || k >= n_out) continue;
+#pragma unroll
+            for (int c = 0; c < OC; ++c) {
+                const int idx = tx + 32 * c;                                // position inside the tile's row piece
+                const int vv = idx / OC;
+                if (v0 + vv < N) out[((size_t)k * N + perm[v0 + vv]) * OC + (idx - vv * OC)] = s_out[gp * 32 * LD + fr * LD + idx];
+            }
+        }
     }
 }
 
-// Ring record of a vertex: its incident faces (ascending, the order of S5:161-166) as {face, v0, v1, v2},
-// kRingFaces slots of four int32 (face = -1: empty; a vertex with more faces keeps the rest in the contributor
-// list and sets slot kRingFaces-1's face to -2).  One coalesced 128-byte load gives a warp every index it
-// needs, so the gathers of a vertex are all independent instead of a centry -> tri -> value chain per face.
-constexpr int kRingFaces = 8;
+struct wave_work {
+    double *It, *cw, *cg;
+    int64_t total;
+};
 
-// ... and the vertex constants the per-frame arithmetic would otherwise recompute in every lane: 1 / area sum of the
-// ring (S5:169), the plane normal e1 x e2 and 1 / |n|^2 (S5:177-179), 1 / |e1|^2, 1 / |e2|^2 (S5:189-190).  fp64
-// divisions cost ~25 instructions each; as reciprocals computed once per vertex they are a multiplication per frame
-// (one rounding more than the reference's division, 1 ulp, inside the 1e-12 parity tolerance).
-constexpr int kVertexConsts = 8;      // inv_area_sum, n[3], inv_nn, inv_e1e1, inv_e2e2, pad
-
-__global__ void wave_ring_kernel(mof_mesh_dev M, int32_t* __restrict__ ring, double* __restrict__ vc) {
-    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= M.n_vertices) return;
-    const int32_t bd = M.diag[v];
-    const int32_t q0 = M.cptr[bd], q1 = M.cptr[bd + 1];
-    {
-        double asum = 0.0;
-        for (int32_t q = q0; q < q1; ++q) asum += M.areas[M.centry[q] >> 4];      // same order as the reference's sum
-        const double* e1 = M.e + 6 * v;
-        const double* e2 = e1 + 3;
-        const double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
-        double* c = vc + (size_t)v * kVertexConsts;
-        c[0] = 1.0 / asum;
-        c[1] = nx; c[2] = ny; c[3] = nz;
-        c[4] = 1.0 / (nx * nx + ny * ny + nz * nz);
-        c[5] = 1.0 / (e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
-        c[6] = 1.0 / (e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
-        c[7] = 0.0;
-    }
-    int32_t* r = ring + (size_t)v * kRingFaces * 4;
-    for (int k = 0; k < kRingFaces; ++k) {
-        const int32_t q = q0 + k;
-        const bool on = q < q1;
-        const int32_t f = on ? M.centry[q] >> 4 : -1;
-        r[4 * k] = (k == kRingFaces - 1 && q1 - q0 > kRingFaces) ? -2 : f;
-        r[4 * k + 1] = on ? M.tri[3 * f] : 0;
-        r[4 * k + 2] = on ? M.tri[3 * f + 1] : 0;
-        r[4 * k + 3] = on ? M.tri[3 * f + 2] : 0;
-    }
+// work = the packed signal It[G][N][32], then cw[nb][2] (wave speed asked for), then cg[nb][3] (grad_point asked for)
+wave_work wave_layout(const mof_mesh_dev* mesh, int64_t n_rows, bool want_grad, bool want_wave, double* work) {
+    const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
+    const int64_t off_cw = G * mesh->n_vertices * MOF_W;
+    const int64_t off_cg = off_cw + (want_wave ? 2 * mesh->n_blocks : 0);
+    wave_work w;
+    w.total = off_cg + (want_grad ? 3 * mesh->n_blocks : 0);
+    w.It = work;
+    w.cw = work && want_wave ? work + off_cw : nullptr;
+    w.cg = work && want_grad ? work + off_cg : nullptr;
+    return w;
 }
 
-// One warp per internal vertex, lane = frame (row 32 g + lane of the call).
-__global__ void __launch_bounds__(256) wave_stencil_kernel(mof_mesh_dev M, const int32_t* __restrict__ ring,
-                                                           const double* __restrict__ vc, int64_t n_rows,
-                                                           int64_t t_first, int64_t T_trial, const double* __restrict__ It,
-                                                           double dt, int phase_mode, double* __restrict__ Gt,
-                                                           double* __restrict__ Wt) {
-    const int64_t N = M.n_vertices;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t v = (int64_t)blockIdx.x * 8 + warp;
-    const int64_t g = blockIdx.y;
-    if (v >= N) return;
-    const double* It_l = It + mof_ix_sca(N, g, 0) + lane;
-    // area-weighted mean of the face gradients, faces ascending (S5:161-169)
-    double gx = 0.0, gy = 0.0, gz = 0.0;
-    const int32_t rec = ring[(size_t)v * kRingFaces * 4 + lane];
-    const double* kc = vc + (size_t)v * kVertexConsts;
-    auto add_face = [&](int64_t f, int64_t t0, int64_t t1, int64_t t2) {
-        const double* gw = M.grad_w + 9 * f;
-        const double I0 = It_l[(size_t)t0 * MOF_W], I1 = It_l[(size_t)t1 * MOF_W], I2 = It_l[(size_t)t2 * MOF_W];
-        const double A = M.areas[f];
-        gx += (I0 * gw[0] + I1 * gw[3] + I2 * gw[6]) * A;                   // S5:154-158,165
-        gy += (I0 * gw[1] + I1 * gw[4] + I2 * gw[7]) * A;
-        gz += (I0 * gw[2] + I1 * gw[5] + I2 * gw[8]) * A;
-    };
-    bool overflow = false;
-#pragma unroll
-    for (int k = 0; k < kRingFaces; ++k) {
-        const int32_t f = __shfl_sync(kFullMask, rec, 4 * k);
-        const int32_t t0 = __shfl_sync(kFullMask, rec, 4 * k + 1), t1 = __shfl_sync(kFullMask, rec, 4 * k + 2),
-                      t2 = __shfl_sync(kFullMask, rec, 4 * k + 3);
-        if (f >= 0) add_face(f, t0, t1, t2);
-        else if (f == -2) overflow = true;
+// groups per pass of the wave-speed kernel: 2 by default, MOF_WAVE_GROUPS=1 or mof_wave_set_groups_per_pass(1) selects
+// the one-group variant (kept for the comparison in profiles/)
+int g_wave_groups = 0;
+int wave_groups_per_pass() {
+    if (g_wave_groups == 0) {
+        const char* e = getenv("MOF_WAVE_GROUPS");
+        g_wave_groups = e && e[0] == '1' ? 1 : 2;
     }
-    if (overflow) {                                  // more than kRingFaces faces: the rest straight from the contributor list
-        const int32_t bd = M.diag[v];
-        for (int32_t q = M.cptr[bd] + kRingFaces - 1; q < M.cptr[bd + 1]; ++q) {
-            const int64_t f = M.centry[q] >> 4;
-            add_face(f, M.tri[3 * f], M.tri[3 * f + 1], M.tri[3 * f + 2]);
-        }
+    return g_wave_groups;
+}
+
+int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
+                     int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, cudaStream_t st) {
+    const int64_t N = mesh->n_vertices;
+    const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
+    if (grad_point) {
+        wave_rows_kernel<3, 1><<<dim3(mof_cdiv(N, kTileVerts), (unsigned)G), 256, 0, st>>>(
+            N, mesh->rowptr, mesh->col, mesh->perm, w.cg, n_rows, out0, n_out, t_first, T_trial, w.It, 1.0 / dt, phase_mode, grad_point);
+        MOF_LAUNCH_CHECK("wave_rows_kernel<3,1>");
     }
-    gx *= kc[0]; gy *= kc[0]; gz *= kc[0];                                     // S5:169
-    if (Gt) {
-        double* gp = Gt + ((size_t)(g * N + v) * 3) * MOF_W + lane;
-        gp[0] = gx; gp[MOF_W] = gy; gp[2 * MOF_W] = gz;
+    if (wave) {
+        if (wave_groups_per_pass() == 2)
+            wave_rows_kernel<2, 2><<<dim3(mof_cdiv(N, kTileVerts), (unsigned)((G + 1) / 2)), 256, 0, st>>>(
+                N, mesh->rowptr, mesh->col, mesh->perm, w.cw, n_rows, out0, n_out, t_first, T_trial, w.It, 1.0 / dt, phase_mode, wave);
+        else
+            wave_rows_kernel<2, 1><<<dim3(mof_cdiv(N, kTileVerts), (unsigned)G), 256, 0, st>>>(
+                N, mesh->rowptr, mesh->col, mesh->perm, w.cw, n_rows, out0, n_out, t_first, T_trial, w.It, 1.0 / dt, phase_mode, wave);
+        MOF_LAUNCH_CHECK("wave_rows_kernel<2,*>");
     }
-    if (!Wt) return;
-    const double* e1 = M.e + 6 * v;
-    const double* e2 = e1 + 3;
-    // project_vector_to_plane (S5:173-180)
-    const double nx = kc[1], ny = kc[2], nz = kc[3];
-    const double s = (gx * nx + gy * ny + gz * nz) * kc[4];
-    const double px = gx - s * nx, py = gy - s * ny, pz = gz - s * nz;
-    // express_vector_on_basis (S5:182-191) and its norm (S5:117)
-    const double al = (px * e1[0] + py * e1[1] + pz * e1[2]) * kc[5];
-    const double be = (px * e2[0] + py * e2[1] + pz * e2[2]) * kc[6];
-    const double dis = sqrt(al * al + be * be);
-    // time derivative: the neighbours in time are the adjacent lanes; the lanes at the ends of the group fetch
-    // theirs from the next / previous group
-    const int64_t r = g * 32 + lane;                                        // row of the call
-    const int64_t t = t_first + r;                                          // frame of the trial
-    const double* Iv = It + (size_t)v * MOF_W;                              // It[gg][v][ll] = Iv[gg * N * 32 + ll]
-    auto at = [&](int64_t row) { return Iv[(size_t)(row >> 5) * N * MOF_W + (row & 31)]; };
-    const double c = It_l[(size_t)v * MOF_W];
-    double prev = __shfl_up_sync(kFullMask, c, 1), next = __shfl_down_sync(kFullMask, c, 1);
-    if (lane == 0 && r > 0) prev = at(r - 1);
-    if (lane == 31 && r + 1 < n_rows) next = at(r + 1);
-    double td = 0.0;
-    if (r < n_rows) {
-        if (phase_mode) {                                                   // S5:60-77
-            if (T_trial == 1) td = 0.0;
-            else if (t == 0) td = angle_subtract(next, c) / dt;
-            else if (t == T_trial - 1) td = angle_subtract(c, prev) / dt;
-            else td = angle_subtract(next, prev) / (2 * dt);
-        } else {                                                            // np.gradient(axis=0, edge_order=2) / dt, S5:24
-            if (t == 0) td = (-1.5 * c + 2.0 * next - 0.5 * at(r + 2)) / dt;
-            else if (t == T_trial - 1) td = (1.5 * c - 2.0 * prev + 0.5 * at(r - 2)) / dt;
-            else td = ((next - prev) / 2.0) / dt;
-        }
-    }
-    Wt[mof_ix_sca(N, g, v) + lane] = td / dis;                              // S5:121
+    return 0;
 }
 
 }  // namespace
 
-extern "C" int64_t mof_wave_work_doubles(int64_t n_vertices, int64_t n_rows, int want_grad, int want_wave) {
-    const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
-    // signal + results in the frame-minor layout, then the ring records (kRingFaces x 4 int32 per vertex)
-    return G * n_vertices * MOF_W * (1 + (want_grad ? 3 : 0) + (want_wave ? 1 : 0)) + n_vertices * (kRingFaces * 4 / 2 + kVertexConsts);
+extern "C" int mof_wave_set_groups_per_pass(int groups) {
+    MOF_REQUIRE(groups == 1 || groups == 2, "1 or 2");
+    g_wave_groups = groups;
+    return 0;
+}
+
+extern "C" int64_t mof_wave_work_doubles(const mof_mesh_dev* mesh, int64_t n_rows, int want_grad, int want_wave) {
+    if (!mesh || n_rows < 0) return -1;
+    return wave_layout(mesh, n_rows, want_grad != 0, want_wave != 0, nullptr).total;
 }
 
 extern "C" int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
@@ -234,43 +293,22 @@ extern "C" int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t 
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
     MOF_REQUIRE(G <= 65535, "at most 65535 x 32 rows per call");
     cudaStream_t st = mof_stream(stream);
-    double* It = work;
-    double* Gt = grad_point ? It + (size_t)G * N * MOF_W : nullptr;
-    double* Wt = wave ? It + (size_t)G * N * MOF_W * (grad_point ? 4 : 1) : nullptr;
-    dim3 tgrid(mof_cdiv(N, 32), (unsigned)G), tblock(32, 8);
-    int32_t* ring = reinterpret_cast<int32_t*>(It + (size_t)G * N * MOF_W * (1 + (grad_point ? 3 : 0) + (wave ? 1 : 0)));
-    double* vc = reinterpret_cast<double*>(ring + (size_t)N * kRingFaces * 4);
-    wave_ring_kernel<<<mof_cdiv(N, 256), 256, 0, st>>>(*mesh, ring, vc);
-    MOF_LAUNCH_CHECK("wave_ring_kernel");
-    wave_pack_kernel<<<tgrid, tblock, 0, st>>>(N, n_rows, mesh->perm, I, ld, It);
+    const wave_work w = wave_layout(mesh, n_rows, grad_point != nullptr, wave != nullptr, work);
+    wave_coef_kernel<<<mof_cdiv(N, 128), 128, 0, st>>>(*mesh, w.cw, w.cg);
+    MOF_LAUNCH_CHECK("wave_coef_kernel");
+    wave_pack_kernel<<<dim3(mof_cdiv(N, 32), (unsigned)G), dim3(32, 8), 0, st>>>(N, n_rows, mesh->perm, I, ld, w.It);
     MOF_LAUNCH_CHECK("wave_pack_kernel");
-    wave_stencil_kernel<<<dim3(mof_cdiv(N, 8), (unsigned)G), 256, 0, st>>>(*mesh, ring, vc, n_rows, t_first, T_trial, It, dt, phase_mode, Gt, Wt);
-    MOF_LAUNCH_CHECK("wave_stencil_kernel");
-    if (grad_point) {
-        wave_unpack_kernel<3><<<tgrid, tblock, 0, st>>>(N, out0, n_out, mesh->perm, Gt, grad_point);
-        MOF_LAUNCH_CHECK("wave_unpack_kernel<3>");
-    }
-    if (wave) {
-        wave_unpack_kernel<1><<<tgrid, tblock, 0, st>>>(N, out0, n_out, mesh->perm, Wt, wave);
-        MOF_LAUNCH_CHECK("wave_unpack_kernel<1>");
-    }
-    return 0;
+    return wave_rows_launch(mesh, w, n_rows, out0, n_out, t_first, T_trial, dt, phase_mode, grad_point, wave, st);
 }
 
-// Roofline hook (bench.py): the stencil alone on a work buffer that mof_wave_speed has already packed.
-extern "C" int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t t_first, int64_t T_trial, double dt,
-                                int phase_mode, int want_grad, int want_wave, double* work, void* stream) {
-    MOF_REQUIRE(mesh && work && n_rows > 0 && (want_grad || want_wave), "bad arguments");
-    const int64_t N = mesh->n_vertices;
-    const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
-    MOF_REQUIRE(G <= 65535, "at most 65535 x 32 rows per call");
-    double* It = work;
-    double* Gt = want_grad ? It + (size_t)G * N * MOF_W : nullptr;
-    double* Wt = want_wave ? It + (size_t)G * N * MOF_W * (want_grad ? 4 : 1) : nullptr;
-    const int32_t* ring = reinterpret_cast<const int32_t*>(It + (size_t)G * N * MOF_W * (1 + (want_grad ? 3 : 0) + (want_wave ? 1 : 0)));
-    const double* vc = reinterpret_cast<const double*>(ring + (size_t)N * kRingFaces * 4);
-    wave_stencil_kernel<<<dim3(mof_cdiv(N, 8), (unsigned)G), 256, 0, mof_stream(stream)>>>(*mesh, ring, vc, n_rows, t_first, T_trial, It, dt,
-                                                                                          phase_mode, Gt, Wt);
-    MOF_LAUNCH_CHECK("wave_stencil_kernel");
-    return 0;
+// Roofline hook (bench.py): the row kernel(s) alone on a work buffer that a mof_wave_speed call with the same mesh,
+// n_rows and outputs has already filled (packed signal + coefficient rows).
+extern "C" int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
+                                int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, double* work,
+                                void* stream) {
+    MOF_REQUIRE(mesh && work && n_rows > 0 && (grad_point || wave) && dt != 0.0, "bad arguments");
+    MOF_REQUIRE(out0 >= 0 && n_out >= 0 && out0 + n_out <= n_rows, "output rows outside the rows passed in");
+    MOF_REQUIRE((n_rows + MOF_W - 1) / MOF_W <= 65535, "at most 65535 x 32 rows per call");
+    const wave_work w = wave_layout(mesh, n_rows, grad_point != nullptr, wave != nullptr, work);
+    return wave_rows_launch(mesh, w, n_rows, out0, n_out, t_first, T_trial, dt, phase_mode, grad_point, wave, mof_stream(stream));
 }

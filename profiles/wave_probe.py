@@ -1,0 +1,103 @@
+"""Config 5 on one GPU, kernel by kernel: S5 wave speed of a T-frame wrapped-phase trial on the pial-like ico7 mesh.
+
+    python profiles/wave_probe.py [--level 7] [--frames 1000] [--steps 10] [--orders 0,1]
+
+For every mesh ordering asked for (0 = reference vertex order, what S5_compute_wave_v.py uses; 1 = Cuthill-McKee, the
+round-2 first version's) and both settings of groups per pass it times, with CUDA events on the launching stream after
+warm-up: the whole mof_wave_speed call (coefficient rows + transpose in + row kernel), the row kernel alone
+(mof_wave_stencil), and reports them against the algorithmic 16 N bytes per frame.  It also checks that every variant
+produces the same array bit for bit (the arithmetic per (vertex, frame) does not depend on the ordering of the tiles) and
+compares a few frames with the numpy oracle.  One JSON line on stdout.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from manifold_based_optical_flow_method_b200 import _lib, synthetic  # noqa: E402
+from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5  # noqa: E402
+from manifold_based_optical_flow_method_b200.mesh import MeshOperator  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--level", type=int, default=7)
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--orders", default="0,1")
+    ap.add_argument("--oracle-frames", type=int, default=4)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    coords, tris, normals, areas = synthetic.pial_like(args.level)
+    N, T = len(coords), args.frames
+    t_k = synthetic.time_axis(T, 512.0)
+    phases = synthetic.wrapped_phase(coords, t_k, seed=1, omega=500.0)
+    from oracle import mof_oracle
+    e = mof_oracle.orthonormal_basis(normals)
+    d = torch.from_numpy(np.ascontiguousarray(phases)).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak = float(json.load(fh)["hbm_gbs"])
+    except Exception:
+        pass
+    out = {"n_vertices": N, "frames": T, "steps": args.steps, "algorithmic_bytes": 16.0 * N * T, "peak_gbs": peak, "variants": []}
+    first = None
+    for order in [int(x) for x in args.orders.split(",")]:
+        nrm = np.zeros_like(coords)
+        nrm[:, 2] = 1.0
+        op = MeshOperator(coords, nrm, tris, areas, reorder=order)
+        op.use_geometry(None, e, None, areas)
+        ms = op.struct()
+        work = torch.empty((int(lib.mof_wave_work_doubles(ctypes.byref(ms), T, 0, 1)),), dtype=torch.float64, device=dev)
+        wv = torch.empty((T, N), dtype=torch.float64, device=dev)
+        for gp in (1, 2):
+            _lib.check(lib.mof_wave_set_groups_per_pass(gp))
+            wv.fill_(float("nan"))
+            for _ in range(3):
+                s5.wave_speed_device(op, d, 0, T, 0, T, 1 / 512.0, True, work=work, wave_out=wv)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                s5.wave_speed_device(op, d, 0, T, 0, T, 1 / 512.0, True, work=work, wave_out=wv)
+            e1.record()
+            for _ in range(args.steps):
+                _lib.check(lib.mof_wave_stencil(ctypes.byref(ms), T, 0, T, 0, T, 1 / 512.0, 1, None, wv.data_ptr(), work.data_ptr(), st))
+            e2.record()
+            torch.cuda.synchronize()
+            call_ms, rows_ms = e0.elapsed_time(e1) / args.steps, e1.elapsed_time(e2) / args.steps
+            if first is None:
+                first = wv.clone()
+                same = True
+            else:
+                same = bool(torch.equal(torch.nan_to_num(wv, nan=0.0, posinf=1e300, neginf=-1e300),
+                                        torch.nan_to_num(first, nan=0.0, posinf=1e300, neginf=-1e300)))
+            rec = {"order": order, "groups_per_pass": gp, "call_ms": call_ms, "rows_ms": rows_ms, "coef_plus_pack_ms": call_ms - rows_ms,
+                   "call_gbs": 16.0 * N * T / call_ms / 1e6, "rows_gbs": 16.0 * N * T / rows_ms / 1e6, "bit_identical_to_first": same}
+            if peak:
+                rec["call_frac"], rec["rows_frac"] = rec["call_gbs"] / peak, rec["rows_gbs"] / peak
+            out["variants"].append(rec)
+        del op, work, wv
+    k = args.oracle_frames
+    if k:
+        wo = mof_oracle.wave_velocity(coords, tris, areas, phases[:k + 1], 1 / 512.0, e, phase=True)[:k]
+        got = first[:k].cpu().numpy()
+        m = np.isfinite(wo)
+        out["rel_l2_vs_oracle"] = float(np.linalg.norm(got[m] - wo[m]) / np.linalg.norm(wo[m]))
+    _lib.check(lib.mof_wave_set_groups_per_pass(2))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

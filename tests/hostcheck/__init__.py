@@ -34,6 +34,9 @@ def load():
     lib.hc_detect.argtypes = [I64, I64, P, P, P, D, D, P, P, P, P, P, P]
     lib.hc_winding.argtypes = [I64, P, P, P, P, P, P, I32, P, P, P, P]
     lib.hc_winding.restype = None
+    lib.hc_wave_coef.argtypes = [P, P, P]
+    lib.hc_wave_rows.argtypes = [P, I32, I64, I64, I64, I64, I64, P, I64, D, I32, P, P]
+    lib.hc_wave_coef.restype = lib.hc_wave_rows.restype = None
     for f in (lib.hc_geom, lib.hc_a2, lib.hc_pack, lib.hc_assemble, lib.hc_spmv, lib.hc_tangent, lib.hc_detect,
               lib.hc_sweep_back, lib.hc_sweep_fwd):
         f.restype = None

@@ -242,4 +242,39 @@ void hc_winding(int64_t N, const double* coords, const double* V, const double* 
     *closest = arg;
     *type = flag;
 }
+
+// K6: coefficient rows (wave_coef_kernel) ...
+void hc_wave_coef(const mof_mesh_dev* M, double* cw, double* cg) {
+    for (int64_t v = 0; v < M->n_vertices; ++v) mof_wave_coef_row_body(*M, v, cw, cg);
+}
+
+// ... and the row products of wave_rows_kernel on the packed signal It[G][N][32] (internal order), written to the
+// caller's (n_out, N[, 3]) array in reference order.  C = 2: coef = cw -> wave speed; C = 3: coef = cg -> grad_point.
+void hc_wave_rows(const mof_mesh_dev* M, int C, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first, int64_t T_trial,
+                  const double* I, int64_t ld, double dt, int phase_mode, const double* coef, double* out) {
+    const int64_t N = M->n_vertices, G = (n_rows + MOF_W - 1) / MOF_W;
+    std::vector<double> It((size_t)G * N * MOF_W, 0.0);                      // wave_pack_kernel
+    for (int64_t k = 0; k < n_rows; ++k)
+        for (int64_t v = 0; v < N; ++v) It[mof_ix_sca(N, k / MOF_W, v) + k % MOF_W] = I[k * ld + M->perm[v]];
+    auto at = [&](int64_t v, int64_t row) { return It[mof_ix_sca(N, row >> 5, v) + (row & 31)]; };
+    const double inv_dt = 1.0 / dt;
+    for (int64_t r = out0; r < out0 + n_out; ++r)
+        for (int64_t v = 0; v < N; ++v) {
+            double acc[3] = {0.0, 0.0, 0.0};
+            for (int32_t j = M->rowptr[v]; j < M->rowptr[v + 1]; ++j)
+                for (int c = 0; c < C; ++c) acc[c] = fma(coef[(size_t)j * C + c], at(M->col[j], r), acc[c]);
+            const size_t o = (size_t)(r - out0) * N + M->perm[v];
+            if (C == 3) {
+                for (int c = 0; c < 3; ++c) out[3 * o + c] = acc[c];
+                continue;
+            }
+            const int64_t t = t_first + r;
+            const bool first = t == 0, last = t == T_trial - 1;
+            const double cur = at(v, r), prev = r > 0 ? at(v, r - 1) : 0.0, next = r + 1 < n_rows ? at(v, r + 1) : 0.0;
+            double far2 = 0.0;
+            if (!phase_mode && first) far2 = at(v, r + 2);
+            else if (!phase_mode && last && r >= 2) far2 = at(v, r - 2);
+            out[o] = mof_wave_speed_body(mof_wave_td_body(phase_mode, first, last, T_trial, cur, prev, next, far2, inv_dt), acc[0], acc[1]);
+        }
+}
 }

@@ -137,3 +137,71 @@ def test_wave_speed_full_size_config5():
     go = mof_oracle.grad_M_I(coords, tris, phases, areas)
     assert rel_l2(grad.cpu().numpy(), go) <= 1e-13
     assert rel_l2(wave.cpu().numpy(), wo) <= 1e-12
+
+
+def _host_wave(case, reorder):
+    """The K6 kernel bodies (csrc/mof_bodies.h) in the plain loops of tests/hostcheck, CPU only."""
+    import ctypes
+    from test_host_logic import HostMesh
+    g = load_golden(case)
+    hm = HostMesh(g, reorder)
+    P = hm.P
+    hm.e[:] = np.asarray(g["e"], dtype=np.float64).reshape(-1, 2, 3)[P.perm]      # S5 is handed e by its caller
+    cw, cg = np.zeros((P.n_blocks, 2)), np.zeros((P.n_blocks, 3))
+    ms = hm.struct()
+    hm.hc.hc_wave_coef(ctypes.byref(ms), cw.ctypes.data, cg.ctypes.data)
+
+    def rows(data, phase, want_grad=False, a=0, b=None, k0=0, k1=None):
+        """frames [k0, k1) of the trial `data` from its rows [a, b)"""
+        T, N = data.shape
+        b, k1 = T if b is None else b, T if k1 is None else k1
+        part = np.ascontiguousarray(data[a:b], dtype=np.float64)
+        out = np.full((k1 - k0, N, 3) if want_grad else (k1 - k0, N), np.nan)
+        coef = cg if want_grad else cw
+        hm.hc.hc_wave_rows(ctypes.byref(ms), 3 if want_grad else 2, b - a, k0 - a, k1 - k0, a, T, part.ctypes.data, N,
+                           ctypes.c_double(float(g["dt"])), 1 if phase else 0, coef.ctypes.data, out.ctypes.data)
+        return out
+    return g, rows
+
+
+@pytest.mark.parametrize("reorder", [0, 1])
+@pytest.mark.parametrize("case", CASES)
+def test_wave_bodies_match_reference_s5(case, reorder):
+    """Coefficient rows + row products (the formulation of csrc/wave.cu) against the outputs of the unmodified S5."""
+    g, rows = _host_wave(case, reorder)
+    assert rel_l2(rows(g["phases"], True), g["wave_velocity_phase"]) <= 1e-12
+    assert rel_l2(rows(g["potentials"], False), g["wave_velocity_amplitude"]) <= 1e-12
+    assert rel_l2(rows(g["phases"], True, want_grad=True), g["grad_point"]) <= 1e-13
+
+
+@pytest.mark.parametrize("phase", [True, False])
+def test_wave_bodies_shards_equal_whole_trial(phase):
+    """A shard computed from its rows plus the halo is bit-identical to the same frames of the whole trial."""
+    from manifold_based_optical_flow_method_b200.S5_compute_wave_v import halo_rows
+    from manifold_based_optical_flow_method_b200.distributed import shard_range
+    g, rows = _host_wave("s5_patch7", 0)
+    data = g["phases"] if phase else g["potentials"]
+    T = len(data)
+    whole = rows(data, phase)
+    for world in (2, 3, T):
+        for r in range(world):
+            k0, k1 = shard_range(T, world, r)
+            if k1 == k0:
+                continue
+            a, b = halo_rows(k0, k1, T, phase)
+            assert np.array_equal(rows(data, phase, a=a, b=b, k0=k0, k1=k1), whole[k0:k1], equal_nan=True), (world, r)
+
+
+def test_angle_subtract_body_is_numpy_mod():
+    """The range branches of mof_angle_subtract_body are exactly np.mod(f1 - f2 + pi, 2 pi) - pi (S5:230), also for
+    arguments outside [-pi, pi] (a two-frame phase trial through the harness: wave = td / 1 on a flat unit mesh is
+    overkill, so the formula is restated here and compared on the values the kernel branches on)."""
+    from oracle import mof_oracle
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.uniform(-np.pi, np.pi, 4000), rng.uniform(-30, 30, 4000), [np.pi, -np.pi, 0.0, 2 * np.pi, 3 * np.pi]])
+    b = np.concatenate([rng.uniform(-np.pi, np.pi, 4000), rng.uniform(-30, 30, 4000), [-np.pi, np.pi, 0.0, -2 * np.pi, -np.pi]])
+    d = a - b + np.pi
+    two_pi = 2 * np.pi
+    m = np.where((d >= 0) & (d < two_pi), d, np.where((d < 0) & (d > -two_pi), d + two_pi,
+                 np.where((d >= two_pi) & (d < 2 * two_pi), d - two_pi, np.mod(d, two_pi))))
+    assert np.array_equal(m - np.pi, mof_oracle.angle_subtract(a, b))
