@@ -447,10 +447,11 @@ MOF_HD double mof_angle_subtract_body(double a, double b) {
     const double kPi = 3.141592653589793, kTwoPi = 2.0 * 3.141592653589793;
     const double d = MOF_ADD(MOF_ADD(a, -b), kPi);
     double m;
-    if (d >= 0.0 && d < kTwoPi) m = d;
-    else if (d < 0.0 && d > -kTwoPi) m = MOF_ADD(d, kTwoPi);
-    else if (d >= kTwoPi && d < 2.0 * kTwoPi) m = MOF_ADD(d, -kTwoPi);
-    else {
+    if (d > -kTwoPi && d < 2.0 * kTwoPi) {
+        m = d;
+        if (d < 0.0) m = MOF_ADD(d, kTwoPi);
+        if (d >= kTwoPi) m = MOF_ADD(d, -kTwoPi);
+    } else {
         m = fmod(d, kTwoPi);
         if (m != 0.0 && m < 0.0) m = MOF_ADD(m, kTwoPi);      // numpy's mod takes the sign of the divisor
     }

@@ -39,7 +39,7 @@ namespace {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kTileVerts = 32;        // vertices per CTA of wave_rows_kernel
-constexpr int kStageEntries = 384;    // block-row entries of a tile staged in shared memory (12 per row; longer rows read global)
+constexpr int kSlots = 8;            // block-row entries per vertex staged in shared memory (valence <= 7; longer rows continue in global)
 
 // (rows, N) row-major, reference vertex order -> It[g][v][32], internal order (rows padded with 0)
 __global__ void __launch_bounds__(256) wave_pack_kernel(int64_t N, int64_t n_rows, const int32_t* __restrict__ perm,
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) wave_pack_kernel(int64_t N, int64_t n_row
     const int64_t o = v < N ? perm[v] : 0;
     for (int fr = ty; fr < 32; fr += 8) {
         const int64_t k = g * 32 + fr;
-        s[fr][tx] = (k < n_rows && v < N) ? I[k * ld + o] : 0.0;
+        s[fr][tx] = (k < n_rows && v < N) ? __ldcs(I + k * ld + o) : 0.0;          // read once: evict first
     }
     __syncthreads();
     for (int vv = ty; vv < 32; vv += 8) {
@@ -71,6 +71,10 @@ __global__ void __launch_bounds__(128) wave_coef_kernel(mof_mesh_dev M, double* 
 // C = 3: coefficients of grad_point -> (T,N,3).  GP = 32-frame groups a CTA takes in one pass (blockIdx.y counts
 // passes): the column indices and coefficients read from shared memory serve GP groups, and a warp has GP x 8 ring
 // lines in flight per vertex.
+// The tile's block rows are staged as kSlots padded slots per vertex (thread = (row, slot), one coalesced pass): a slot
+// past the end of a row holds the vertex itself with zero coefficients, so the eight products of a vertex are straight-
+// line code with no selects; the entries of a row beyond kSlots (valence > 7) are read from global memory behind them,
+// in the same ascending column order.
 template <int C, int GP>
 __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
     int64_t N, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
@@ -78,87 +82,100 @@ __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
     const double* __restrict__ It, double inv_dt, int phase_mode, double* __restrict__ out) {
     constexpr int OC = C == 3 ? 3 : 1;                 // doubles written per (vertex, frame)
     constexpr int LD = kTileVerts * OC + 1;            // odd row length: both sides of the transpose are conflict-free
+    constexpr int CP = C == 3 ? 4 : 2;                 // doubles per staged slot: one (two) 16-byte shared loads
     __shared__ double s_out[GP * 32 * LD];
-    __shared__ __align__(16) double s_coef[kStageEntries * C];
-    __shared__ int32_t s_col[kStageEntries];
-    __shared__ int32_t s_rp[kTileVerts + 1];
+    __shared__ __align__(16) double s_coef[kTileVerts * kSlots * CP];
+    __shared__ __align__(16) int32_t s_col[kTileVerts * kSlots];
+    __shared__ int32_t s_j0[kTileVerts], s_cnt[kTileVerts];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t v0 = (int64_t)blockIdx.x * kTileVerts;
     const int64_t g0 = (int64_t)blockIdx.y * GP;
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
-    const int64_t v_end = v0 + kTileVerts < N ? v0 + kTileVerts : N;
-    // ---- the tile's block rows: row pointers, column indices and coefficients in one coalesced pass
-    const int32_t e0 = rowptr[v0], e1 = rowptr[v_end];
-    const int ne = e1 - e0 < kStageEntries ? e1 - e0 : kStageEntries;
-    if (tid <= kTileVerts) s_rp[tid] = rowptr[v0 + tid < N ? v0 + tid : N];
-    for (int i = tid; i < ne; i += 256) s_col[i] = col[e0 + i];
-    for (int i = tid; i < ne * C; i += 256) s_coef[i] = coef[(size_t)e0 * C + i];
+    {   // ---- stage the tile's block rows: thread = (row, slot)
+        const int row = tid >> 3, slot = tid & (kSlots - 1);
+        const int64_t v = v0 + row;
+        int32_t j0 = 0, cnt = 0;
+        if (v < N) { j0 = rowptr[v]; cnt = rowptr[v + 1] - j0; }
+        if (slot == 0) { s_j0[row] = j0; s_cnt[row] = cnt; }
+        int32_t u = v < N ? (int32_t)v : 0;
+        double w[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = 0.0;
+        if (slot < cnt) {
+            u = col[j0 + slot];
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] = coef[(size_t)(j0 + slot) * C + c];
+        }
+        s_col[tid] = u;
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_coef[tid * CP + c] = w[c];
+    }
     __syncthreads();
 
-    // value of vertex u in this lane's frame of group g0 + gp: It_l[gp][u * 32]; a pass that reaches past the last group
-    // computes its first group twice and writes it once
-    const double* It_l[GP];
+    // Offsets, relative to a vertex's first line It[0][v][0], of this lane's frame in group g0 + gp and of its neighbours
+    // in time (the previous / next frame of lane 0 / 31 lives in the neighbouring group's line).  A pass that reaches past
+    // the last group computes its first group twice and writes it once.
+    const int64_t group_stride = N * MOF_W;
+    int64_t o_cur[GP], o_prev[GP], o_next[GP];
 #pragma unroll
-    for (int gp = 0; gp < GP; ++gp) It_l[gp] = It + mof_ix_sca(N, g0 + gp < G ? g0 + gp : g0, 0) + lane;
+    for (int gp = 0; gp < GP; ++gp) {
+        const int64_t g = g0 + gp < G ? g0 + gp : g0;
+        const int64_t r = g * 32 + lane;
+        auto off = [&](int64_t row) { return (row >> 5) * group_stride + (row & 31); };
+        o_cur[gp] = off(r);
+        o_prev[gp] = off(r > 0 ? r - 1 : r);
+        o_next[gp] = off(r + 1 < G * 32 ? r + 1 : r);
+    }
 #pragma unroll 1
     for (int i = 0; i < 4; ++i) {
         const int vv = warp * 4 + i;
         const int64_t v = v0 + vv;
         if (v >= N) break;                                                  // warp-uniform
-        const int j0 = s_rp[vv] - e0, cnt = s_rp[vv + 1] - s_rp[vv];
+        const int4 ca = *reinterpret_cast<const int4*>(s_col + vv * kSlots), cb = *reinterpret_cast<const int4*>(s_col + vv * kSlots + 4);
+        const int32_t us[kSlots] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        double val[GP][kSlots];
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) {
+            const double* line = It + (size_t)us[k] * MOF_W;
+#pragma unroll
+            for (int gp = 0; gp < GP; ++gp) val[gp][k] = line[o_cur[gp]];
+        }
         double acc[GP][C];
 #pragma unroll
         for (int gp = 0; gp < GP; ++gp)
 #pragma unroll
             for (int c = 0; c < C; ++c) acc[gp][c] = 0.0;
-        if (j0 + cnt <= ne) {                                               // the whole row is staged (always, up to valence 11)
-            // eight slots, straight-line: a slot past the end of the row re-reads the row's last entry (an L1 hit) and
-            // its product is discarded, so all loads of a vertex are in flight together and there is no branch ladder
-            const int last = cnt - 1;                                       // cnt >= 1: the diagonal block
-            double val[GP][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const size_t u = (size_t)s_col[j0 + (k < last ? k : last)] * MOF_W;
+        for (int k = 0; k < kSlots; ++k) {
+            const double* wk = s_coef + (vv * kSlots + k) * CP;
+            double w[C];
+            if (C == 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(wk);
+                w[0] = t2.x; w[1] = t2.y;
+            } else {
 #pragma unroll
-                for (int gp = 0; gp < GP; ++gp) val[gp][k] = It_l[gp][u];
+                for (int c = 0; c < C; ++c) w[c] = wk[c];
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int kk = j0 + (k < last ? k : last);
+            for (int c = 0; c < C; ++c)
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const double w = s_coef[kk * C + c];
-#pragma unroll
-                    for (int gp = 0; gp < GP; ++gp) {
-                        const double f = fma(w, val[gp][k], acc[gp][c]);
-                        acc[gp][c] = k < cnt ? f : acc[gp][c];
-                    }
-                }
-            }
+                for (int gp = 0; gp < GP; ++gp) acc[gp][c] = fma(w[c], val[gp][k], acc[gp][c]);
+        }
+        const int cnt = s_cnt[vv];
+        if (cnt > kSlots) {                                                 // valence > 7: the rest of the row, same order
+            const int32_t j0 = s_j0[vv];
 #pragma unroll 1
-            for (int k = 8; k < cnt; ++k) {
-                const size_t u = (size_t)s_col[j0 + k] * MOF_W;
+            for (int k = kSlots; k < cnt; ++k) {
+                const double* line = It + (size_t)col[j0 + k] * MOF_W;
 #pragma unroll
                 for (int gp = 0; gp < GP; ++gp) {
-                    const double x = It_l[gp][u];
+                    const double x = line[o_cur[gp]];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) acc[gp][c] = fma(s_coef[(j0 + k) * C + c], x, acc[gp][c]);
-                }
-            }
-        } else {                                                            // a long row beyond the staged entries: same order from global
-            const int32_t* cj = col + e0 + j0;
-            const double* kj = coef + (size_t)(e0 + j0) * C;
-#pragma unroll 1
-            for (int k = 0; k < cnt; ++k) {
-                const size_t u = (size_t)cj[k] * MOF_W;
-#pragma unroll
-                for (int gp = 0; gp < GP; ++gp) {
-                    const double x = It_l[gp][u];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) acc[gp][c] = fma(kj[(size_t)k * C + c], x, acc[gp][c]);
+                    for (int c = 0; c < C; ++c) acc[gp][c] = fma(coef[(size_t)(j0 + k) * C + c], x, acc[gp][c]);
                 }
             }
         }
+        const double* Iv = It + (size_t)v * MOF_W;
 #pragma unroll
         for (int gp = 0; gp < GP; ++gp) {
             double* so = s_out + gp * 32 * LD + lane * LD + vv * OC;
@@ -166,30 +183,24 @@ __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
 #pragma unroll
                 for (int c = 0; c < OC; ++c) so[c] = acc[gp][c];
             } else {
-                // time derivative: the neighbours in time are the adjacent lanes; the lanes at the ends of the group fetch
-                // theirs from the next / previous group
                 const int64_t r = (g0 + gp) * 32 + lane;                    // row of the call
                 const int64_t t = t_first + r;                              // frame of the trial
-                const double* Iv = It + (size_t)v * MOF_W;                  // It[gg][v][ll] = Iv[gg * N * 32 + ll]
-                auto at = [&](int64_t row) { return Iv[(size_t)(row >> 5) * N * MOF_W + (row & 31)]; };
-                const double cur = It_l[gp][(size_t)v * MOF_W];
-                double prev = __shfl_up_sync(kFullMask, cur, 1), next = __shfl_down_sync(kFullMask, cur, 1);
-                if (lane == 0 && r > 0 && r < n_rows) prev = at(r - 1);
-                if (lane == 31 && r + 1 < n_rows) next = at(r + 1);
-                double td = 0.0;
-                if (r < n_rows) {
-                    const bool first = t == 0, last_t = t == T_trial - 1;
-                    double far2 = 0.0;                                      // np.gradient's one-sided ends reach two frames in
-                    if (!phase_mode && first) far2 = at(r + 2);
-                    else if (!phase_mode && last_t && r >= 2) far2 = at(r - 2);
-                    td = mof_wave_td_body(phase_mode, first, last_t, T_trial, cur, prev, next, far2, inv_dt);
+                const bool first = t == 0, last_t = t == T_trial - 1;
+                const double cur = Iv[o_cur[gp]], prev = Iv[o_prev[gp]], next = Iv[o_next[gp]];
+                double far2 = 0.0;                                          // np.gradient's one-sided ends reach two frames in
+                if (!phase_mode && r < n_rows && (first || (last_t && r >= 2))) {
+                    const int64_t row = first ? r + 2 : r - 2;
+                    far2 = Iv[(row >> 5) * group_stride + (row & 31)];
                 }
-                so[0] = mof_wave_speed_body(td, acc[gp][0], acc[gp][1 % C]);
+                so[0] = mof_wave_speed_body(mof_wave_td_body(phase_mode, first, last_t, T_trial, cur, prev, next, far2, inv_dt),
+                                            acc[gp][0], acc[gp][1 % C]);
             }
         }
     }
     __syncthreads();
-    // ---- transposed write: thread column tx walks the tile's doubles of one frame row, 8 rows per pass
+    // ---- transposed write: thread column tx walks the tile's doubles of one frame row, 8 rows per pass.  Streaming
+    // stores: the result is not read again, and a group's It lines (N x 256 bytes) should stay in L2 for the ring
+    // re-reads of the tiles that follow.
     const int tx = tid & 31, ty = tid >> 5;
 #pragma unroll
     for (int gp = 0; gp < GP; ++gp) {
@@ -201,7 +212,7 @@ __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
             for (int c = 0; c < OC; ++c) {
                 const int idx = tx + 32 * c;                                // position inside the tile's row piece
                 const int vv = idx / OC;
-                if (v0 + vv < N) out[((size_t)k * N + perm[v0 + vv]) * OC + (idx - vv * OC)] = s_out[gp * 32 * LD + fr * LD + idx];
+                if (v0 + vv < N) __stcs(out + ((size_t)k * N + perm[v0 + vv]) * OC + (idx - vv * OC), s_out[gp * 32 * LD + fr * LD + idx]);
             }
         }
     }

@@ -5,9 +5,10 @@
 For every mesh ordering asked for (0 = reference vertex order, what S5_compute_wave_v.py uses; 1 = Cuthill-McKee, the
 round-2 first version's) and both settings of groups per pass it times, with CUDA events on the launching stream after
 warm-up: the whole mof_wave_speed call (coefficient rows + transpose in + row kernel), the row kernel alone
-(mof_wave_stencil), and reports them against the algorithmic 16 N bytes per frame.  It also checks that every variant
-produces the same array bit for bit (the arithmetic per (vertex, frame) does not depend on the ordering of the tiles) and
-compares a few frames with the numpy oracle.  One JSON line on stdout.
+(mof_wave_stencil), and reports them against the algorithmic 16 N bytes per frame.  It also records whether a variant
+produces the same array bit for bit as the first one (groups per pass must not matter; another mesh ordering sums a
+row's products in another column order and may differ in the last bits) and compares a few frames with the numpy
+oracle.  One JSON line on stdout.
 """
 import argparse
 import ctypes
