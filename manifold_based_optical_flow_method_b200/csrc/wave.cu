@@ -41,9 +41,12 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kTileVerts = 32;        // vertices per CTA of wave_rows_kernel
 constexpr int kSlots = 8;            // block-row entries per vertex staged in shared memory (valence <= 7; longer rows continue in global)
 
-// (rows, N) row-major, reference vertex order -> It[g][v][32], internal order (rows padded with 0)
+// (rows, N) row-major, reference vertex order -> It[g][v][32], internal order (rows padded with 0), and the time halo
+// of every group Ih[g][v] = {row 32 g - 1, row 32 g + 32} (0 outside the rows of the call): the neighbours in time of a
+// group's first and last frame, which the row kernel would otherwise fetch as two 32-byte sectors of other groups' lines
 __global__ void __launch_bounds__(256) wave_pack_kernel(int64_t N, int64_t n_rows, const int32_t* __restrict__ perm,
-                                                        const double* __restrict__ I, int64_t ld, double* __restrict__ It) {
+                                                        const double* __restrict__ I, int64_t ld, double* __restrict__ It,
+                                                        double* __restrict__ Ih) {
     __shared__ double s[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t g = blockIdx.y;
@@ -54,11 +57,33 @@ __global__ void __launch_bounds__(256) wave_pack_kernel(int64_t N, int64_t n_row
         const int64_t k = g * 32 + fr;
         s[fr][tx] = (k < n_rows && v < N) ? __ldcs(I + k * ld + o) : 0.0;          // read once: evict first
     }
+    if (ty < 2 && v < N) {
+        const int64_t k = ty == 0 ? g * 32 - 1 : g * 32 + 32;
+        Ih[(g * N + v) * 2 + ty] = (k >= 0 && k < n_rows) ? I[k * ld + o] : 0.0;
+    }
     __syncthreads();
     for (int vv = ty; vv < 32; vv += 8) {
         const int64_t w = v0 + vv;
         if (w < N) It[mof_ix_sca(N, g, w) + tx] = s[tx][vv];
     }
+}
+
+// Loads with an L2 evict-last hint: the block rows (column indices + coefficients, 20 bytes per entry) are re-read by
+// every 32-frame group, one whole pass over the signal apart.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double ldg_keep(const double* ptr, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int32_t ldg_keep(const int32_t* ptr, uint64_t pol) {
+    int32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    return v;
 }
 
 // Coefficient rows aligned with the block pattern: cg[j][3] and / or cw[j][2] for block j = (row v, column u).
@@ -69,32 +94,39 @@ __global__ void __launch_bounds__(128) wave_coef_kernel(mof_mesh_dev M, double* 
 
 // One sparse row product per (vertex, frame).  C = 2: coefficients (alpha, beta) -> wave speed (T,N);
 // C = 3: coefficients of grad_point -> (T,N,3).  GP = 32-frame groups a CTA takes in one pass (blockIdx.y counts
-// passes): the column indices and coefficients read from shared memory serve GP groups, and a warp has GP x 8 ring
-// lines in flight per vertex.
+// passes): the column indices and coefficients read from shared memory then serve GP groups.  PIPE: the ring lines of a
+// warp's next vertex are requested before the current vertex is computed (two register sets, statically alternated).
+// KEEP: the block rows are loaded with an L2 evict-last hint.
 // The tile's block rows are staged as kSlots padded slots per vertex (thread = (row, slot), one coalesced pass): a slot
 // past the end of a row holds the vertex itself with zero coefficients, so the eight products of a vertex are straight-
 // line code with no selects; the entries of a row beyond kSlots (valence > 7) are read from global memory behind them,
 // in the same ascending column order.
-template <int C, int GP>
-__global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
+template <int C, int GP, bool PIPE, bool KEEP>
+__global__ void __launch_bounds__(256, (GP == 1 && !PIPE) ? 4 : 3) wave_rows_kernel(
     int64_t N, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
     const double* __restrict__ coef, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first, int64_t T_trial,
-    const double* __restrict__ It, double inv_dt, int phase_mode, double* __restrict__ out) {
+    const double* __restrict__ It, const double* __restrict__ Ih, double inv_dt, int phase_mode, double* __restrict__ out) {
     constexpr int OC = C == 3 ? 3 : 1;                 // doubles written per (vertex, frame)
     constexpr int LD = kTileVerts * OC + 1;            // odd row length: both sides of the transpose are conflict-free
     constexpr int CP = C == 3 ? 4 : 2;                 // doubles per staged slot: one (two) 16-byte shared loads
     __shared__ double s_out[GP * 32 * LD];
     __shared__ __align__(16) double s_coef[kTileVerts * kSlots * CP];
     __shared__ __align__(16) int32_t s_col[kTileVerts * kSlots];
+    __shared__ double s_halo[GP * kTileVerts * 2];
     __shared__ int32_t s_j0[kTileVerts], s_cnt[kTileVerts];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t v0 = (int64_t)blockIdx.x * kTileVerts;
     const int64_t g0 = (int64_t)blockIdx.y * GP;
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
-    {   // ---- stage the tile's block rows: thread = (row, slot)
+    // a pass that reaches past the last group computes its first group twice and writes it once
+    int64_t grp[GP];
+#pragma unroll
+    for (int gp = 0; gp < GP; ++gp) grp[gp] = g0 + gp < G ? g0 + gp : g0;
+    {   // ---- stage the tile's block rows: thread = (row, slot) ...
         const int row = tid >> 3, slot = tid & (kSlots - 1);
         const int64_t v = v0 + row;
         int32_t j0 = 0, cnt = 0;
+        const uint64_t keep = KEEP ? l2_evict_last_policy() : 0;
         if (v < N) { j0 = rowptr[v]; cnt = rowptr[v + 1] - j0; }
         if (slot == 0) { s_j0[row] = j0; s_cnt[row] = cnt; }
         int32_t u = v < N ? (int32_t)v : 0;
@@ -102,44 +134,43 @@ __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
 #pragma unroll
         for (int c = 0; c < C; ++c) w[c] = 0.0;
         if (slot < cnt) {
-            u = col[j0 + slot];
+            u = KEEP ? ldg_keep(col + j0 + slot, keep) : col[j0 + slot];
 #pragma unroll
-            for (int c = 0; c < C; ++c) w[c] = coef[(size_t)(j0 + slot) * C + c];
+            for (int c = 0; c < C; ++c) w[c] = KEEP ? ldg_keep(coef + (size_t)(j0 + slot) * C + c, keep) : coef[(size_t)(j0 + slot) * C + c];
         }
         s_col[tid] = u;
 #pragma unroll
         for (int c = 0; c < C; ++c) s_coef[tid * CP + c] = w[c];
+        // ... and the time halo of its vertices (C = 2 only reads it)
+        if (C == 2 && tid < GP * kTileVerts * 2) {
+            const int gp = tid / (kTileVerts * 2), idx = tid - gp * kTileVerts * 2;
+            const int64_t gg = g0 + gp < G ? g0 + gp : g0;
+            s_halo[tid] = v0 + (idx >> 1) < N ? Ih[(gg * N + v0) * 2 + idx] : 0.0;
+        }
     }
     __syncthreads();
 
-    // Offsets, relative to a vertex's first line It[0][v][0], of this lane's frame in group g0 + gp and of its neighbours
-    // in time (the previous / next frame of lane 0 / 31 lives in the neighbouring group's line).  A pass that reaches past
-    // the last group computes its first group twice and writes it once.
-    const int64_t group_stride = N * MOF_W;
-    int64_t o_cur[GP], o_prev[GP], o_next[GP];
+    const double* It_l[GP];                         // this lane's frame of group g0 + gp: vertex u at It_l[gp][u * 32]
 #pragma unroll
-    for (int gp = 0; gp < GP; ++gp) {
-        const int64_t g = g0 + gp < G ? g0 + gp : g0;
-        const int64_t r = g * 32 + lane;
-        auto off = [&](int64_t row) { return (row >> 5) * group_stride + (row & 31); };
-        o_cur[gp] = off(r);
-        o_prev[gp] = off(r > 0 ? r - 1 : r);
-        o_next[gp] = off(r + 1 < G * 32 ? r + 1 : r);
-    }
-#pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int vv = warp * 4 + i;
-        const int64_t v = v0 + vv;
-        if (v >= N) break;                                                  // warp-uniform
+    for (int gp = 0; gp < GP; ++gp) It_l[gp] = It + mof_ix_sca(N, grp[gp], 0) + lane;
+
+    // the ring lines (and, for the time derivative, the vertex's own line) of tile vertex vv
+    auto request = [&](int vv, double (&val)[GP][kSlots], double (&cur)[GP]) {
+        if (v0 + vv >= N) return;                                           // warp-uniform
         const int4 ca = *reinterpret_cast<const int4*>(s_col + vv * kSlots), cb = *reinterpret_cast<const int4*>(s_col + vv * kSlots + 4);
         const int32_t us[kSlots] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-        double val[GP][kSlots];
 #pragma unroll
-        for (int k = 0; k < kSlots; ++k) {
-            const double* line = It + (size_t)us[k] * MOF_W;
+        for (int k = 0; k < kSlots; ++k)
 #pragma unroll
-            for (int gp = 0; gp < GP; ++gp) val[gp][k] = line[o_cur[gp]];
+            for (int gp = 0; gp < GP; ++gp) val[gp][k] = It_l[gp][(size_t)us[k] * MOF_W];
+        if (C == 2) {
+#pragma unroll
+            for (int gp = 0; gp < GP; ++gp) cur[gp] = It_l[gp][(size_t)(v0 + vv) * MOF_W];
         }
+    };
+    auto compute = [&](int vv, const double (&val)[GP][kSlots], const double (&cur)[GP]) {
+        const int64_t v = v0 + vv;
+        if (v >= N) return;                                                 // warp-uniform
         double acc[GP][C];
 #pragma unroll
         for (int gp = 0; gp < GP; ++gp)
@@ -166,16 +197,15 @@ __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
             const int32_t j0 = s_j0[vv];
 #pragma unroll 1
             for (int k = kSlots; k < cnt; ++k) {
-                const double* line = It + (size_t)col[j0 + k] * MOF_W;
+                const size_t u = (size_t)col[j0 + k] * MOF_W;
 #pragma unroll
                 for (int gp = 0; gp < GP; ++gp) {
-                    const double x = line[o_cur[gp]];
+                    const double x = It_l[gp][u];
 #pragma unroll
                     for (int c = 0; c < C; ++c) acc[gp][c] = fma(coef[(size_t)(j0 + k) * C + c], x, acc[gp][c]);
                 }
             }
         }
-        const double* Iv = It + (size_t)v * MOF_W;
 #pragma unroll
         for (int gp = 0; gp < GP; ++gp) {
             double* so = s_out + gp * 32 * LD + lane * LD + vv * OC;
@@ -183,17 +213,41 @@ __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
 #pragma unroll
                 for (int c = 0; c < OC; ++c) so[c] = acc[gp][c];
             } else {
+                // time derivative: the neighbours in time are the adjacent lanes, the staged halo at the ends of the group
                 const int64_t r = (g0 + gp) * 32 + lane;                    // row of the call
                 const int64_t t = t_first + r;                              // frame of the trial
                 const bool first = t == 0, last_t = t == T_trial - 1;
-                const double cur = Iv[o_cur[gp]], prev = Iv[o_prev[gp]], next = Iv[o_next[gp]];
+                double prev = __shfl_up_sync(kFullMask, cur[gp], 1), next = __shfl_down_sync(kFullMask, cur[gp], 1);
+                if (lane == 0) prev = s_halo[(gp * kTileVerts + vv) * 2];
+                if (lane == 31) next = s_halo[(gp * kTileVerts + vv) * 2 + 1];
                 double far2 = 0.0;                                          // np.gradient's one-sided ends reach two frames in
                 if (!phase_mode && r < n_rows && (first || (last_t && r >= 2))) {
                     const int64_t row = first ? r + 2 : r - 2;
-                    far2 = Iv[(row >> 5) * group_stride + (row & 31)];
+                    far2 = It[mof_ix_sca(N, row >> 5, v) + (row & 31)];
                 }
-                so[0] = mof_wave_speed_body(mof_wave_td_body(phase_mode, first, last_t, T_trial, cur, prev, next, far2, inv_dt),
+                so[0] = mof_wave_speed_body(mof_wave_td_body(phase_mode, first, last_t, T_trial, cur[gp], prev, next, far2, inv_dt),
                                             acc[gp][0], acc[gp][1 % C]);
+            }
+        }
+    };
+    {
+        const int vb = warp * 4;                                            // a warp walks four vertices of the tile
+        double va[GP][kSlots], ca[GP];
+        if (PIPE) {
+            double vb2[GP][kSlots], cb2[GP];
+            request(vb, va, ca);
+            request(vb + 1, vb2, cb2);
+            compute(vb, va, ca);
+            request(vb + 2, va, ca);
+            compute(vb + 1, vb2, cb2);
+            request(vb + 3, vb2, cb2);
+            compute(vb + 2, va, ca);
+            compute(vb + 3, vb2, cb2);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                request(vb + i, va, ca);
+                compute(vb + i, va, ca);
             }
         }
     }
@@ -219,60 +273,67 @@ __global__ void __launch_bounds__(256, GP == 1 ? 4 : 3) wave_rows_kernel(
 }
 
 struct wave_work {
-    double *It, *cw, *cg;
+    double *It, *Ih, *cw, *cg;
     int64_t total;
 };
 
-// work = the packed signal It[G][N][32], then cw[nb][2] (wave speed asked for), then cg[nb][3] (grad_point asked for)
+// work = the packed signal It[G][N][32], its time halo Ih[G][N][2], then cw[nb][2] (wave speed asked for), then
+// cg[nb][3] (grad_point asked for)
 wave_work wave_layout(const mof_mesh_dev* mesh, int64_t n_rows, bool want_grad, bool want_wave, double* work) {
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
-    const int64_t off_cw = G * mesh->n_vertices * MOF_W;
+    const int64_t off_ih = G * mesh->n_vertices * MOF_W;
+    const int64_t off_cw = off_ih + G * mesh->n_vertices * 2;
     const int64_t off_cg = off_cw + (want_wave ? 2 * mesh->n_blocks : 0);
     wave_work w;
     w.total = off_cg + (want_grad ? 3 * mesh->n_blocks : 0);
     w.It = work;
+    w.Ih = work ? work + off_ih : nullptr;
     w.cw = work && want_wave ? work + off_cw : nullptr;
     w.cg = work && want_grad ? work + off_cg : nullptr;
     return w;
 }
 
-// groups per pass of the wave-speed kernel: 2 by default, MOF_WAVE_GROUPS=1 or mof_wave_set_groups_per_pass(1) selects
-// the one-group variant (kept for the comparison in profiles/)
-int g_wave_groups = 0;
-int wave_groups_per_pass() {
-    if (g_wave_groups == 0) {
-        const char* e = getenv("MOF_WAVE_GROUPS");
-        g_wave_groups = e && e[0] == '1' ? 1 : 2;
+// Variant of the wave-speed row kernel: 0 = one group per pass, 1 = one group per pass with the next vertex's lines
+// requested ahead, 2 = two groups per pass, 3 = 1 with L2 evict-last hints on the block rows.  MOF_WAVE_VARIANT or mof_wave_set_variant() select one (results are
+// bit-identical); the default is the fastest measured at config 5 (profiles/).
+constexpr int kWaveVariantDefault = 1;
+int g_wave_variant = -1;
+int wave_variant() {
+    if (g_wave_variant < 0) {
+        const char* e = getenv("MOF_WAVE_VARIANT");
+        g_wave_variant = e && e[0] >= '0' && e[0] <= '3' && !e[1] ? e[0] - '0' : kWaveVariantDefault;
     }
-    return g_wave_groups;
+    return g_wave_variant;
 }
 
 int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first,
                      int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, cudaStream_t st) {
     const int64_t N = mesh->n_vertices;
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
+    const dim3 grid1(mof_cdiv(N, kTileVerts), (unsigned)G), grid2(mof_cdiv(N, kTileVerts), (unsigned)((G + 1) / 2));
+#define MOF_WAVE_ARGS(coef_, out_) \
+    N, mesh->rowptr, mesh->col, mesh->perm, coef_, n_rows, out0, n_out, t_first, T_trial, w.It, w.Ih, 1.0 / dt, phase_mode, out_
     if (grad_point) {
-        wave_rows_kernel<3, 1><<<dim3(mof_cdiv(N, kTileVerts), (unsigned)G), 256, 0, st>>>(
-            N, mesh->rowptr, mesh->col, mesh->perm, w.cg, n_rows, out0, n_out, t_first, T_trial, w.It, 1.0 / dt, phase_mode, grad_point);
-        MOF_LAUNCH_CHECK("wave_rows_kernel<3,1>");
+        wave_rows_kernel<3, 1, false, false><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cg, grad_point));
+        MOF_LAUNCH_CHECK("wave_rows_kernel<3,1,0>");
     }
     if (wave) {
-        if (wave_groups_per_pass() == 2)
-            wave_rows_kernel<2, 2><<<dim3(mof_cdiv(N, kTileVerts), (unsigned)((G + 1) / 2)), 256, 0, st>>>(
-                N, mesh->rowptr, mesh->col, mesh->perm, w.cw, n_rows, out0, n_out, t_first, T_trial, w.It, 1.0 / dt, phase_mode, wave);
-        else
-            wave_rows_kernel<2, 1><<<dim3(mof_cdiv(N, kTileVerts), (unsigned)G), 256, 0, st>>>(
-                N, mesh->rowptr, mesh->col, mesh->perm, w.cw, n_rows, out0, n_out, t_first, T_trial, w.It, 1.0 / dt, phase_mode, wave);
-        MOF_LAUNCH_CHECK("wave_rows_kernel<2,*>");
+        const int variant = wave_variant();
+        if (variant == 3) wave_rows_kernel<2, 1, true, true><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
+        else if (variant == 2) wave_rows_kernel<2, 2, false, false><<<grid2, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
+        else if (variant == 1) wave_rows_kernel<2, 1, true, false><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
+        else wave_rows_kernel<2, 1, false, false><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
+        MOF_LAUNCH_CHECK("wave_rows_kernel<2,*,*>");
     }
+#undef MOF_WAVE_ARGS
     return 0;
 }
 
 }  // namespace
 
-extern "C" int mof_wave_set_groups_per_pass(int groups) {
-    MOF_REQUIRE(groups == 1 || groups == 2, "1 or 2");
-    g_wave_groups = groups;
+extern "C" int mof_wave_set_variant(int variant) {
+    MOF_REQUIRE(variant >= 0 && variant <= 3, "0 .. 3");
+    g_wave_variant = variant;
     return 0;
 }
 
@@ -307,7 +368,7 @@ extern "C" int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t 
     const wave_work w = wave_layout(mesh, n_rows, grad_point != nullptr, wave != nullptr, work);
     wave_coef_kernel<<<mof_cdiv(N, 128), 128, 0, st>>>(*mesh, w.cw, w.cg);
     MOF_LAUNCH_CHECK("wave_coef_kernel");
-    wave_pack_kernel<<<dim3(mof_cdiv(N, 32), (unsigned)G), dim3(32, 8), 0, st>>>(N, n_rows, mesh->perm, I, ld, w.It);
+    wave_pack_kernel<<<dim3(mof_cdiv(N, 32), (unsigned)G), dim3(32, 8), 0, st>>>(N, n_rows, mesh->perm, I, ld, w.It, w.Ih);
     MOF_LAUNCH_CHECK("wave_pack_kernel");
     return wave_rows_launch(mesh, w, n_rows, out0, n_out, t_first, T_trial, dt, phase_mode, grad_point, wave, st);
 }

@@ -3,10 +3,10 @@
     python profiles/wave_probe.py [--level 7] [--frames 1000] [--steps 10] [--orders 0,1]
 
 For every mesh ordering asked for (0 = reference vertex order, what S5_compute_wave_v.py uses; 1 = Cuthill-McKee, the
-round-2 first version's) and both settings of groups per pass it times, with CUDA events on the launching stream after
+round-2 first version's) and every variant of the row kernel (include/mof_b200.h: mof_wave_set_variant) it times, with CUDA events on the launching stream after
 warm-up: the whole mof_wave_speed call (coefficient rows + transpose in + row kernel), the row kernel alone
 (mof_wave_stencil), and reports them against the algorithmic 16 N bytes per frame.  It also records whether a variant
-produces the same array bit for bit as the first one (groups per pass must not matter; another mesh ordering sums a
+produces the same array bit for bit as the first one (the kernel variant must not matter; another mesh ordering sums a
 row's products in another column order and may differ in the last bits) and compares a few frames with the numpy
 oracle.  One JSON line on stdout.
 """
@@ -62,8 +62,8 @@ def main():
         ms = op.struct()
         work = torch.empty((int(lib.mof_wave_work_doubles(ctypes.byref(ms), T, 0, 1)),), dtype=torch.float64, device=dev)
         wv = torch.empty((T, N), dtype=torch.float64, device=dev)
-        for gp in (1, 2):
-            _lib.check(lib.mof_wave_set_groups_per_pass(gp))
+        for gp in (0, 1, 2, 3):
+            _lib.check(lib.mof_wave_set_variant(gp))
             wv.fill_(float("nan"))
             for _ in range(3):
                 s5.wave_speed_device(op, d, 0, T, 0, T, 1 / 512.0, True, work=work, wave_out=wv)
@@ -84,7 +84,7 @@ def main():
             else:
                 same = bool(torch.equal(torch.nan_to_num(wv, nan=0.0, posinf=1e300, neginf=-1e300),
                                         torch.nan_to_num(first, nan=0.0, posinf=1e300, neginf=-1e300)))
-            rec = {"order": order, "groups_per_pass": gp, "call_ms": call_ms, "rows_ms": rows_ms, "coef_plus_pack_ms": call_ms - rows_ms,
+            rec = {"order": order, "variant": gp, "call_ms": call_ms, "rows_ms": rows_ms, "coef_plus_pack_ms": call_ms - rows_ms,
                    "call_gbs": 16.0 * N * T / call_ms / 1e6, "rows_gbs": 16.0 * N * T / rows_ms / 1e6, "bit_identical_to_first": same}
             if peak:
                 rec["call_frac"], rec["rows_frac"] = rec["call_gbs"] / peak, rec["rows_gbs"] / peak
@@ -96,7 +96,7 @@ def main():
         got = first[:k].cpu().numpy()
         m = np.isfinite(wo)
         out["rel_l2_vs_oracle"] = float(np.linalg.norm(got[m] - wo[m]) / np.linalg.norm(wo[m]))
-    _lib.check(lib.mof_wave_set_groups_per_pass(2))
+    _lib.check(lib.mof_wave_set_variant(1))
     print(json.dumps(out))
 
 
