@@ -363,7 +363,7 @@ int mof_rbf_evaluate(int64_t n_vertices, int64_t n_centres, int64_t n_frames, co
  * sharded over GPUs (config 5): every rank passes its range plus the halo -- no collective on the data path.
  * work: device scratch of mof_wave_work_doubles(mesh, n_rows, grad_point != NULL, wave != NULL) doubles: the
  * signal in the frame-minor layout [group][internal vertex][32 frames], the two time neighbours of every group per
- * vertex, and the coefficient rows (two / three
+ * vertex, and the coefficient rows (CSR-aligned and padded to eight slots per vertex) (two / three
  * doubles per block of the mesh pattern) that turn the per-frame work into one sparse row product per vertex
  * (csrc/wave.cu); the results go straight into grad_point / wave.  The kernels work for any mesh ordering; the
  * transposes are fully coalesced when the mesh was built with reorder = 0 (perm = identity), which is what
@@ -379,11 +379,11 @@ int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int
                      int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, double* work,
                      void* stream);
 
-/* Tuning knob: variant of the wave-speed row kernel -- 0: one 32-frame group per CTA pass; 1 (default): the same with
- * the ring lines of a warp's next vertex requested before the current one is computed; 2: two groups per pass; 3: 1 with L2 evict-last hints on the
- * mesh's block rows.
- * The environment variable MOF_WAVE_VARIANT sets it at first use.  Results are bit-identical. */
+/* Tuning knob: variant of the wave-speed row kernel -- 0: one 32-frame group per CTA pass (four CTAs per SM); 1: two
+ * groups per pass; 2: one group per pass compiled for five CTAs per SM.  The environment variable MOF_WAVE_VARIANT
+ * sets it at first use; the default is the fastest measured at config 5.  Results are bit-identical. */
 int mof_wave_set_variant(int variant);
+int mof_wave_get_variant(void);
 
 /* ------------------------------------------------------------------------- *
  * On-disk formats either side of the path ("next" row 4 of SURVEY 8f), host only, multi-threaded.

@@ -30,7 +30,7 @@ EXPORTS = [
     "mof_pack_frames", "mof_assemble_batch",
     "mof_level_desc_build", "mof_spmv_batch", "mof_pcg_solve_batch", "mof_pcg_last_path", "mof_unpack_solution",
     "mof_tangent_to_xyz", "mof_vmax", "mof_singularity_flags", "mof_singularity_compact",
-    "mof_classify_singularities", "mof_winding_numbers", "mof_wave_speed", "mof_wave_work_doubles", "mof_wave_stencil", "mof_wave_set_variant", "mof_rbf_fit", "mof_rbf_evaluate", "mof_csv_write", "mof_csv_dims", "mof_csv_read",
+    "mof_classify_singularities", "mof_winding_numbers", "mof_wave_speed", "mof_wave_work_doubles", "mof_wave_stencil", "mof_wave_set_variant", "mof_wave_get_variant", "mof_rbf_fit", "mof_rbf_evaluate", "mof_csv_write", "mof_csv_dims", "mof_csv_read",
 ]
 
 
@@ -157,6 +157,8 @@ def _declare(lib):
     lib.mof_wave_work_doubles.restype = c_int64
     lib.mof_wave_set_variant.restype = c_int
     lib.mof_wave_set_variant.argtypes = [c_int]
+    lib.mof_wave_get_variant.restype = c_int
+    lib.mof_wave_get_variant.argtypes = []
     lib.mof_wave_work_doubles.argtypes = [POINTER(MeshDev), c_int64, c_int, c_int]
     lib.mof_singularity_compact.restype = c_int
     lib.mof_singularity_compact.argtypes = [c_int64, c_int64, c_int64] + [P] * 16

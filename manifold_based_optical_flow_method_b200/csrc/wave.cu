@@ -68,43 +68,37 @@ __global__ void __launch_bounds__(256) wave_pack_kernel(int64_t N, int64_t n_row
     }
 }
 
-// Loads with an L2 evict-last hint: the block rows (column indices + coefficients, 20 bytes per entry) are re-read by
-// every 32-frame group, one whole pass over the signal apart.
-__device__ __forceinline__ uint64_t l2_evict_last_policy() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ double ldg_keep(const double* ptr, uint64_t pol) {
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(ptr), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ int32_t ldg_keep(const int32_t* ptr, uint64_t pol) {
-    int32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
-    return v;
-}
-
-// Coefficient rows aligned with the block pattern: cg[j][3] and / or cw[j][2] for block j = (row v, column u).
-__global__ void __launch_bounds__(128) wave_coef_kernel(mof_mesh_dev M, double* __restrict__ cw, double* __restrict__ cg) {
+// Coefficient rows aligned with the block pattern: cg[j][3] and / or cw[j][2] for block j = (row v, column u), and the
+// same rows padded to kSlots slots per vertex for the row kernel's one-pass staging: pcol[v][8], pw[v][8][2], pg[v][8][4]
+// (a slot past the end of a row: the vertex itself, zero coefficients; entries beyond kSlots stay in the CSR arrays).
+__global__ void __launch_bounds__(128) wave_coef_kernel(mof_mesh_dev M, double* __restrict__ cw, double* __restrict__ cg,
+                                                        int32_t* __restrict__ pcol, double* __restrict__ pw, double* __restrict__ pg) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < M.n_vertices) mof_wave_coef_row_body(M, v, cw, cg);
+    if (v >= M.n_vertices) return;
+    mof_wave_coef_row_body(M, v, cw, cg);
+    const int32_t j0 = M.rowptr[v], cnt = M.rowptr[v + 1] - j0;
+    for (int k = 0; k < kSlots; ++k) {
+        const bool on = k < cnt;
+        const size_t j = (size_t)j0 + k, p = (size_t)v * kSlots + k;
+        pcol[p] = on ? M.col[j] : (int32_t)v;
+        if (pw) { pw[2 * p] = on ? cw[2 * j] : 0.0; pw[2 * p + 1] = on ? cw[2 * j + 1] : 0.0; }
+        if (pg) { pg[4 * p] = on ? cg[3 * j] : 0.0; pg[4 * p + 1] = on ? cg[3 * j + 1] : 0.0; pg[4 * p + 2] = on ? cg[3 * j + 2] : 0.0; pg[4 * p + 3] = 0.0; }
+    }
 }
 
 // One sparse row product per (vertex, frame).  C = 2: coefficients (alpha, beta) -> wave speed (T,N);
 // C = 3: coefficients of grad_point -> (T,N,3).  GP = 32-frame groups a CTA takes in one pass (blockIdx.y counts
-// passes): the column indices and coefficients read from shared memory then serve GP groups.  PIPE: the ring lines of a
-// warp's next vertex are requested before the current vertex is computed (two register sets, statically alternated).
-// KEEP: the block rows are loaded with an L2 evict-last hint.
-// The tile's block rows are staged as kSlots padded slots per vertex (thread = (row, slot), one coalesced pass): a slot
-// past the end of a row holds the vertex itself with zero coefficients, so the eight products of a vertex are straight-
-// line code with no selects; the entries of a row beyond kSlots (valence > 7) are read from global memory behind them,
-// in the same ascending column order.
-template <int C, int GP, bool PIPE, bool KEEP>
-__global__ void __launch_bounds__(256, (GP == 1 && !PIPE) ? 4 : 3) wave_rows_kernel(
+// passes): the column indices and coefficients read from shared memory then serve GP groups.  MINB: CTAs per SM the
+// kernel is compiled for.
+// The tile's block rows arrive as kSlots padded slots per vertex (wave_coef_kernel wrote them that way: thread =
+// (row, slot), one coalesced pass of 16-byte loads that depends on nothing): a slot past the end of a row holds the
+// vertex itself with zero coefficients, so the eight products of a vertex are straight-line code with no selects; the
+// entries of a row beyond kSlots (valence > 7) are read from the CSR arrays behind them, in the same ascending column
+// order.
+template <int C, int GP, int MINB>
+__global__ void __launch_bounds__(256, MINB) wave_rows_kernel(
     int64_t N, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-    const double* __restrict__ coef, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first, int64_t T_trial,
+    const double* __restrict__ coef, const int32_t* __restrict__ pcol, const double* __restrict__ pcoef, int64_t n_rows, int64_t out0, int64_t n_out, int64_t t_first, int64_t T_trial,
     const double* __restrict__ It, const double* __restrict__ Ih, double inv_dt, int phase_mode, double* __restrict__ out) {
     constexpr int OC = C == 3 ? 3 : 1;                 // doubles written per (vertex, frame)
     constexpr int LD = kTileVerts * OC + 1;            // odd row length: both sides of the transpose are conflict-free
@@ -122,25 +116,21 @@ __global__ void __launch_bounds__(256, (GP == 1 && !PIPE) ? 4 : 3) wave_rows_ker
     int64_t grp[GP];
 #pragma unroll
     for (int gp = 0; gp < GP; ++gp) grp[gp] = g0 + gp < G ? g0 + gp : g0;
-    {   // ---- stage the tile's block rows: thread = (row, slot) ...
-        const int row = tid >> 3, slot = tid & (kSlots - 1);
-        const int64_t v = v0 + row;
-        int32_t j0 = 0, cnt = 0;
-        const uint64_t keep = KEEP ? l2_evict_last_policy() : 0;
-        if (v < N) { j0 = rowptr[v]; cnt = rowptr[v + 1] - j0; }
-        if (slot == 0) { s_j0[row] = j0; s_cnt[row] = cnt; }
-        int32_t u = v < N ? (int32_t)v : 0;
-        double w[C];
+    {   // ---- stage the tile's padded block rows (thread = (row, slot), 16-byte loads, nothing depends on anything) ...
+        const size_t p = (size_t)v0 * kSlots + tid;
+        const bool on = p < (size_t)N * kSlots;
+        s_col[tid] = on ? pcol[p] : 0;
+        const double2* src = reinterpret_cast<const double2*>(pcoef + p * CP);
+        double2* dst = reinterpret_cast<double2*>(s_coef + tid * CP);
 #pragma unroll
-        for (int c = 0; c < C; ++c) w[c] = 0.0;
-        if (slot < cnt) {
-            u = KEEP ? ldg_keep(col + j0 + slot, keep) : col[j0 + slot];
-#pragma unroll
-            for (int c = 0; c < C; ++c) w[c] = KEEP ? ldg_keep(coef + (size_t)(j0 + slot) * C + c, keep) : coef[(size_t)(j0 + slot) * C + c];
+        for (int q = 0; q < CP / 2; ++q) dst[q] = on ? src[q] : make_double2(0.0, 0.0);
+        // ... the row lengths (a row longer than kSlots continues in the CSR arrays) ...
+        if (tid < kTileVerts) {
+            const int64_t v = v0 + tid;
+            const int32_t j0 = v < N ? rowptr[v] : 0;
+            s_j0[tid] = j0;
+            s_cnt[tid] = v < N ? rowptr[v + 1] - j0 : 0;
         }
-        s_col[tid] = u;
-#pragma unroll
-        for (int c = 0; c < C; ++c) s_coef[tid * CP + c] = w[c];
         // ... and the time halo of its vertices (C = 2 only reads it)
         if (C == 2 && tid < GP * kTileVerts * 2) {
             const int gp = tid / (kTileVerts * 2), idx = tid - gp * kTileVerts * 2;
@@ -148,6 +138,8 @@ __global__ void __launch_bounds__(256, (GP == 1 && !PIPE) ? 4 : 3) wave_rows_ker
             s_halo[tid] = v0 + (idx >> 1) < N ? Ih[(gg * N + v0) * 2 + idx] : 0.0;
         }
     }
+    // position of this thread's vertex column in the caller's array (transposed write below), requested early
+    const int64_t o_out = v0 + lane < N ? perm[v0 + lane] : 0;
     __syncthreads();
 
     const double* It_l[GP];                         // this lane's frame of group g0 + gp: vertex u at It_l[gp][u * 32]
@@ -233,75 +225,76 @@ __global__ void __launch_bounds__(256, (GP == 1 && !PIPE) ? 4 : 3) wave_rows_ker
     {
         const int vb = warp * 4;                                            // a warp walks four vertices of the tile
         double va[GP][kSlots], ca[GP];
-        if (PIPE) {
-            double vb2[GP][kSlots], cb2[GP];
-            request(vb, va, ca);
-            request(vb + 1, vb2, cb2);
-            compute(vb, va, ca);
-            request(vb + 2, va, ca);
-            compute(vb + 1, vb2, cb2);
-            request(vb + 3, vb2, cb2);
-            compute(vb + 2, va, ca);
-            compute(vb + 3, vb2, cb2);
-        } else {
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i) {
-                request(vb + i, va, ca);
-                compute(vb + i, va, ca);
-            }
+        for (int i = 0; i < 4; ++i) {
+            request(vb + i, va, ca);
+            compute(vb + i, va, ca);
         }
     }
     __syncthreads();
     // ---- transposed write: thread column tx walks the tile's doubles of one frame row, 8 rows per pass.  Streaming
     // stores: the result is not read again, and a group's It lines (N x 256 bytes) should stay in L2 for the ring
     // re-reads of the tiles that follow.
-    const int tx = tid & 31, ty = tid >> 5;
+    const int tx = lane, ty = warp;
 #pragma unroll
     for (int gp = 0; gp < GP; ++gp) {
         if (g0 + gp >= G) break;
+#pragma unroll
         for (int fr = ty; fr < 32; fr += 8) {
             const int64_t k = (g0 + gp) * 32 + fr - out0;
             if (k < 0 || k >= n_out) continue;
+            if (C == 2) {
+                if (v0 + tx < N) __stcs(out + (size_t)k * N + o_out, s_out[gp * 32 * LD + fr * LD + tx]);
+            } else {
 #pragma unroll
-            for (int c = 0; c < OC; ++c) {
-                const int idx = tx + 32 * c;                                // position inside the tile's row piece
-                const int vv = idx / OC;
-                if (v0 + vv < N) __stcs(out + ((size_t)k * N + perm[v0 + vv]) * OC + (idx - vv * OC), s_out[gp * 32 * LD + fr * LD + idx]);
+                for (int c = 0; c < OC; ++c) {
+                    const int idx = tx + 32 * c;                            // position inside the tile's row piece
+                    const int vv = idx / OC;
+                    if (v0 + vv < N) __stcs(out + ((size_t)k * N + perm[v0 + vv]) * OC + (idx - vv * OC), s_out[gp * 32 * LD + fr * LD + idx]);
+                }
             }
         }
     }
 }
 
 struct wave_work {
-    double *It, *Ih, *cw, *cg;
+    double *It, *Ih, *cw, *cg, *pw, *pg;
+    int32_t* pcol;
     int64_t total;
 };
 
-// work = the packed signal It[G][N][32], its time halo Ih[G][N][2], then cw[nb][2] (wave speed asked for), then
-// cg[nb][3] (grad_point asked for)
+// work = the packed signal It[G][N][32], its time halo Ih[G][N][2], the padded column indices pcol[N][8] (int32), then
+// per output asked for the CSR-aligned and the padded coefficient rows: cw[nb][2], pw[N][8][2] (wave speed),
+// cg[nb][3] (+1 pad), pg[N][8][4] (grad_point).  Every piece starts on a 16-byte boundary.
 wave_work wave_layout(const mof_mesh_dev* mesh, int64_t n_rows, bool want_grad, bool want_wave, double* work) {
-    const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
-    const int64_t off_ih = G * mesh->n_vertices * MOF_W;
-    const int64_t off_cw = off_ih + G * mesh->n_vertices * 2;
-    const int64_t off_cg = off_cw + (want_wave ? 2 * mesh->n_blocks : 0);
+    const int64_t G = (n_rows + MOF_W - 1) / MOF_W, N = mesh->n_vertices, nb = mesh->n_blocks;
+    int64_t off = 0;
+    auto take = [&](int64_t doubles, bool on) {
+        double* p = on && work ? work + off : nullptr;
+        if (on) off += (doubles + 1) & ~int64_t(1);
+        return p;
+    };
     wave_work w;
-    w.total = off_cg + (want_grad ? 3 * mesh->n_blocks : 0);
-    w.It = work;
-    w.Ih = work ? work + off_ih : nullptr;
-    w.cw = work && want_wave ? work + off_cw : nullptr;
-    w.cg = work && want_grad ? work + off_cg : nullptr;
+    w.It = take(G * N * MOF_W, true);
+    w.Ih = take(G * N * 2, true);
+    w.pcol = reinterpret_cast<int32_t*>(take(N * kSlots / 2, true));
+    w.cw = take(2 * nb, want_wave);
+    w.pw = take(N * kSlots * 2, want_wave);
+    w.cg = take(3 * nb, want_grad);
+    w.pg = take(N * kSlots * 4, want_grad);
+    w.total = off;
     return w;
 }
 
-// Variant of the wave-speed row kernel: 0 = one group per pass, 1 = one group per pass with the next vertex's lines
-// requested ahead, 2 = two groups per pass, 3 = 1 with L2 evict-last hints on the block rows.  MOF_WAVE_VARIANT or mof_wave_set_variant() select one (results are
+// Variant of the wave-speed row kernel: 0 = one 32-frame group per CTA pass, 1 = two groups per pass, 2 = one group per
+// pass compiled for five CTAs per SM.  MOF_WAVE_VARIANT or mof_wave_set_variant() select one (results are
 // bit-identical); the default is the fastest measured at config 5 (profiles/).
 constexpr int kWaveVariantDefault = 1;
 int g_wave_variant = -1;
 int wave_variant() {
     if (g_wave_variant < 0) {
         const char* e = getenv("MOF_WAVE_VARIANT");
-        g_wave_variant = e && e[0] >= '0' && e[0] <= '3' && !e[1] ? e[0] - '0' : kWaveVariantDefault;
+        g_wave_variant = e && e[0] >= '0' && e[0] <= '2' && !e[1] ? e[0] - '0' : kWaveVariantDefault;
     }
     return g_wave_variant;
 }
@@ -311,18 +304,17 @@ int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_row
     const int64_t N = mesh->n_vertices;
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
     const dim3 grid1(mof_cdiv(N, kTileVerts), (unsigned)G), grid2(mof_cdiv(N, kTileVerts), (unsigned)((G + 1) / 2));
-#define MOF_WAVE_ARGS(coef_, out_) \
-    N, mesh->rowptr, mesh->col, mesh->perm, coef_, n_rows, out0, n_out, t_first, T_trial, w.It, w.Ih, 1.0 / dt, phase_mode, out_
+#define MOF_WAVE_ARGS(coef_, pcoef_, out_) \
+    N, mesh->rowptr, mesh->col, mesh->perm, coef_, w.pcol, pcoef_, n_rows, out0, n_out, t_first, T_trial, w.It, w.Ih, 1.0 / dt, phase_mode, out_
     if (grad_point) {
-        wave_rows_kernel<3, 1, false, false><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cg, grad_point));
-        MOF_LAUNCH_CHECK("wave_rows_kernel<3,1,0>");
+        wave_rows_kernel<3, 1, 4><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cg, w.pg, grad_point));
+        MOF_LAUNCH_CHECK("wave_rows_kernel<3,1,4>");
     }
     if (wave) {
         const int variant = wave_variant();
-        if (variant == 3) wave_rows_kernel<2, 1, true, true><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
-        else if (variant == 2) wave_rows_kernel<2, 2, false, false><<<grid2, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
-        else if (variant == 1) wave_rows_kernel<2, 1, true, false><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
-        else wave_rows_kernel<2, 1, false, false><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, wave));
+        if (variant == 2) wave_rows_kernel<2, 1, 5><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
+        else if (variant == 1) wave_rows_kernel<2, 2, 3><<<grid2, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
+        else wave_rows_kernel<2, 1, 4><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
         MOF_LAUNCH_CHECK("wave_rows_kernel<2,*,*>");
     }
 #undef MOF_WAVE_ARGS
@@ -331,8 +323,10 @@ int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_row
 
 }  // namespace
 
+extern "C" int mof_wave_get_variant(void) { return wave_variant(); }
+
 extern "C" int mof_wave_set_variant(int variant) {
-    MOF_REQUIRE(variant >= 0 && variant <= 3, "0 .. 3");
+    MOF_REQUIRE(variant >= 0 && variant <= 2, "0, 1 or 2");
     g_wave_variant = variant;
     return 0;
 }
@@ -366,7 +360,7 @@ extern "C" int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t 
     MOF_REQUIRE(G <= 65535, "at most 65535 x 32 rows per call");
     cudaStream_t st = mof_stream(stream);
     const wave_work w = wave_layout(mesh, n_rows, grad_point != nullptr, wave != nullptr, work);
-    wave_coef_kernel<<<mof_cdiv(N, 128), 128, 0, st>>>(*mesh, w.cw, w.cg);
+    wave_coef_kernel<<<mof_cdiv(N, 128), 128, 0, st>>>(*mesh, w.cw, w.cg, w.pcol, w.pw, w.pg);
     MOF_LAUNCH_CHECK("wave_coef_kernel");
     wave_pack_kernel<<<dim3(mof_cdiv(N, 32), (unsigned)G), dim3(32, 8), 0, st>>>(N, n_rows, mesh->perm, I, ld, w.It, w.Ih);
     MOF_LAUNCH_CHECK("wave_pack_kernel");
