@@ -20,17 +20,22 @@
 // most on the parity cases (tests/test_wave_speed.py asserts <= 1e-12 / 1e-13).
 //
 // Layout.  The (T,N) signal is transposed once into the frame-minor layout of the solver (It[group][vertex][32 frames],
-// wave_pack_kernel).  wave_rows_kernel: a CTA owns 32 consecutive vertices of one 32-frame group; it stages the
-// column indices and coefficients of its 32 block rows in shared memory with one coalesced pass, then every warp walks
-// four vertices with lane = frame -- each ring value is one 256-byte line that 32 frames share, the time neighbours are
-// the adjacent lanes -- and the tile is transposed through shared memory so that the result is written straight into
-// the caller's (T,N[,3]) array as 256-byte (768-byte) row pieces: no frame-minor result, no transpose kernel behind it.
+// wave_pack_kernel, which also leaves every group's two time neighbours per vertex in Ih).  wave_rows_kernel: a CTA
+// owns 32 consecutive vertices of one 32-frame group; it stages the padded column indices and coefficients of its 32
+// block rows in shared memory with one coalesced pass, then every warp walks four vertices with lane = frame -- each
+// ring value is one 256-byte line that 32 frames share, the time neighbours are the adjacent lanes -- and the tile is
+// transposed through shared memory so that the result is written straight into the caller's (T,N[,3]) array as
+// 256-byte (768-byte) row pieces: no frame-minor result, no transpose kernel behind it.
 // Algorithmic HBM bytes: 8 N read + 8 N written per frame (the pack moves another 16 N); the ring re-reads are served
 // by L1 (inside the CTA's tile) and L2 (a group's It is N x 256 bytes = 42 MB at 164k vertices).
 // The wave operator keeps the mesh in REFERENCE vertex order (S5_compute_wave_v._operator: reorder = 0), which
 // makes both transposes fully coalesced; the kernels honour mesh->perm all the same.
 // A call may cover a SHARD of a trial: rows outside [out0, out0 + n_out) are halo for the time derivative, and the
 // one-sided end formulas apply at the trial's ends only (t_first, T_trial).
+// Measured at config 5 (1000 frames x 163,842 vertices, profiles/r2_wave_probe.json, r2_ncu_summary.md section 5):
+// pack 0.63 ms, row kernel 1.75 ms (round 2's first version: stencil 4.89 + transpose out 1.23 ms); the row kernel
+// issues 225 instructions and 56 L1 wavefronts per (vertex, 32 frames) and runs with the issue slots and the L1 data
+// pipe both about 60 % busy -- neither DRAM (26 % active) nor L2 limits it.
 #include <stdlib.h>
 
 #include "mof_common.cuh"
@@ -289,7 +294,7 @@ wave_work wave_layout(const mof_mesh_dev* mesh, int64_t n_rows, bool want_grad, 
 // Variant of the wave-speed row kernel: 0 = one 32-frame group per CTA pass, 1 = two groups per pass, 2 = one group per
 // pass compiled for five CTAs per SM.  MOF_WAVE_VARIANT or mof_wave_set_variant() select one (results are
 // bit-identical); the default is the fastest measured at config 5 (profiles/).
-constexpr int kWaveVariantDefault = 1;
+constexpr int kWaveVariantDefault = 2;      // 1000 frames x 163,842 vertices: 1.93 / 1.83 / 1.75 ms for variants 0 / 1 / 2
 int g_wave_variant = -1;
 int wave_variant() {
     if (g_wave_variant < 0) {
