@@ -516,7 +516,7 @@ def run_b200(args):
         n_w = 5
         variants = {}
         default_variant = int(lib5.mof_wave_get_variant())
-        for gp in (0, 2, 3, 1):                               # variants of the row kernel (include/mof_b200.h); 1 is the default and runs last
+        for gp in (0, 1, 2):                                # variants of the row kernel (include/mof_b200.h: mof_wave_set_variant)
             _lib.check(lib5.mof_wave_set_variant(gp))
             w0, w1, w2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             for _ in range(2):
@@ -531,6 +531,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             variants[gp] = (w0.elapsed_time(w1) / n_w, w1.elapsed_time(w2) / n_w)
         _lib.check(lib5.mof_wave_set_variant(default_variant))
+        s5.wave_speed_device(op5, ph, 0, T, 0, T, 1.0 / SF, True, work=work, wave_out=wv)     # wv: the default variant's result
         call_ms, rows_ms = variants[default_variant]
         call_gbs = 16.0 * N * T / (call_ms * 1e-3) / 1e9
         rows_gbs = 16.0 * N * T / (rows_ms * 1e-3) / 1e9
