@@ -380,7 +380,8 @@ int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int
                      void* stream);
 
 /* Tuning knob: variant of the wave-speed row kernel -- 0: one 32-frame group per CTA pass (four CTAs per SM); 1: two
- * groups per pass; 2: one group per pass compiled for five CTAs per SM.  The environment variable MOF_WAVE_VARIANT
+ * groups per pass (three CTAs per SM); 2: one group per pass compiled for five CTAs per SM; 3: two groups per pass
+ * compiled for four CTAs per SM.  The environment variable MOF_WAVE_VARIANT
  * sets it at first use; the default is the fastest measured at config 5.  Results are bit-identical. */
 int mof_wave_set_variant(int variant);
 int mof_wave_get_variant(void);

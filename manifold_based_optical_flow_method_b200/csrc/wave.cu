@@ -292,14 +292,14 @@ wave_work wave_layout(const mof_mesh_dev* mesh, int64_t n_rows, bool want_grad, 
 }
 
 // Variant of the wave-speed row kernel: 0 = one 32-frame group per CTA pass, 1 = two groups per pass, 2 = one group per
-// pass compiled for five CTAs per SM.  MOF_WAVE_VARIANT or mof_wave_set_variant() select one (results are
+// pass compiled for five CTAs per SM, 3 = two groups per pass compiled for four CTAs per SM.  MOF_WAVE_VARIANT or mof_wave_set_variant() select one (results are
 // bit-identical); the default is the fastest measured at config 5 (profiles/).
 constexpr int kWaveVariantDefault = 2;      // 1000 frames x 163,842 vertices: 1.93 / 1.83 / 1.75 ms for variants 0 / 1 / 2
 int g_wave_variant = -1;
 int wave_variant() {
     if (g_wave_variant < 0) {
         const char* e = getenv("MOF_WAVE_VARIANT");
-        g_wave_variant = e && e[0] >= '0' && e[0] <= '2' && !e[1] ? e[0] - '0' : kWaveVariantDefault;
+        g_wave_variant = e && e[0] >= '0' && e[0] <= '3' && !e[1] ? e[0] - '0' : kWaveVariantDefault;
     }
     return g_wave_variant;
 }
@@ -317,7 +317,8 @@ int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_row
     }
     if (wave) {
         const int variant = wave_variant();
-        if (variant == 2) wave_rows_kernel<2, 1, 5><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
+        if (variant == 3) wave_rows_kernel<2, 2, 4><<<grid2, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
+        else if (variant == 2) wave_rows_kernel<2, 1, 5><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
         else if (variant == 1) wave_rows_kernel<2, 2, 3><<<grid2, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
         else wave_rows_kernel<2, 1, 4><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
         MOF_LAUNCH_CHECK("wave_rows_kernel<2,*,*>");
@@ -331,7 +332,7 @@ int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_row
 extern "C" int mof_wave_get_variant(void) { return wave_variant(); }
 
 extern "C" int mof_wave_set_variant(int variant) {
-    MOF_REQUIRE(variant >= 0 && variant <= 2, "0, 1 or 2");
+    MOF_REQUIRE(variant >= 0 && variant <= 3, "0 .. 3");
     g_wave_variant = variant;
     return 0;
 }

@@ -64,7 +64,7 @@ def main():
         ms = op.struct()
         work = torch.empty((int(lib.mof_wave_work_doubles(ctypes.byref(ms), T, 0, 1)),), dtype=torch.float64, device=dev)
         wv = torch.empty((T, N), dtype=torch.float64, device=dev)
-        for gp in (0, 1, 2):
+        for gp in (0, 1, 2, 3):
             _lib.check(lib.mof_wave_set_variant(gp))
             wv.fill_(float("nan"))
             for _ in range(3):
