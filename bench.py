@@ -516,7 +516,7 @@ def run_b200(args):
         n_w = 5
         variants = {}
         default_variant = int(lib5.mof_wave_get_variant())
-        for gp in (0, 1, 2, 3):                                # variants of the row kernel (include/mof_b200.h: mof_wave_set_variant)
+        for gp in range(7):                                   # variants of the row kernel (include/mof_b200.h: mof_wave_set_variant)
             _lib.check(lib5.mof_wave_set_variant(gp))
             w0, w1, w2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             for _ in range(2):

@@ -379,10 +379,9 @@ int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_t out0, int
                      int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, double* work,
                      void* stream);
 
-/* Tuning knob: variant of the wave-speed row kernel -- 0: one 32-frame group per CTA pass (four CTAs per SM); 1: two
- * groups per pass (three CTAs per SM); 2: one group per pass compiled for five CTAs per SM; 3: two groups per pass
- * compiled for four CTAs per SM.  The environment variable MOF_WAVE_VARIANT
- * sets it at first use; the default is the fastest measured at config 5.  Results are bit-identical. */
+/* Tuning knob: variant of the wave-speed row kernel = (32-frame groups per CTA pass, CTAs per SM compiled for):
+ * 0: (1,4)  1: (2,3)  2: (1,5)  3: (2,4)  4: (2,5)  5: (3,4)  6: (4,3).  The environment variable MOF_WAVE_VARIANT sets
+ * it at first use; the default is the fastest measured at config 5.  Results are bit-identical. */
 int mof_wave_set_variant(int variant);
 int mof_wave_get_variant(void);
 

@@ -291,15 +291,18 @@ wave_work wave_layout(const mof_mesh_dev* mesh, int64_t n_rows, bool want_grad, 
     return w;
 }
 
-// Variant of the wave-speed row kernel: 0 = one 32-frame group per CTA pass, 1 = two groups per pass, 2 = one group per
-// pass compiled for five CTAs per SM, 3 = two groups per pass compiled for four CTAs per SM.  MOF_WAVE_VARIANT or mof_wave_set_variant() select one (results are
-// bit-identical); the default is the fastest measured at config 5 (profiles/).
-constexpr int kWaveVariantDefault = 2;      // 1000 frames x 163,842 vertices: 1.93 / 1.83 / 1.75 ms for variants 0 / 1 / 2
+// Variants of the wave-speed row kernel = (32-frame groups per CTA pass, CTAs per SM it is compiled for):
+//   0: (1, 4)   1: (2, 3)   2: (1, 5)   3: (2, 4)   4: (2, 5)   5: (3, 4)   6: (4, 3)
+// More groups per pass: fewer instructions and shared-memory reads per (vertex, frame), more ring lines in flight per warp,
+// a larger L2 working set; more CTAs per SM: fewer registers per thread.  MOF_WAVE_VARIANT or mof_wave_set_variant()
+// select one (results are bit-identical); the default is the fastest measured at config 5 (profiles/r2_wave_probe.json).
+constexpr int kWaveVariants = 7;
+constexpr int kWaveVariantDefault = 3;
 int g_wave_variant = -1;
 int wave_variant() {
     if (g_wave_variant < 0) {
         const char* e = getenv("MOF_WAVE_VARIANT");
-        g_wave_variant = e && e[0] >= '0' && e[0] <= '3' && !e[1] ? e[0] - '0' : kWaveVariantDefault;
+        g_wave_variant = e && e[0] >= '0' && e[0] < '0' + kWaveVariants && !e[1] ? e[0] - '0' : kWaveVariantDefault;
     }
     return g_wave_variant;
 }
@@ -308,19 +311,23 @@ int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_row
                      int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, cudaStream_t st) {
     const int64_t N = mesh->n_vertices;
     const int64_t G = (n_rows + MOF_W - 1) / MOF_W;
-    const dim3 grid1(mof_cdiv(N, kTileVerts), (unsigned)G), grid2(mof_cdiv(N, kTileVerts), (unsigned)((G + 1) / 2));
+    auto grid = [&](int gp) { return dim3(mof_cdiv(N, kTileVerts), (unsigned)((G + gp - 1) / gp)); };
 #define MOF_WAVE_ARGS(coef_, pcoef_, out_) \
     N, mesh->rowptr, mesh->col, mesh->perm, coef_, w.pcol, pcoef_, n_rows, out0, n_out, t_first, T_trial, w.It, w.Ih, 1.0 / dt, phase_mode, out_
     if (grad_point) {
-        wave_rows_kernel<3, 1, 4><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cg, w.pg, grad_point));
+        wave_rows_kernel<3, 1, 4><<<grid(1), 256, 0, st>>>(MOF_WAVE_ARGS(w.cg, w.pg, grad_point));
         MOF_LAUNCH_CHECK("wave_rows_kernel<3,1,4>");
     }
     if (wave) {
-        const int variant = wave_variant();
-        if (variant == 3) wave_rows_kernel<2, 2, 4><<<grid2, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
-        else if (variant == 2) wave_rows_kernel<2, 1, 5><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
-        else if (variant == 1) wave_rows_kernel<2, 2, 3><<<grid2, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
-        else wave_rows_kernel<2, 1, 4><<<grid1, 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave));
+        switch (wave_variant()) {
+        case 0: wave_rows_kernel<2, 1, 4><<<grid(1), 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave)); break;
+        case 1: wave_rows_kernel<2, 2, 3><<<grid(2), 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave)); break;
+        case 2: wave_rows_kernel<2, 1, 5><<<grid(1), 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave)); break;
+        case 4: wave_rows_kernel<2, 2, 5><<<grid(2), 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave)); break;
+        case 5: wave_rows_kernel<2, 3, 4><<<grid(3), 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave)); break;
+        case 6: wave_rows_kernel<2, 4, 3><<<grid(4), 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave)); break;
+        default: wave_rows_kernel<2, 2, 4><<<grid(2), 256, 0, st>>>(MOF_WAVE_ARGS(w.cw, w.pw, wave)); break;
+        }
         MOF_LAUNCH_CHECK("wave_rows_kernel<2,*,*>");
     }
 #undef MOF_WAVE_ARGS
@@ -332,7 +339,7 @@ int wave_rows_launch(const mof_mesh_dev* mesh, const wave_work& w, int64_t n_row
 extern "C" int mof_wave_get_variant(void) { return wave_variant(); }
 
 extern "C" int mof_wave_set_variant(int variant) {
-    MOF_REQUIRE(variant >= 0 && variant <= 3, "0 .. 3");
+    MOF_REQUIRE(variant >= 0 && variant < kWaveVariants, "0 .. 6");
     g_wave_variant = variant;
     return 0;
 }

@@ -28,6 +28,49 @@ from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5  # n
 from manifold_based_optical_flow_method_b200.mesh import MeshOperator  # noqa: E402
 
 
+def edge_checks(lib, variants):
+    """The parity cases of tests/test_wave_speed.py under every kernel variant, in this process: the golden of the
+    unmodified S5 on the open patch (irregular valence up to 8: rows longer than the staged slots), and ragged shards
+    of a 70-frame trial (three 32-frame groups, the last one partial) against the whole trial, bit for bit."""
+    from manifold_based_optical_flow_method_b200.distributed import shard_range
+    from oracle import mof_oracle
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "s5_patch7.npz")))
+    dt = float(g["dt"])
+    surf = synthetic.SurfaceMesh(g["coordinates"], g["triangles"], g["normals"], g["areas"])
+    coords, tris, normals, areas = synthetic.pial_like(3)
+    e3 = mof_oracle.orthonormal_basis(normals)
+    T = 70
+    t_k = synthetic.time_axis(T, 512.0)
+    data = {True: synthetic.wrapped_phase(coords, t_k, seed=2, omega=300.0), False: synthetic.travelling_wave(coords, t_k, seed=2)}
+
+    def rel(a, b):
+        m = np.isfinite(b)
+        return float(np.linalg.norm(a[m] - b[m]) / np.linalg.norm(b[m]))
+    res = {}
+    for variant in variants:
+        _lib.check(lib.mof_wave_set_variant(variant))
+        r = {"golden_phase": rel(s5.wave_velocity_phase(surf, g["phases"], dt, len(g["phases"]), g["e"]), g["wave_velocity_phase"]),
+             "golden_amplitude": rel(s5.wave_velocity_amplitude(surf, g["potentials"], dt, len(g["potentials"]), g["e"]),
+                                     g["wave_velocity_amplitude"])}
+        op = s5._operator(coords, tris, areas, e3)
+        ok = True
+        for phase in (True, False):
+            d = torch.from_numpy(np.ascontiguousarray(data[phase])).to(op.device)
+            _, whole = s5.wave_speed_device(op, d, 0, T, 0, T, 1 / 512.0, phase)
+            r["oracle_" + ("phase" if phase else "amplitude")] = rel(
+                whole.cpu().numpy(), mof_oracle.wave_velocity(coords, tris, areas, data[phase], 1 / 512.0, e3, phase=phase))
+            for world in (2, 3, 8):
+                for rank in range(world):
+                    k0, k1 = shard_range(T, world, rank)
+                    a, b = s5.halo_rows(k0, k1, T, phase)
+                    _, part = s5.wave_speed_device(op, d[a:b], a, T, k0 - a, k1 - k0, 1 / 512.0, phase)
+                    ok = ok and bool(torch.equal(part, whole[k0:k1]))
+        r["shards_bit_identical"] = ok
+        r["pass"] = bool(ok and max(v for k, v in r.items() if k.startswith(("golden", "oracle"))) <= 1e-12)
+        res[str(variant)] = r
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=7)
@@ -35,6 +78,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--orders", default="0,1")
     ap.add_argument("--oracle-frames", type=int, default=4)
+    ap.add_argument("--edge-checks", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.load()
@@ -64,7 +108,7 @@ def main():
         ms = op.struct()
         work = torch.empty((int(lib.mof_wave_work_doubles(ctypes.byref(ms), T, 0, 1)),), dtype=torch.float64, device=dev)
         wv = torch.empty((T, N), dtype=torch.float64, device=dev)
-        for gp in (0, 1, 2, 3):
+        for gp in range(7):
             _lib.check(lib.mof_wave_set_variant(gp))
             wv.fill_(float("nan"))
             for _ in range(3):
@@ -98,6 +142,8 @@ def main():
         got = first[:k].cpu().numpy()
         m = np.isfinite(wo)
         out["rel_l2_vs_oracle"] = float(np.linalg.norm(got[m] - wo[m]) / np.linalg.norm(wo[m]))
+    if args.edge_checks:
+        out["edge_checks"] = edge_checks(lib, range(7))
     _lib.check(lib.mof_wave_set_variant(default_variant))
     print(json.dumps(out))
 
