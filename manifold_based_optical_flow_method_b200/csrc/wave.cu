@@ -33,9 +33,10 @@
 // A call may cover a SHARD of a trial: rows outside [out0, out0 + n_out) are halo for the time derivative, and the
 // one-sided end formulas apply at the trial's ends only (t_first, T_trial).
 // Measured at config 5 (1000 frames x 163,842 vertices, profiles/r2_wave_probe.json, r2_ncu_summary.md section 5):
-// pack 0.63 ms, row kernel 1.75 ms (round 2's first version: stencil 4.89 + transpose out 1.23 ms); the row kernel
-// issues 225 instructions and 56 L1 wavefronts per (vertex, 32 frames) and runs with the issue slots and the L1 data
-// pipe both about 60 % busy -- neither DRAM (26 % active) nor L2 limits it.
+// pack 0.63 ms, row kernel 1.63 ms (round 2's first version: stencil 4.89 + transpose out 1.23 ms); with one group per
+// pass the row kernel issues 238 instructions and 56 L1 wavefronts per (vertex, 32 frames) and runs with the issue slots
+// and the L1 data pipe both about 60 % busy -- neither DRAM (26 % active) nor L2 limits it; three groups per pass
+// (the default) share the shared-memory reads of the block rows and shave another 7 %.
 #include <stdlib.h>
 
 #include "mof_common.cuh"
@@ -297,7 +298,7 @@ wave_work wave_layout(const mof_mesh_dev* mesh, int64_t n_rows, bool want_grad, 
 // a larger L2 working set; more CTAs per SM: fewer registers per thread.  MOF_WAVE_VARIANT or mof_wave_set_variant()
 // select one (results are bit-identical); the default is the fastest measured at config 5 (profiles/r2_wave_probe.json).
 constexpr int kWaveVariants = 7;
-constexpr int kWaveVariantDefault = 3;
+constexpr int kWaveVariantDefault = 5;      // row kernel, 1000 frames x 163,842 vertices: 1.93 1.83 1.75 1.67 1.76 1.63 1.66 ms for variants 0 .. 6
 int g_wave_variant = -1;
 int wave_variant() {
     if (g_wave_variant < 0) {
