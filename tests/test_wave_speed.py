@@ -205,3 +205,42 @@ def test_angle_subtract_body_is_numpy_mod():
     m = np.where((d >= 0) & (d < two_pi), d, np.where((d < 0) & (d > -two_pi), d + two_pi,
                  np.where((d >= two_pi) & (d < 2 * two_pi), d - two_pi, np.mod(d, two_pi))))
     assert np.array_equal(m - np.pi, mof_oracle.angle_subtract(a, b))
+
+
+def test_wave_c_abi_argument_errors():
+    """mof_wave_speed / mof_wave_stencil / mof_wave_set_variant validate their arguments before anything is launched
+    (CPU: the calls return an error code and a message, no device is touched)."""
+    import ctypes
+    from manifold_based_optical_flow_method_b200 import _lib
+    lib = _lib.load()
+    ms = _lib.MeshDev()
+    ms.n_vertices, ms.n_faces, ms.n_blocks, ms.n_contrib = 10, 16, 58, 144
+    P = ctypes.c_void_p
+    buf = (ctypes.c_double * 16)()
+    ptr = ctypes.cast(buf, P)
+    M = ctypes.byref(ms)
+    # scratch size: the packed signal (G N 32), its time halo (G N 2), the padded columns (N 8 int32) and, per output,
+    # CSR-aligned + padded coefficient rows
+    G, N, nb = 2, 10, 58
+    base = G * N * 32 + G * N * 2 + N * 8 // 2
+    assert lib.mof_wave_work_doubles(M, 40, 0, 1) == base + 2 * nb + N * 8 * 2
+    assert lib.mof_wave_work_doubles(M, 40, 1, 0) == base + 3 * nb + N * 8 * 4
+    assert lib.mof_wave_work_doubles(None, 40, 0, 1) == -1
+
+    def speed(n_rows=8, out0=0, n_out=8, t_first=0, T=8, I=ptr, ld=10, dt=0.5, phase=1, grad=None, wave=ptr, work=ptr):
+        return lib.mof_wave_speed(M, n_rows, out0, n_out, t_first, T, I, ld, dt, phase, grad, wave, work, None)
+    for kw, msg in ((dict(I=None), "bad arguments"), (dict(ld=9), "bad arguments"), (dict(dt=0.0), "bad arguments"),
+                    (dict(wave=None), "nothing to compute"), (dict(out0=4, n_out=5), "output rows outside"),
+                    (dict(t_first=1), "rows outside the trial"), (dict(phase=0, T=2, n_rows=2, n_out=2), "at least 3 frames"),
+                    (dict(n_rows=4, n_out=4, t_first=2, T=8), "lack the time-derivative halo"),
+                    (dict(phase=0, n_rows=5, out0=0, n_out=5, t_first=3, T=8), "lack the time-derivative halo")):
+        assert speed(**kw) == -1, kw
+        assert msg in _lib.last_error(), (kw, _lib.last_error())
+    assert speed(n_out=0) == 0                       # nothing asked for: nothing launched
+    assert lib.mof_wave_stencil(M, 0, 0, 0, 0, 8, 0.5, 1, None, ptr, ptr, None) == -1
+    assert lib.mof_wave_stencil(M, 8, 0, 8, 0, 8, 0.5, 1, None, None, ptr, None) == -1
+    keep = lib.mof_wave_get_variant()
+    assert 0 <= keep <= 6
+    assert lib.mof_wave_set_variant(7) == -1 and lib.mof_wave_set_variant(-1) == -1
+    assert lib.mof_wave_set_variant(0) == 0 and lib.mof_wave_get_variant() == 0
+    assert lib.mof_wave_set_variant(keep) == 0
