@@ -361,7 +361,7 @@ int mof_rbf_evaluate(int64_t n_vertices, int64_t n_centres, int64_t n_frames, co
  * the other rows are halo (one frame either side; two at a trial end in amplitude mode, where np.gradient's
  * one-sided formula applies).  Whole trial on one GPU: n_rows = n_out = T_trial, out0 = t_first = 0.  Frames
  * sharded over GPUs (config 5): every rank passes its range plus the halo -- no collective on the data path.
- * work: device scratch of mof_wave_work_doubles(mesh, n_rows, grad_point != NULL, wave != NULL) doubles: the
+ * work: 16-byte aligned device scratch of mof_wave_work_doubles(mesh, n_rows, grad_point != NULL, wave != NULL) doubles: the
  * signal in the frame-minor layout [group][internal vertex][32 frames], the two time neighbours of every group per
  * vertex, and the coefficient rows (CSR-aligned and padded to eight slots per vertex) (two / three
  * doubles per block of the mesh pattern) that turn the per-frame work into one sparse row product per vertex

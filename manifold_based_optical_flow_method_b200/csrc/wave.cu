@@ -355,6 +355,7 @@ extern "C" int mof_wave_speed(const mof_mesh_dev* mesh, int64_t n_rows, int64_t 
                               double* wave, double* work, void* stream) {
     MOF_REQUIRE(mesh && I && work && n_rows >= 0 && ld >= mesh->n_vertices && dt != 0.0, "bad arguments");
     MOF_REQUIRE(grad_point || wave, "nothing to compute");
+    MOF_REQUIRE((reinterpret_cast<uintptr_t>(work) & 15) == 0, "work must be 16-byte aligned");
     MOF_REQUIRE(out0 >= 0 && n_out >= 0 && out0 + n_out <= n_rows, "output rows outside the rows passed in");
     MOF_REQUIRE(t_first >= 0 && t_first + n_rows <= T_trial, "rows outside the trial");
     MOF_REQUIRE(phase_mode || !wave || T_trial >= 3, "np.gradient(edge_order=2) needs at least 3 frames");
@@ -387,6 +388,7 @@ extern "C" int mof_wave_stencil(const mof_mesh_dev* mesh, int64_t n_rows, int64_
                                 int64_t T_trial, double dt, int phase_mode, double* grad_point, double* wave, double* work,
                                 void* stream) {
     MOF_REQUIRE(mesh && work && n_rows > 0 && (grad_point || wave) && dt != 0.0, "bad arguments");
+    MOF_REQUIRE((reinterpret_cast<uintptr_t>(work) & 15) == 0, "work must be 16-byte aligned");
     MOF_REQUIRE(out0 >= 0 && n_out >= 0 && out0 + n_out <= n_rows, "output rows outside the rows passed in");
     MOF_REQUIRE((n_rows + MOF_W - 1) / MOF_W <= 65535, "at most 65535 x 32 rows per call");
     const wave_work w = wave_layout(mesh, n_rows, grad_point != nullptr, wave != nullptr, work);

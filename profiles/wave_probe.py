@@ -124,14 +124,17 @@ def main():
             e2.record()
             torch.cuda.synchronize()
             call_ms, rows_ms = e0.elapsed_time(e1) / args.steps, e1.elapsed_time(e2) / args.steps
+            rel_to_first = 0.0
             if first is None:
                 first = wv.clone()
                 same = True
             else:
+                fin = torch.isfinite(first) & torch.isfinite(wv)
+                rel_to_first = float(torch.linalg.vector_norm(wv[fin] - first[fin]) / torch.linalg.vector_norm(first[fin]))
                 same = bool(torch.equal(torch.nan_to_num(wv, nan=0.0, posinf=1e300, neginf=-1e300),
                                         torch.nan_to_num(first, nan=0.0, posinf=1e300, neginf=-1e300)))
             rec = {"order": order, "variant": gp, "call_ms": call_ms, "rows_ms": rows_ms, "coef_plus_pack_ms": call_ms - rows_ms,
-                   "call_gbs": 16.0 * N * T / call_ms / 1e6, "rows_gbs": 16.0 * N * T / rows_ms / 1e6, "bit_identical_to_first": same}
+                   "call_gbs": 16.0 * N * T / call_ms / 1e6, "rows_gbs": 16.0 * N * T / rows_ms / 1e6, "bit_identical_to_first": same, "rel_l2_to_first": rel_to_first}
             if peak:
                 rec["call_frac"], rec["rows_frac"] = rec["call_gbs"] / peak, rec["rows_gbs"] / peak
             out["variants"].append(rec)

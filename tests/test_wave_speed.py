@@ -236,6 +236,7 @@ def test_wave_c_abi_argument_errors():
                     (dict(phase=0, n_rows=5, out0=0, n_out=5, t_first=3, T=8), "lack the time-derivative halo")):
         assert speed(**kw) == -1, kw
         assert msg in _lib.last_error(), (kw, _lib.last_error())
+    assert speed(work=ctypes.c_void_p(ptr.value + 8)) == -1 and "16-byte aligned" in _lib.last_error()
     assert speed(n_out=0) == 0                       # nothing asked for: nothing launched
     assert lib.mof_wave_stencil(M, 0, 0, 0, 0, 8, 0.5, 1, None, ptr, ptr, None) == -1
     assert lib.mof_wave_stencil(M, 8, 0, 8, 0, 8, 0.5, 1, None, None, ptr, None) == -1
