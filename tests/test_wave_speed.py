@@ -245,3 +245,25 @@ def test_wave_c_abi_argument_errors():
     assert lib.mof_wave_set_variant(7) == -1 and lib.mof_wave_set_variant(-1) == -1
     assert lib.mof_wave_set_variant(0) == 0 and lib.mof_wave_get_variant() == 0
     assert lib.mof_wave_set_variant(keep) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reorder", [1, 3])
+def test_wave_speed_on_a_renumbered_mesh(reorder):
+    """The C ABI takes any mesh handle: with a renumbered mesh (Cuthill-McKee, level-scheduled) the transposes gather /
+    scatter through mesh->perm and a row's products are summed in another column order -- same result to rounding."""
+    import torch
+    from manifold_based_optical_flow_method_b200 import S5_compute_wave_v as s5
+    from manifold_based_optical_flow_method_b200.mesh import MeshOperator
+    coords, tris, normals, areas = synthetic.pial_like(3)
+    T, SF = 40, 512.0
+    t_k = synthetic.time_axis(T, SF)
+    e = mof_oracle.orthonormal_basis(normals)
+    op = MeshOperator(coords, normals, tris, areas, reorder=reorder)
+    op.use_geometry(None, e, None, areas)
+    for phase in (True, False):
+        data = synthetic.wrapped_phase(coords, t_k, seed=5, omega=300.0) if phase else synthetic.travelling_wave(coords, t_k, seed=5)
+        d = torch.from_numpy(np.ascontiguousarray(data)).to(op.device)
+        grad, wave = s5.wave_speed_device(op, d, 0, T, 0, T, 1 / SF, phase, want_grad=True)
+        assert rel_l2(wave.cpu().numpy(), mof_oracle.wave_velocity(coords, tris, areas, data, 1 / SF, e, phase=phase)) <= 1e-12
+        assert rel_l2(grad.cpu().numpy(), mof_oracle.grad_M_I(coords, tris, data, areas)) <= 1e-13
